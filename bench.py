@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- projected-view renders/s (fwd+bwd, 128^2) of the fused depth-map render, with its HBM roofline and the
+reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--images I] [--views P] [--size S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one pass of the hot path (chain C of SURVEY.md 8d: normal -> shading -> warp_canon_depth ->
+get_inv_warped_2d_grid -> grid_sample -> clamp, forward AND backward to depth/albedo/view/light) over one batch of
+synthetic input: `--images` images x `--views` pseudo-views at side `--size` per GPU.  Default = BASELINE.json
+configs[1] (GAN2Shape cat config: 128^2, 16 pseudo-views per image) in its batched form, 256 images per GPU, so the
+per-step working set (4.5 GB algorithmic) is far larger than the 126 MB L2 (timing rule: inputs larger than L2).
+
+Keys of the JSON line: see the round prompt; `value` = renders/s with inputs resident in HBM (CUDA events, max over
+ranks); `e2e` = the same through the public API with pinned HOST inputs copied in and the gradients + loss copied out
+every step; `roofline` = live CUDA-event timing of every kernel of the step (g2s_profile_*), algorithmic bytes from
+SURVEY.md 8(d); `cpu_baseline` = the oracle (reference renderer.py on torch-CPU + the C restatement of the external
+rasteriser's brute-force loop) on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFGS = {"rot_center_depth": 1.0, "fov": 10, "tex_cube_size": 2}
+MIN_DEPTH, MAX_DEPTH = 0.9, 1.1
+METRIC = "projected-view renders/sec (fwd+bwd)"
+UNIT = "renders/s"
+
+
+def alg_bytes_per_render(S, P):
+    """fwd 32 S^2 + 16 S^2/P, bwd 32 S^2 + 32 S^2/P."""
+    return 64.0 * S * S + 48.0 * S * S / P
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(S, views, steps, warmup, threads):
+    """The reference's CPU implementation of the path = the oracle: reference renderer.py arithmetic on torch-CPU plus
+    the faithful O((2S)^2 * 4(S-1)^2) rasteriser loop (oracle/nr_raster.c, OpenMP).  Returns renders/s over `steps`
+    steps of `views` views of one image (fwd+bwd)."""
+    import torch
+    import torch.nn.functional as F
+    import g2s_b200
+    from g2s_b200 import synthetic
+    from oracle import nr_port, renderer_oracle as ro
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    nr_port.MODE["raster"] = "brute"
+    case = synthetic.make_case(S, views, seed=1234)
+    orc = ro.OracleRenderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH)
+
+    def step():
+        depth = case["depth"].clone().requires_grad_(True)
+        albedo = case["albedo"].clone().requires_grad_(True)
+        view = case["view"].clone().requires_grad_(True)
+        light = case["light"].clone().requires_grad_(True)
+        out = orc.render_chain(depth, albedo, view, light)
+        (out["recon_im"] * case["cotangent"]).sum().backward()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    nr_port.MODE["raster"] = "culled"
+    return views * steps / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S, P = args.size, args.views
+    threads = os.cpu_count() or 1
+    views = 2 if S <= 128 else 1
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    value, dt = cpu_reference_run(S, views, steps, warmup, threads)
+    sample = "%d step(s) x %d view(s) of one %dx%d image, fwd+bwd, brute-force face loop" % (steps, views, S, S)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, per_gpu_images=args.images),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, per_gpu_images):
+    return {"workload": "GAN2Shape cat config (BASELINE.json configs[1]): %dx%d depth, %d projected pseudo-views per "
+                        "image, fwd+bwd; batched form, %d images per GPU per step" % (args.size, args.size, args.views,
+                                                                                      per_gpu_images),
+            "image_size": args.size, "views_per_image": args.views, "images_per_gpu": per_gpu_images,
+            "align_corners": False,
+            "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB); no explicit flush",
+            "cotangent": "device-resident fixed random d(loss)/d(recon_im) (stands in for the on-device losses of "
+                         "model.py:274-278)"}
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import g2s_b200
+    from g2s_b200 import synthetic, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    S, P, N = args.size, args.views, args.images
+    B = N * P
+    case = synthetic.make_case(S, P, seed=1234 + rank, n_images=N)
+    ren = g2s_b200.Renderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH, device=dev)
+    host = {k: case[k].pin_memory() for k in ("depth", "albedo", "view", "light")}
+    cot = case["cotangent"].to(dev)
+    d_in = {k: v.to(dev) for k, v in host.items()}
+    loss_buf = torch.zeros((), device=dev)
+
+    def step_device():
+        depth = d_in["depth"].requires_grad_(True)
+        albedo = d_in["albedo"].requires_grad_(True)
+        view = d_in["view"].requires_grad_(True)
+        light = d_in["light"].requires_grad_(True)
+        for tns in (depth, albedo, view, light):
+            tns.grad = None
+        recon_im, recon_depth, fidx = ren.render_chain(depth, albedo, view, light, views_per_image=P)
+        loss = (recon_im * cot).sum()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(loss.detach(), op=dist.ReduceOp.SUM)   # the only exchange: the scalar loss
+        return loss
+
+    h_out = {"depth": torch.empty(N, S, S).pin_memory(), "albedo": torch.empty(N, 3, S, S).pin_memory(),
+             "view": torch.empty(B, 6).pin_memory(), "light": torch.empty(B, 4).pin_memory(),
+             "loss": torch.empty(()).pin_memory()}
+
+    def step_e2e():
+        depth = host["depth"].to(dev, non_blocking=True).requires_grad_(True)
+        albedo = host["albedo"].to(dev, non_blocking=True).requires_grad_(True)
+        view = host["view"].to(dev, non_blocking=True).requires_grad_(True)
+        light = host["light"].to(dev, non_blocking=True).requires_grad_(True)
+        recon_im, recon_depth, fidx = ren.render_chain(depth, albedo, view, light, views_per_image=P)
+        loss = (recon_im * cot).sum()
+        loss.backward()
+        h_out["depth"].copy_(depth.grad, non_blocking=True)
+        h_out["albedo"].copy_(albedo.grad, non_blocking=True)
+        h_out["view"].copy_(view.grad, non_blocking=True)
+        h_out["light"].copy_(light.grad, non_blocking=True)
+        h_out["loss"].copy_(loss.detach(), non_blocking=True)
+
+    h2d = sum(host[k].numel() * 4 for k in host)
+    d2h = sum(h_out[k].numel() * 4 for k in h_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tns = torch.tensor([ms], device=dev)
+            dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+            ms = float(tns.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.g2s_launch_count()
+    lib.g2s_profile_enable(1)
+    ms_total = timed(step_device, args.steps)
+    lib.g2s_profile_enable(0)
+    launches = lib.g2s_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+
+    names = (ctypes.c_char_p * 32)()
+    tot = (ctypes.c_float * 32)()
+    cnt = (ctypes.c_int * 32)()
+    nk = lib.g2s_profile_read(32, names, tot, cnt)
+    kernels = [{"name": names[i].decode(), "launches": int(cnt[i]), "ms_per_launch": tot[i] / cnt[i],
+                "ms_per_step": tot[i] / args.steps} for i in range(nk)]
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    renders = B * world
+    value = renders / (ms_step * 1e-3)
+    e2e_value = renders / (ms_e2e / args.steps * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    per_render = alg_bytes_per_render(S, P)
+    # per-kernel algorithmic bytes per launch (DESIGN.md "kernels"): the HBM traffic each kernel cannot avoid
+    S2 = float(S * S)
+    kb = {"k_normal_fwd": N * (4 + 12) * S2,
+          "k_splat": N * 4 * S2,                                   # reads the depth maps; the z-buffer is an L2 workspace
+          "k_resolve_fused": B * 32 * S2 + N * 24 * S2,            # writes recon_depth+recon_im+face_idx; reads normal/albedo
+          "k_render_bwd_pixel": B * (12 + 4) * S2 + N * 24 * S2,   # reads grad_recon_im, recon_depth, normal/albedo
+          "k_render_bwd_tex": N * (24 + 24) * S2,                  # reads normal/albedo, writes grad_albedo/grad_normal
+          "k_normal_bwd": N * (12 + 4 + 4) * S2,
+          "k_raster_bwd": B * 16 * S2 + N * 8 * S2}                # reads the face-index map (+depth), writes grad_depth
+    for k in kernels:
+        k["alg_bytes_per_launch"] = kb.get(k["name"])
+        k["share_of_step"] = k["ms_per_step"] / ms_step
+        if k["alg_bytes_per_launch"]:
+            k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9
+            k["frac"] = k["achieved_gbs"] / peak
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    dom = kernels[0] if kernels else None
+    step_achieved = value / world * per_render / 1e9
+    roofline = {"bound": "hbm", "kernel": dom["name"] if dom else None,
+                "achieved": dom.get("achieved_gbs") if dom else None, "peak": peak, "unit": "GB/s",
+                "frac": dom.get("frac") if dom else None, "traffic": None, "peak_source": peak_src,
+                "kernel_share_of_step": dom["share_of_step"] if dom else None,
+                "step": {"alg_bytes_per_render": per_render, "achieved": step_achieved, "frac": step_achieved / peak,
+                         "note": "whole fwd+bwd step, SURVEY.md 8(d): renders/s/GPU x (64 S^2 + 48 S^2/P) bytes"},
+                "kernels": kernels}
+
+    threads = os.cpu_count() or 1
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        views = 2 if S <= 128 else 1
+        v, dt = cpu_reference_run(S, views, 2, 0, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "2 steps x %d view(s) of one %dx%d image, fwd+bwd, oracle with the reference's "
+                                  "brute-force face loop (%.1f s)" % (views, S, S, dt)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, N), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--views", type=int, default=16, help="projected pseudo-views per image")
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+"""gan-2d-to-3d_b200 -- B200-native (sm_100a) implementation of GAN2Shape's differentiable depth-map renderer path
+(reference: GAN2Shape/renderer).  The directory name is not a Python identifier; import it through the
+repo-root shim:  `import g2s_b200`  (g2s_b200.py loads this package under that name).
+
+Public surface (same names as the reference's GAN2Shape.renderer):
+    Renderer, get_grid, get_rotation_matrix, get_transform_matrices, get_face_idx
+plus the caller-side helpers the fused path absorbs (get_lighting_directions, get_shading) and the autograd
+Functions in `functional`.
+"""
+from .utils import (get_grid, get_rotation_matrix, get_transform_matrices, get_face_idx, get_lighting_directions,
+                    get_shading)
+from .renderer import Renderer, EPS
+from . import functional, synthetic, build as _build  # noqa: F401
+
+__all__ = ["Renderer", "get_grid", "get_rotation_matrix", "get_transform_matrices", "get_face_idx",
+           "get_lighting_directions", "get_shading", "functional", "synthetic", "EPS"]

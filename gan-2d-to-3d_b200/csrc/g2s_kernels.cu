@@ -1,0 +1,1323 @@
+// g2s_kernels.cu -- sm_100a kernels + C ABI (include/g2s_b200.h) of the depth-map renderer path.
+//
+// Reference being replaced: GAN2Shape/renderer/renderer.py:61-139, 252-277, GAN2Shape/renderer/utils.py,
+// GAN2Shape/model.py:146-151, 257-270, 347-360 and the external neural_renderer rasteriser
+// (renderer.py:47-54, 120).  See DESIGN.md for the kernel list, data layout and rooflines.
+//
+// Nothing here is a dense contraction: no tensor cores.  The kernels are HBM/L2- and fp32-ALU-bound;
+// the design rules are coalesced 8/16-byte accesses, shared-memory staging of the projected vertex
+// tiles, 64-bit RED.MIN for the z-buffer and warp-level reductions for the per-view gradients.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "../../include/g2s_b200.h"
+#include "g2s_raster.cuh"
+
+using namespace g2s;
+
+namespace {
+
+constexpr int PIX_THREADS = 256;
+
+Cam make_cam(const g2s_camera* c) {
+    Cam k;
+    for (int i = 0; i < 9; i++) {
+        k.K[i] = c->K[i];
+        k.invK[i] = c->inv_K[i];
+    }
+    k.rcd = c->rot_center_depth;
+    k.os = (float)c->image_size;
+    k.half_os = (float)(c->image_size / 2.0);
+    k.near = c->near_z;
+    k.far = c->far_z;
+    k.clamp_lo = c->clamp_lo;
+    k.clamp_hi = c->clamp_hi;
+    k.S = c->image_size;
+    return k;
+}
+
+
+// ---- instrumentation: launch counter + optional CUDA-event timing of every kernel (bench.py / tests) ----
+enum KernelId { K_ZINIT, K_SPLAT, K_RESOLVE, K_RESOLVE_FUSED, K_GRID_FWD, K_GRID_BWD, K_NORMAL_FWD, K_NORMAL_BWD,
+                K_SAMPLE_FWD, K_SAMPLE_BWD, K_CLAMP_GRAD, K_RASTER_BWD, K_BWD_PIXEL, K_BWD_TEX, K_GRID3D, K_RESOLVE_RGB,
+                K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"k_zbuf_init", "k_splat", "k_resolve", "k_resolve_fused", "k_warp_grid_fwd",
+                                           "k_warp_grid_bwd", "k_normal_fwd", "k_normal_bwd", "k_sample_fwd",
+                                           "k_sample_bwd", "k_clamp_grad", "k_raster_bwd", "k_render_bwd_pixel",
+                                           "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb"};
+std::atomic<long> g_launches{0};
+struct ProfRec { int id; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+
+struct Launch {
+    int id; cudaStream_t st; bool rec; cudaEvent_t a, b;
+    Launch(int id_, cudaStream_t st_) : id(id_), st(st_), rec(false) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (g_prof_on) {
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            auto get = [&]() { cudaEvent_t e; if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+                               else cudaEventCreate(&e); return e; };
+            a = get(); b = get(); rec = true;
+            cudaEventRecord(a, st);
+        }
+    }
+    ~Launch() {
+        if (rec) {
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            g_prof_recs.push_back({id, a, b});
+        }
+    }
+};
+
+inline int launch_status() { return cudaGetLastError() == cudaSuccess ? G2S_OK : G2S_ERR_LAUNCH; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum v[0..N) over the block and atomically add the totals to dst[0..N).  All threads must call.
+template <int N, int THREADS>
+__device__ __forceinline__ void block_accumulate(float (&v)[N], float* dst) {
+    __shared__ float red[N * (THREADS / 32)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const float s = warp_sum(v[k]);
+        if (lane == 0) red[warp * N + k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) s += red[w * N + threadIdx.x];
+        if (s != 0.f) atomicAdd(&dst[threadIdx.x], s);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// z-buffer
+__global__ void k_zbuf_init(unsigned long long* zb, long n, unsigned long long key) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) zb[i] = key;
+}
+
+// Projected (u, v, z) of the tile's vertices -> shared memory.
+template <bool FROM_VERTS>
+__device__ __forceinline__ void tile_project(const Cam& cam, const float* __restrict__ depth_b,
+                                             const float* __restrict__ verts_b, const float* sRt, int ty0,
+                                             int tx0, float* sv) {
+    const int S = cam.S;
+    for (int i = threadIdx.x; i < TV * TV; i += SPLAT_THREADS) {
+        const int vy = ty0 + i / TV, vx = tx0 + i % TV;
+        float ndc[3] = {0.f, 0.f, 0.f};
+        if (vy < S && vx < S) {
+            float q[3];
+            if (FROM_VERTS) {
+                const float* p = &verts_b[((long)vy * S + vx) * 3];
+                q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+            } else {
+                float ray[3];
+                pixel_ray(cam, vx, vy, ray);
+                warp_point(cam, sRt, sRt + 9, ray, depth_b[vy * S + vx], q);
+            }
+            project_ndc(cam, q, ndc);
+        }
+        sv[i * 3 + 0] = ndc[0];
+        sv[i * 3 + 1] = ndc[1];
+        sv[i * 3 + 2] = ndc[2];
+    }
+}
+
+__device__ __forceinline__ void splat_one(const Tri& f, float* fi, bool& have_fi, int xi, int yi, float xp, float yp,
+                                          int is, float near, float far, uint32_t face, unsigned long long* zb) {
+    float w[3], zp;
+    if (tri_sample(f, fi, have_fi, xi, yi, xp, yp, is, near, far, w, &zp))
+        atomicMin(&zb[(long)(is - 1 - yi) * is + xi], zkey_pack(zp, face));
+}
+
+// Forward rasterisation of the grid mesh of one view into the packed-key z-buffer.
+// grid = (tiles, n_views), block = TILE*TILE threads (one per quad).
+template <bool FROM_VERTS>
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+        const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
+        int tiles_x) {
+    __shared__ float sv[TV * TV * 3];
+    __shared__ float sRt[12];
+    __shared__ unsigned short squeue[SPLAT_THREADS * 4];
+    __shared__ int sqn;
+    const int tid = threadIdx.x, b = blockIdx.y, S = cam.S, is = 2 * S;
+    const int ty0 = (blockIdx.x / tiles_x) * TILE, tx0 = (blockIdx.x % tiles_x) * TILE;
+    if (!FROM_VERTS) {
+        if (tid < 9) sRt[tid] = R[b * 9 + tid];
+        else if (tid < 12) sRt[tid] = t[b * 3 + tid - 9];
+    }
+    if (tid == 0) sqn = 0;
+    __syncthreads();
+    tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
+                             FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, sRt, ty0, tx0, sv);
+    __syncthreads();
+
+    unsigned long long* zb = zbuf + (long)b * is * is;
+    const int Q = (S - 1) * (S - 1);
+    const int qy = tid / TILE, qx = tid % TILE;
+    if (ty0 + qy < S - 1 && tx0 + qx < S - 1) {
+        const int qid = (ty0 + qy) * (S - 1) + tx0 + qx;
+#pragma unroll 1
+        for (int w = 0; w < 4; w++) {
+            const Tri f = tile_winding(sv, qy, qx, w);
+            if (tri_is_back(f)) continue;
+            BBox bb;
+            if (!tri_bbox(f, is, bb)) continue;
+            const int n = (bb.x1 - bb.x0 + 1) * (bb.y1 - bb.y0 + 1);
+            if (n > SMALL_BOX) {
+                squeue[atomicAdd(&sqn, 1)] = (unsigned short)(tid * 4 + w);
+                continue;
+            }
+            float fi[9];
+            bool have_fi = false;
+            const uint32_t face = (uint32_t)(w * Q + qid);
+            for (int yi = bb.y0; yi <= bb.y1; yi++) {
+                const float yp = pix_center_ndc(yi, is);
+                for (int xi = bb.x0; xi <= bb.x1; xi++)
+                    splat_one(f, fi, have_fi, xi, yi, pix_center_ndc(xi, is), yp, is, cam.near, cam.far, face, zb);
+            }
+        }
+    }
+    __syncthreads();
+    // large faces: one warp per face, lanes stride over the bounding box
+    const int nq = sqn, lane = tid & 31;
+    for (int e = tid >> 5; e < nq; e += SPLAT_THREADS / 32) {
+        const int item = squeue[e], qt = item >> 2, w = item & 3;
+        const int fqy = qt / TILE, fqx = qt % TILE;
+        const Tri f = tile_winding(sv, fqy, fqx, w);
+        BBox bb;
+        tri_bbox(f, is, bb);
+        const int bw = bb.x1 - bb.x0 + 1, n = bw * (bb.y1 - bb.y0 + 1);
+        const uint32_t face = (uint32_t)(w * Q + (ty0 + fqy) * (S - 1) + tx0 + fqx);
+        float fi[9];
+        bool have_fi = false;
+        for (int idx = lane; idx < n; idx += 32) {
+            const int yi = bb.y0 + idx / bw, xi = bb.x0 + idx % bw;
+            splat_one(f, fi, have_fi, xi, yi, pix_center_ndc(xi, is), pix_center_ndc(yi, is), is, cam.near, cam.far,
+                      face, zb);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading + bilinear sampling (model.py:355-360, 270)
+
+struct LightP {
+    float a, b, dx, dy, dz;
+};
+
+__device__ __forceinline__ bool bilinear_setup(float gx, float gy, int W, int H, int align, int& x0, int& y0,
+                                               float& tx, float& ty) {
+    const float ix = grid_unnormalize(gx, W, align), iy = grid_unnormalize(gy, H, align);
+    if (!(ix > -1.0f && ix < (float)W && iy > -1.0f && iy < (float)H)) return false;
+    const float fx = floorf(ix), fy = floorf(iy);
+    x0 = (int)fx; y0 = (int)fy;
+    tx = ix - fx; ty = iy - fy;
+    return true;
+}
+
+// shading terms at one texel; tex[c] = (albedo/2+.5)*shade*2-1
+__device__ __forceinline__ void shade_texel(const float* __restrict__ normal_img, const float* __restrict__ albedo_img,
+                                            int HW, int p, const LightP& L, float tex[3], float* shade_out,
+                                            float* ndotl_out) {
+    const float n0 = normal_img[p * 3 + 0], n1 = normal_img[p * 3 + 1], n2 = normal_img[p * 3 + 2];
+    const float ndl = n0 * L.dx + n1 * L.dy + n2 * L.dz;
+    const float sh = L.a + L.b * fmaxf(ndl, 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; c++) tex[c] = (albedo_img[c * HW + p] * 0.5f + 0.5f) * sh * 2.0f - 1.0f;
+    *shade_out = sh;
+    *ndotl_out = ndl;
+}
+
+struct FusedArgs {
+    const float* R;
+    const float* t;
+    const float* light;   // [n_views,5]
+    const float* normal;  // [n_images,S,S,3]
+    const float* albedo;  // [n_images,3,S,S]
+    float* recon_im;      // [n_views,3,S,S]
+    int vpi;
+    int align;
+};
+
+// z-buffer resolve: face-index map, flip + 2x2 mean + clamp -> recon_depth, z-buffer reset; when FUSED
+// also inverse warp grid + shaded bilinear sampling -> recon_im.  One thread per output pixel.
+template <bool FUSED>
+__global__ void __launch_bounds__(PIX_THREADS)
+k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restrict__ recon_depth,
+          int* __restrict__ face_idx, const FusedArgs fa) {
+    const int S = cam.S, is = 2 * S, b = blockIdx.y;
+    const int pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= S * S) return;
+    const int i = pix / S, j = pix - i * S;
+    unsigned long long* zb = zbuf + (long)b * is * is;
+    ulonglong2* r0 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i) * is + 2 * j);
+    ulonglong2* r1 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i + 1) * is + 2 * j);
+    const ulonglong2 k0 = *r0, k1 = *r1;
+    const unsigned long long empty = zkey_empty(cam.far);
+    *r0 = make_ulonglong2(empty, empty);
+    *r1 = make_ulonglong2(empty, empty);
+    if (face_idx) {
+        int* fo = face_idx + (long)b * is * is;
+        *reinterpret_cast<int2*>(fo + (long)(2 * i) * is + 2 * j) = make_int2(zkey_face(k0.x), zkey_face(k0.y));
+        *reinterpret_cast<int2*>(fo + (long)(2 * i + 1) * is + 2 * j) = make_int2(zkey_face(k1.x), zkey_face(k1.y));
+    }
+    const float sum = add(add(add(zkey_depth(k0.x), zkey_depth(k0.y)), zkey_depth(k1.x)), zkey_depth(k1.y));
+    const float rd = fminf(fmaxf(mul(sum, 0.25f), cam.clamp_lo), cam.clamp_hi);
+    recon_depth[(long)b * S * S + pix] = rd;
+    if (FUSED) {
+        const int img = b / fa.vpi;
+        float Rm[9], tv[3], ray[3], q[3], v[3], g[2];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&fa.R[b * 9 + k]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) tv[k] = __ldg(&fa.t[b * 3 + k]);
+        pixel_ray(cam, j, i, ray);
+        inv_warp_point(cam, Rm, tv, ray, rd, q, v);
+        point_to_grid(cam, q, S, S, g);
+        LightP L;
+        L.a = __ldg(&fa.light[b * 5 + 0]); L.b = __ldg(&fa.light[b * 5 + 1]);
+        L.dx = __ldg(&fa.light[b * 5 + 2]); L.dy = __ldg(&fa.light[b * 5 + 3]); L.dz = __ldg(&fa.light[b * 5 + 4]);
+        const float* nimg = fa.normal + (long)img * S * S * 3;
+        const float* aimg = fa.albedo + (long)img * S * S * 3;
+        float out[3] = {0.f, 0.f, 0.f};
+        int x0, y0;
+        float tx, ty;
+        if (bilinear_setup(g[0], g[1], S, S, fa.align, x0, y0, tx, ty)) {
+#pragma unroll
+            for (int tap = 0; tap < 4; tap++) {
+                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
+                const float wgt = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
+                float tex[3], sh, ndl;
+                shade_texel(nimg, aimg, S * S, yy * S + xx, L, tex, &sh, &ndl);
+#pragma unroll
+                for (int c = 0; c < 3; c++) out[c] += wgt * tex[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            fa.recon_im[((long)b * 3 + c) * S * S + pix] = fminf(fmaxf(out[c], -1.f), 1.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone per-pixel operators
+
+__global__ void __launch_bounds__(PIX_THREADS)
+k_warp_grid_fwd(const Cam cam, const float* __restrict__ depth, long dstride, const float* __restrict__ R,
+                const float* __restrict__ t, int H, int W, int inverse, float* __restrict__ grid) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
+    float Rm[9], tv[3], ray[3], q[3], v[3], g[2];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rm[k] = __ldg(&R[b * 9 + k]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) tv[k] = __ldg(&t[b * 3 + k]);
+    pixel_ray(cam, x, y, ray);
+    const float d = depth[(long)b * dstride + pix];
+    if (inverse) inv_warp_point(cam, Rm, tv, ray, d, q, v);
+    else warp_point(cam, Rm, tv, ray, d, q);
+    point_to_grid(cam, q, W, H, g);
+    reinterpret_cast<float2*>(grid)[(long)b * H * W + pix] = make_float2(g[0], g[1]);
+}
+
+// Backward of (depth -> sampling grid) for one pixel.  Returns d(loss)/d(depth) and accumulates the
+// pixel's contribution to grad_R (acc[0..9)) and grad_t (acc[9..12)).
+__device__ __forceinline__ float warp_grid_bwd_pixel(const Cam& cam, const float* Rm, const float* tv, int x, int y,
+                                                     int W, int H, float d, int inverse, float Gx, float Gy,
+                                                     float acc[12]) {
+    float ray[3], q[3], v[3];
+    pixel_ray(cam, x, y, ray);
+    if (inverse) {
+        inv_warp_point(cam, Rm, tv, ray, d, q, v);
+    } else {
+        warp_point(cam, Rm, tv, ray, d, q);
+        v[0] = ray[0] * d; v[1] = ray[1] * d; v[2] = ray[2] * d - cam.rcd;
+    }
+    const float iz = 1.0f / q[2];
+    const float nx = q[0] * iz, ny = q[1] * iz;
+    const float dpx = Gx * 2.0f / (float)(W - 1), dpy = Gy * 2.0f / (float)(H - 1);
+    const float dnx = dpx * cam.K[0] + dpy * cam.K[3], dny = dpx * cam.K[1] + dpy * cam.K[4];
+    float dq[3] = {dnx * iz, dny * iz, -(dnx * nx + dny * ny) * iz};
+    float dv[3];
+    if (inverse) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dv[k] = dq[0] * Rm[3 * k] + dq[1] * Rm[3 * k + 1] + dq[2] * Rm[3 * k + 2];
+#pragma unroll
+            for (int j = 0; j < 3; j++) acc[3 * k + j] += v[k] * dq[j];
+            acc[9 + k] -= dv[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dv[k] = dq[0] * Rm[k] + dq[1] * Rm[3 + k] + dq[2] * Rm[6 + k];
+#pragma unroll
+            for (int j = 0; j < 3; j++) acc[3 * j + k] += dq[j] * v[k];
+            acc[9 + k] += dq[k];
+        }
+    }
+    return dv[0] * ray[0] + dv[1] * ray[1] + dv[2] * ray[2];
+}
+
+__global__ void __launch_bounds__(PIX_THREADS)
+k_warp_grid_bwd(const Cam cam, const float* __restrict__ depth, long dstride, const float* __restrict__ R,
+                const float* __restrict__ t, int H, int W, int inverse, const float* __restrict__ grad_grid,
+                float* __restrict__ grad_depth, float* __restrict__ grad_R, float* __restrict__ grad_t) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0.f;
+    if (pix < H * W) {
+        const int y = pix / W, x = pix - y * W;
+        float Rm[9], tv[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&R[b * 9 + k]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) tv[k] = __ldg(&t[b * 3 + k]);
+        const float2 G = reinterpret_cast<const float2*>(grad_grid)[(long)b * H * W + pix];
+        grad_depth[(long)b * H * W + pix] =
+            warp_grid_bwd_pixel(cam, Rm, tv, x, y, W, H, depth[(long)b * dstride + pix], inverse, G.x, G.y, acc);
+    }
+    if (grad_R) {
+        float accR[9], acct[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) accR[k] = acc[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
+        block_accumulate<9, PIX_THREADS>(accR, grad_R + b * 9);
+        block_accumulate<3, PIX_THREADS>(acct, grad_t + b * 3);
+    }
+}
+
+// 3-D point of pixel (x,y): ray * depth
+__device__ __forceinline__ void depth_point(const Cam& cam, const float* __restrict__ dimg, int W, int x, int y,
+                                            float p[3]) {
+    float ray[3];
+    pixel_ray(cam, x, y, ray);
+    const float d = dimg[y * W + x];
+    p[0] = mul(ray[0], d); p[1] = mul(ray[1], d); p[2] = mul(ray[2], d);
+}
+
+__global__ void __launch_bounds__(PIX_THREADS)
+k_normal_fwd(const Cam cam, const float* __restrict__ depth, int H, int W, float* __restrict__ normal) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
+    const float* dimg = depth + (long)b * H * W;
+    float n[3] = {0.f, 0.f, dvd(1.0f, add(1.0f, 1e-7f))};
+    if (x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2) {
+        float pl[3], pr[3], pu[3], pd[3], len;
+        depth_point(cam, dimg, W, x - 1, y, pl);
+        depth_point(cam, dimg, W, x + 1, y, pr);
+        depth_point(cam, dimg, W, x, y - 1, pu);
+        depth_point(cam, dimg, W, x, y + 1, pd);
+        normal_from_points(pl, pr, pu, pd, n, &len);
+    }
+    float* o = normal + ((long)b * H * W + pix) * 3;
+    o[0] = n[0]; o[1] = n[1]; o[2] = n[2];
+}
+
+// d(loss)/d(tu), d(loss)/d(tv) of the normal at interior pixel (x,y) given d(loss)/d(normal)
+__device__ __forceinline__ void normal_tangent_grads(const Cam& cam, const float* __restrict__ dimg,
+                                                     const float* __restrict__ gnimg, int H, int W, int x, int y,
+                                                     float gtu[3], float gtv[3]) {
+    gtu[0] = gtu[1] = gtu[2] = 0.f;
+    gtv[0] = gtv[1] = gtv[2] = 0.f;
+    if (x < 1 || x > W - 2 || y < 1 || y > H - 2) return;
+    float pl[3], pr[3], pu[3], pd[3];
+    depth_point(cam, dimg, W, x - 1, y, pl);
+    depth_point(cam, dimg, W, x + 1, y, pr);
+    depth_point(cam, dimg, W, x, y - 1, pu);
+    depth_point(cam, dimg, W, x, y + 1, pd);
+    const float tu[3] = {pr[0] - pl[0], pr[1] - pl[1], pr[2] - pl[2]};
+    const float tv[3] = {pd[0] - pu[0], pd[1] - pu[1], pd[2] - pu[2]};
+    const float c[3] = {tu[1] * tv[2] - tu[2] * tv[1], tu[2] * tv[0] - tu[0] * tv[2], tu[0] * tv[1] - tu[1] * tv[0]};
+    const float len = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    const float den = len + 1e-7f;
+    const float* gn = gnimg + (y * W + x) * 3;
+    const float g0 = gn[0], g1 = gn[1], g2 = gn[2];
+    // n = c / den, den = |c| + eps
+    const float gdotc = g0 * c[0] + g1 * c[1] + g2 * c[2];
+    const float s = len > 0.f ? gdotc / (den * den * len) : 0.f;
+    const float gc[3] = {g0 / den - s * c[0], g1 / den - s * c[1], g2 / den - s * c[2]};
+    gtu[0] = tv[1] * gc[2] - tv[2] * gc[1];
+    gtu[1] = tv[2] * gc[0] - tv[0] * gc[2];
+    gtu[2] = tv[0] * gc[1] - tv[1] * gc[0];
+    gtv[0] = gc[1] * tu[2] - gc[2] * tu[1];
+    gtv[1] = gc[2] * tu[0] - gc[0] * tu[2];
+    gtv[2] = gc[0] * tu[1] - gc[1] * tu[0];
+}
+
+// gather form of the normal backward: pixel (x,y) is the +tu endpoint of (x-1,y), the -tu endpoint of
+// (x+1,y), the +tv endpoint of (x,y-1) and the -tv endpoint of (x,y+1)
+__global__ void __launch_bounds__(PIX_THREADS)
+k_normal_bwd(const Cam cam, const float* __restrict__ depth, int H, int W, const float* __restrict__ grad_normal,
+             float* __restrict__ grad_depth, int accumulate) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
+    const float* dimg = depth + (long)b * H * W;
+    const float* gn = grad_normal + (long)b * H * W * 3;
+    float gp[3] = {0.f, 0.f, 0.f}, a[3], c[3];
+    if (x >= 1) {
+        normal_tangent_grads(cam, dimg, gn, H, W, x - 1, y, a, c);
+        gp[0] += a[0]; gp[1] += a[1]; gp[2] += a[2];
+    }
+    if (x <= W - 2) {
+        normal_tangent_grads(cam, dimg, gn, H, W, x + 1, y, a, c);
+        gp[0] -= a[0]; gp[1] -= a[1]; gp[2] -= a[2];
+    }
+    if (y >= 1) {
+        normal_tangent_grads(cam, dimg, gn, H, W, x, y - 1, a, c);
+        gp[0] += c[0]; gp[1] += c[1]; gp[2] += c[2];
+    }
+    if (y <= H - 2) {
+        normal_tangent_grads(cam, dimg, gn, H, W, x, y + 1, a, c);
+        gp[0] -= c[0]; gp[1] -= c[1]; gp[2] -= c[2];
+    }
+    float ray[3];
+    pixel_ray(cam, x, y, ray);
+    const float gd = gp[0] * ray[0] + gp[1] * ray[1] + gp[2] * ray[2];
+    float* o = grad_depth + (long)b * H * W + pix;
+    *o = accumulate ? *o + gd : gd;
+}
+
+__global__ void __launch_bounds__(PIX_THREADS)
+k_sample_fwd(const float* __restrict__ input, long istride, const float* __restrict__ grid, int C, int H, int W,
+             int Ho, int Wo, int mode, int align, float* __restrict__ out) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= Ho * Wo) return;
+    const float2 g = reinterpret_cast<const float2*>(grid)[(long)b * Ho * Wo + pix];
+    const float* in = input + (long)b * istride;
+    float* o = out + (long)b * C * Ho * Wo + pix;
+    if (mode == 1) {
+        const float ix = nearbyintf(grid_unnormalize(g.x, W, align)), iy = nearbyintf(grid_unnormalize(g.y, H, align));
+        const bool ok = ix >= 0.f && ix < (float)W && iy >= 0.f && iy < (float)H;
+        const int p = ok ? (int)iy * W + (int)ix : 0;
+        for (int c = 0; c < C; c++) o[(long)c * Ho * Wo] = ok ? in[(long)c * H * W + p] : 0.f;
+        return;
+    }
+    int x0, y0;
+    float tx, ty;
+    const bool any = bilinear_setup(g.x, g.y, W, H, align, x0, y0, tx, ty);
+    for (int c = 0; c < C; c++) {
+        float acc = 0.f;
+        if (any) {
+#pragma unroll
+            for (int tap = 0; tap < 4; tap++) {
+                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+                acc += ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty) * in[(long)c * H * W + yy * W + xx];
+            }
+        }
+        o[(long)c * Ho * Wo] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(PIX_THREADS)
+k_sample_bwd(const float* __restrict__ input, long istride, const float* __restrict__ grid,
+             const float* __restrict__ grad_out, int C, int H, int W, int Ho, int Wo, int mode, int align,
+             float* __restrict__ grad_input, long gistride, float* __restrict__ grad_grid) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= Ho * Wo) return;
+    const float2 g = reinterpret_cast<const float2*>(grid)[(long)b * Ho * Wo + pix];
+    const float* in = input + (long)b * istride;
+    const float* go = grad_out + (long)b * C * Ho * Wo + pix;
+    float* gi = grad_input ? grad_input + (long)b * gistride : nullptr;
+    float gix = 0.f, giy = 0.f;
+    if (mode == 1) {
+        const float ix = nearbyintf(grid_unnormalize(g.x, W, align)), iy = nearbyintf(grid_unnormalize(g.y, H, align));
+        if (gi && ix >= 0.f && ix < (float)W && iy >= 0.f && iy < (float)H) {
+            const int p = (int)iy * W + (int)ix;
+            for (int c = 0; c < C; c++) atomicAdd(&gi[(long)c * H * W + p], go[(long)c * Ho * Wo]);
+        }
+    } else {
+        int x0, y0;
+        float tx, ty;
+        if (bilinear_setup(g.x, g.y, W, H, align, x0, y0, tx, ty)) {
+            for (int c = 0; c < C; c++) {
+                const float G = go[(long)c * Ho * Wo];
+#pragma unroll
+                for (int tap = 0; tap < 4; tap++) {
+                    const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                    if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+                    const float wx = (tap & 1) ? tx : 1.f - tx, wy = (tap >> 1) ? ty : 1.f - ty;
+                    const long p = (long)c * H * W + yy * W + xx;
+                    if (gi) atomicAdd(&gi[p], wx * wy * G);
+                    const float val = in[p];
+                    gix += ((tap & 1) ? 1.f : -1.f) * wy * val * G;
+                    giy += ((tap >> 1) ? 1.f : -1.f) * wx * val * G;
+                }
+            }
+        }
+    }
+    if (grad_grid) {
+        const float mx = align ? (float)(W - 1) * 0.5f : (float)W * 0.5f;
+        const float my = align ? (float)(H - 1) * 0.5f : (float)H * 0.5f;
+        reinterpret_cast<float2*>(grad_grid)[(long)b * Ho * Wo + pix] = make_float2(gix * mx, giy * my);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of warp_canon_depth
+
+// g_sub = d(loss)/d(each of the 4 sub-pixel depths) of an output pixel: clamp mask * g / 4
+__global__ void k_clamp_grad(const float* __restrict__ recon_depth, const float* __restrict__ grad, float lo, float hi,
+                             long n, float* __restrict__ g_sub) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float rd = recon_depth[i];
+    g_sub[i] = (rd > lo && rd < hi) ? 0.25f * grad[i] : 0.f;
+}
+
+// per-face accumulation of A_k = sum over the sub-pixels this face won of g * w_k * zp^2
+__device__ __forceinline__ void bwd_one(const Tri& f, float* fi, bool& have_fi, int xi, int yi, int is,
+                                        const int* __restrict__ fmap, const float* __restrict__ gsub, int S,
+                                        int face, float A[3], const Cam& cam) {
+    const int r = is - 1 - yi;
+    if (fmap[(long)r * is + xi] != face) return;
+    const float g = gsub[(r >> 1) * S + (xi >> 1)];
+    if (g == 0.f) return;
+    if (!have_fi) {
+        tri_face_inv(f, is, fi);
+        have_fi = true;
+    }
+    float w[3], zp = 0.f;
+    tri_weights_depth(f, fi, xi, yi, cam.near, cam.far, w, &zp);
+    const float s = g * zp * zp;
+    A[0] += s * w[0]; A[1] += s * w[1]; A[2] += s * w[2];
+}
+
+// scatter one face's gradient to its three vertices' (u,v,z) accumulators in shared memory
+__device__ __forceinline__ void bwd_face_scatter(const Tri& f, const float* fi, const float A[3], int is, float* sg,
+                                                 int qy, int qx, int w) {
+    // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
+    const float t0 = -(fi[0] / f.z0 + fi[3] / f.z1 + fi[6] / f.z2);
+    const float t1 = -(fi[1] / f.z0 + fi[4] / f.z1 + fi[7] / f.z2);
+    const float hs = 0.5f * (float)is;
+    const float z[3] = {f.z0, f.z1, f.z2};
+    // vertex slots of the winding (same order as tile_winding)
+    const int a = (qy * TV + qx) * 3, b = ((qy + 1) * TV + qx) * 3, c = (qy * TV + qx + 1) * 3,
+              d = ((qy + 1) * TV + qx + 1) * 3;
+    int v[3];
+    switch (w) {
+        case 0: v[0] = a; v[1] = b; v[2] = c; break;
+        case 1: v[0] = c; v[1] = b; v[2] = d; break;
+        case 2: v[0] = c; v[1] = b; v[2] = a; break;
+        default: v[0] = d; v[1] = b; v[2] = c; break;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (A[k] == 0.f) continue;
+        atomicAdd(&sg[v[k] + 0], -t0 * A[k] * hs);
+        atomicAdd(&sg[v[k] + 1], -t1 * A[k] * hs);
+        atomicAdd(&sg[v[k] + 2], A[k] / (z[k] * z[k]));
+    }
+}
+
+// Backward rasterisation: same tiling and the same candidate boxes as k_splat; every winding collects
+// the sub-pixels it won from the face-index map, turns them into vertex (u,v,z) gradients in shared
+// memory, and the tile pushes those through projection / rotation to grad_depth, grad_R, grad_t.
+__global__ void __launch_bounds__(SPLAT_THREADS)
+k_raster_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+             const float* __restrict__ t, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
+             float* __restrict__ grad_depth, long gdstride, float* __restrict__ grad_R, float* __restrict__ grad_t,
+             int tiles_x) {
+    __shared__ float sv[TV * TV * 3];
+    __shared__ float sg[TV * TV * 3];
+    __shared__ float sRt[12];
+    __shared__ unsigned short squeue[SPLAT_THREADS * 4];
+    __shared__ int sqn;
+    const int tid = threadIdx.x, b = blockIdx.y, S = cam.S, is = 2 * S;
+    const int ty0 = (blockIdx.x / tiles_x) * TILE, tx0 = (blockIdx.x % tiles_x) * TILE;
+    if (tid < 9) sRt[tid] = R[b * 9 + tid];
+    else if (tid < 12) sRt[tid] = t[b * 3 + tid - 9];
+    if (tid == 0) sqn = 0;
+    for (int i = tid; i < TV * TV * 3; i += SPLAT_THREADS) sg[i] = 0.f;
+    __syncthreads();
+    const float* dimg = depth + (long)(b / vpi) * dstride;
+    tile_project<false>(cam, dimg, nullptr, sRt, ty0, tx0, sv);
+    __syncthreads();
+
+    const int* fmap = face_idx + (long)b * is * is;
+    const float* gs = g_sub + (long)b * S * S;
+    const int Q = (S - 1) * (S - 1);
+    const int qy = tid / TILE, qx = tid % TILE;
+    if (ty0 + qy < S - 1 && tx0 + qx < S - 1) {
+        const int qid = (ty0 + qy) * (S - 1) + tx0 + qx;
+#pragma unroll 1
+        for (int w = 0; w < 4; w++) {
+            const Tri f = tile_winding(sv, qy, qx, w);
+            if (tri_is_back(f)) continue;
+            BBox bb;
+            if (!tri_bbox(f, is, bb)) continue;
+            const int n = (bb.x1 - bb.x0 + 1) * (bb.y1 - bb.y0 + 1);
+            if (n > SMALL_BOX) {
+                squeue[atomicAdd(&sqn, 1)] = (unsigned short)(tid * 4 + w);
+                continue;
+            }
+            float fi[9], A[3] = {0.f, 0.f, 0.f};
+            bool have_fi = false;
+            const int face = w * Q + qid;
+            for (int yi = bb.y0; yi <= bb.y1; yi++)
+                for (int xi = bb.x0; xi <= bb.x1; xi++) bwd_one(f, fi, have_fi, xi, yi, is, fmap, gs, S, face, A, cam);
+            if (have_fi) bwd_face_scatter(f, fi, A, is, sg, qy, qx, w);
+        }
+    }
+    __syncthreads();
+    const int nq = sqn, lane = tid & 31;
+    for (int e = tid >> 5; e < nq; e += SPLAT_THREADS / 32) {
+        const int item = squeue[e], qt = item >> 2, w = item & 3;
+        const int fqy = qt / TILE, fqx = qt % TILE;
+        const Tri f = tile_winding(sv, fqy, fqx, w);
+        BBox bb;
+        tri_bbox(f, is, bb);
+        const int bw = bb.x1 - bb.x0 + 1, n = bw * (bb.y1 - bb.y0 + 1);
+        const int face = w * Q + (ty0 + fqy) * (S - 1) + tx0 + fqx;
+        float fi[9], A[3] = {0.f, 0.f, 0.f};
+        bool have_fi = false;
+        for (int idx = lane; idx < n; idx += 32)
+            bwd_one(f, fi, have_fi, bb.x0 + idx % bw, bb.y0 + idx / bw, is, fmap, gs, S, face, A, cam);
+        A[0] = warp_sum(A[0]); A[1] = warp_sum(A[1]); A[2] = warp_sum(A[2]);
+        if (lane == 0 && (A[0] != 0.f || A[1] != 0.f || A[2] != 0.f)) {
+            tri_face_inv(f, is, fi);
+            bwd_face_scatter(f, fi, A, is, sg, fqy, fqx, w);
+        }
+    }
+    __syncthreads();
+    // vertex chain: (u,v,z) NDC gradient -> 3-D point -> depth, R, t
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0.f;
+    for (int i = tid; i < TV * TV; i += SPLAT_THREADS) {
+        const int vy = ty0 + i / TV, vx = tx0 + i % TV;
+        const float gu = sg[i * 3], gv = sg[i * 3 + 1], gz = sg[i * 3 + 2];
+        if (vy >= S || vx >= S || (gu == 0.f && gv == 0.f && gz == 0.f)) continue;
+        float ray[3], q[3];
+        pixel_ray(cam, vx, vy, ray);
+        const float d = dimg[vy * S + vx];
+        warp_point(cam, sRt, sRt + 9, ray, d, q);
+        const float v[3] = {ray[0] * d, ray[1] * d, ray[2] * d - cam.rcd};
+        const float zz = q[2] + 1e-9f, iz = 1.0f / zz;
+        const float x_ = q[0] * iz, y_ = q[1] * iz;
+        const float gup = gu * (2.0f / cam.os), gvp = -gv * (2.0f / cam.os);
+        const float gx_ = gup * cam.K[0] + gvp * cam.K[3], gy_ = gup * cam.K[1] + gvp * cam.K[4];
+        const float gq[3] = {gx_ * iz, gy_ * iz, gz - (gx_ * x_ + gy_ * y_) * iz};
+        float gd = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float gvk = gq[0] * sRt[k] + gq[1] * sRt[3 + k] + gq[2] * sRt[6 + k];
+            gd += gvk * ray[k];
+#pragma unroll
+            for (int j = 0; j < 3; j++) acc[3 * j + k] += gq[j] * v[k];
+            acc[9 + k] += gq[k];
+        }
+        atomicAdd(&grad_depth[(long)(b / vpi) * gdstride + vy * S + vx], gd);
+    }
+    if (grad_R) {
+        float accR[9], acct[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) accR[k] = acc[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
+        block_accumulate<9, SPLAT_THREADS>(accR, grad_R + b * 9);
+        block_accumulate<3, SPLAT_THREADS>(acct, grad_t + b * 3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused render backward, pixel stage: clamp(-1,1) -> shaded bilinear sampling -> inverse warp grid.
+// Writes per-view texture gradients (atomics into grad_tex_ws), the masked quarter gradient of
+// recon_depth (g_sub) and accumulates grad_R / grad_t.
+__global__ void __launch_bounds__(PIX_THREADS)
+k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ recon_depth,
+                   const float* __restrict__ grad_recon_im, const float* __restrict__ grad_recon_depth,
+                   float* __restrict__ g_sub, float* __restrict__ grad_tex, float* __restrict__ grad_R,
+                   float* __restrict__ grad_t) {
+    const int S = cam.S, b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0.f;
+    if (pix < S * S) {
+        const int i = pix / S, j = pix - i * S, img = b / fa.vpi;
+        float Rm[9], tv[3], ray[3], q[3], v[3], g[2];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&fa.R[b * 9 + k]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) tv[k] = __ldg(&fa.t[b * 3 + k]);
+        const float rd = recon_depth[(long)b * S * S + pix];
+        pixel_ray(cam, j, i, ray);
+        inv_warp_point(cam, Rm, tv, ray, rd, q, v);
+        point_to_grid(cam, q, S, S, g);
+        LightP L;
+        L.a = __ldg(&fa.light[b * 5 + 0]); L.b = __ldg(&fa.light[b * 5 + 1]);
+        L.dx = __ldg(&fa.light[b * 5 + 2]); L.dy = __ldg(&fa.light[b * 5 + 3]); L.dz = __ldg(&fa.light[b * 5 + 4]);
+        const float* nimg = fa.normal + (long)img * S * S * 3;
+        const float* aimg = fa.albedo + (long)img * S * S * 3;
+        float G[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) G[c] = grad_recon_im[((long)b * 3 + c) * S * S + pix];
+        float gix = 0.f, giy = 0.f;
+        int x0, y0;
+        float tx, ty;
+        if (bilinear_setup(g[0], g[1], S, S, fa.align, x0, y0, tx, ty)) {
+            float tex[4][3], out[3] = {0.f, 0.f, 0.f};
+            bool ok[4];
+#pragma unroll
+            for (int tap = 0; tap < 4; tap++) {
+                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                ok[tap] = !(xx < 0 || xx >= S || yy < 0 || yy >= S);
+                tex[tap][0] = tex[tap][1] = tex[tap][2] = 0.f;
+                if (!ok[tap]) continue;
+                float sh, ndl;
+                shade_texel(nimg, aimg, S * S, yy * S + xx, L, tex[tap], &sh, &ndl);
+                const float wgt = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
+#pragma unroll
+                for (int c = 0; c < 3; c++) out[c] += wgt * tex[tap][c];
+            }
+            // clamp(-1,1) passes the gradient where -1 <= x <= 1
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (!(out[c] >= -1.f && out[c] <= 1.f)) G[c] = 0.f;
+            float* gt_b = grad_tex + (long)b * 3 * S * S;
+#pragma unroll
+            for (int tap = 0; tap < 4; tap++) {
+                if (!ok[tap]) continue;
+                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                const float wx = (tap & 1) ? tx : 1.f - tx, wy = (tap >> 1) ? ty : 1.f - ty;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (G[c] != 0.f) atomicAdd(&gt_b[c * S * S + yy * S + xx], wx * wy * G[c]);
+                    gix += ((tap & 1) ? 1.f : -1.f) * wy * tex[tap][c] * G[c];
+                    giy += ((tap >> 1) ? 1.f : -1.f) * wx * tex[tap][c] * G[c];
+                }
+            }
+        }
+        const float mult = fa.align ? (float)(S - 1) * 0.5f : (float)S * 0.5f;
+        float gd = warp_grid_bwd_pixel(cam, Rm, tv, j, i, S, S, rd, 1, gix * mult, giy * mult, acc);
+        if (grad_recon_depth) gd += grad_recon_depth[(long)b * S * S + pix];
+        g_sub[(long)b * S * S + pix] = (rd > cam.clamp_lo && rd < cam.clamp_hi) ? 0.25f * gd : 0.f;
+    }
+    float accR[9], acct[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) accR[k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
+    block_accumulate<9, PIX_THREADS>(accR, grad_R + b * 9);
+    block_accumulate<3, PIX_THREADS>(acct, grad_t + b * 3);
+}
+
+// fused render backward, texture stage: per image pixel, loop over the image's views and turn the
+// per-view texture gradients into grad_albedo, grad_normal (registers, no atomics) and grad_light
+// (warp reduction + one atomic per warp and view).
+__global__ void __launch_bounds__(PIX_THREADS)
+k_render_bwd_tex(int S, const FusedArgs fa, const float* __restrict__ grad_tex, float* __restrict__ grad_albedo,
+                 float* __restrict__ grad_normal, float* __restrict__ grad_light) {
+    const int img = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    const bool live = pix < S * S;
+    const int p = live ? pix : 0;
+    const float* nimg = fa.normal + (long)img * S * S * 3;
+    const float* aimg = fa.albedo + (long)img * S * S * 3;
+    const float n0 = nimg[p * 3], n1 = nimg[p * 3 + 1], n2 = nimg[p * 3 + 2];
+    const float al[3] = {aimg[p], aimg[S * S + p], aimg[2 * S * S + p]};
+    float ga[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
+    for (int vi = 0; vi < fa.vpi; vi++) {
+        const int b = img * fa.vpi + vi;
+        const float la = __ldg(&fa.light[b * 5]), lb = __ldg(&fa.light[b * 5 + 1]), dx = __ldg(&fa.light[b * 5 + 2]),
+                    dy = __ldg(&fa.light[b * 5 + 3]), dz = __ldg(&fa.light[b * 5 + 4]);
+        float T[3] = {0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) T[c] = grad_tex[((long)b * 3 + c) * S * S + p];
+        }
+        const float ndl = n0 * dx + n1 * dy + n2 * dz;
+        const float diff = fmaxf(ndl, 0.f);
+        const float sh = la + lb * diff;
+        // tex_c = (al_c/2 + .5) * sh * 2 - 1
+        float dsh = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            ga[c] += T[c] * sh;
+            dsh += T[c] * (al[c] + 1.0f);
+        }
+        const float ddiff = ndl >= 0.f ? dsh * lb : 0.f;
+        gn[0] += ddiff * dx; gn[1] += ddiff * dy; gn[2] += ddiff * dz;
+        float lg[5] = {dsh, dsh * diff, ddiff * n0, ddiff * n1, ddiff * n2};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            lg[k] = warp_sum(lg[k]);
+            if ((threadIdx.x & 31) == 0 && lg[k] != 0.f) atomicAdd(&grad_light[b * 5 + k], lg[k]);
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) grad_albedo[((long)img * 3 + c) * S * S + p] = ga[c];
+        float* o = grad_normal + ((long)img * S * S + p) * 3;
+        o[0] = gn[0]; o[1] = gn[1]; o[2] = gn[2];
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// mesh-texture branch (render_yaw / render_view / render_given_view with grid_sample=False)
+
+// rotate about the centroid (0,0,rcd): mm3(p - c0, M) + c0 with M = R (transpose = 0) or R^T (1)
+__device__ __forceinline__ void rotate_point(const Cam& cam, const float* R, int transpose, float p[3]) {
+    const float v0 = p[0], v1 = p[1], v2 = sub(p[2], cam.rcd);
+    float q[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float m0 = transpose ? R[j] : R[3 * j], m1 = transpose ? R[3 + j] : R[3 * j + 1],
+                    m2 = transpose ? R[6 + j] : R[3 * j + 2];
+        float acc = mul(v0, m0);
+        acc = fma_(v1, m1, acc);
+        acc = fma_(v2, m2, acc);
+        q[j] = acc;
+    }
+    p[0] = add(q[0], 0.0f); p[1] = add(q[1], 0.0f); p[2] = add(q[2], cam.rcd);
+}
+
+struct Crop {
+    int on, top, bottom, left, right;
+};
+
+// depth_to_3d_grid + crop + inverse warp (R0,t0) + rotation R1 + warp (R2,t2): renderer.py:143-192
+__global__ void __launch_bounds__(PIX_THREADS)
+k_grid3d(const Cam cam, const float* __restrict__ depth, long dstride, int H, int W, const Crop crop,
+         const float* __restrict__ R0, const float* __restrict__ t0, const float* __restrict__ R1,
+         const float* __restrict__ R2, const float* __restrict__ t2, float* __restrict__ out) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
+    const float* dimg = depth + (long)b * dstride;
+    float p[3];
+    if (crop.on) {
+        const int ys = min(max(y, crop.top), H - 1 - crop.bottom), xs = min(max(x, crop.left), W - 1 - crop.right);
+        float a[3];
+        depth_point(cam, dimg, W, xs, y, a);
+        p[0] = a[0];
+        depth_point(cam, dimg, W, x, ys, a);
+        p[1] = a[1];
+        depth_point(cam, dimg, W, xs, ys, a);
+        p[2] = a[2];
+    } else {
+        depth_point(cam, dimg, W, x, y, p);
+    }
+    if (R0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = add(p[k], -__ldg(&t0[b * 3 + k]));
+        float Rm[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&R0[b * 9 + k]);
+        rotate_point(cam, Rm, 1, p);
+    }
+    if (R1) {
+        float Rm[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&R1[b * 9 + k]);
+        rotate_point(cam, Rm, 0, p);
+    }
+    if (R2) {
+        float Rm[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&R2[b * 9 + k]);
+        rotate_point(cam, Rm, 0, p);
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = add(p[k], __ldg(&t2[b * 3 + k]));
+    }
+    float* o = out + ((long)b * H * W + pix) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+}
+
+struct Bg {
+    float c[4];
+};
+
+// utils.py:83-95 cube coefficients (rows i = i0*4 + i1*2 + i2)
+__device__ __constant__ float kCube[8][3] = {{0.5f, 0.5f, 0.5f}, {0.f, 0.f, 1.f}, {0.f, 1.f, 0.f}, {-0.5f, 0.5f, 0.5f},
+                                             {1.f, 0.f, 0.f}, {0.5f, -0.5f, 0.5f}, {0.5f, 0.5f, -0.5f}, {0.f, 0.f, 0.f}};
+
+// colour of one covered sub-pixel: [nr] forward_texture_sampling with the 2^3 cube of utils.py:98-109
+template <int C>
+__device__ __forceinline__ void rgb_subpixel(const Cam& cam, const float* __restrict__ verts_b,
+                                             const float* __restrict__ im_b, int face, int xi, int yi, float zp_key,
+                                             float eps, float out[C]) {
+    const int S = cam.S, is = 2 * S, Q = (S - 1) * (S - 1);
+    int vidx[3];
+    face_vertices(face, S, vidx);
+    float ndc[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float* p = &verts_b[(long)vidx[k] * 3];
+        const float q[3] = {p[0], p[1], p[2]};
+        project_ndc(cam, q, ndc[k]);
+    }
+    const Tri f = make_tri(ndc[0], ndc[1], ndc[2]);
+    float fi[9], w[3], zp = zp_key;
+    tri_face_inv(f, is, fi);
+    tri_weights_depth(f, fi, xi, yi, cam.near, cam.far, w, &zp);
+    const float z[3] = {f.z0, f.z1, f.z2};
+    float tif[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float v = mul(mul(w[k], 1.0f), dvd(zp, z[k]));
+        v = fmaxf(v, 0.f);
+        v = fminf(v, sub(1.0f, eps));
+        tif[k] = v;
+    }
+    // vertex colours in the order get_textures_from_im stacks them
+    const bool rev = face >= 2 * Q;
+    int fb = rev ? face - 2 * Q : face;
+    const bool second = fb >= Q;
+    if (second) fb -= Q;
+    const int qy = fb / (S - 1), qx = fb - qy * (S - 1);
+    const int p00 = qy * S + qx;
+    int cp[3];
+    if (!second) { cp[0] = p00; cp[1] = p00 + 1; cp[2] = p00 + S; }
+    else { cp[0] = p00 + S; cp[1] = p00 + 1; cp[2] = p00 + S + 1; }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const float v0 = im_b[(long)c * S * S + cp[0]], v1 = im_b[(long)c * S * S + cp[1]],
+                    v2 = im_b[(long)c * S * S + cp[2]];
+        float acc = 0.f;
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) {
+            float wt = 1.f;
+            int ti[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float fr = tif[k] - (float)(int)tif[k];
+                if (((pn >> k) & 1) == 0) { wt *= 1.f - fr; ti[k] = (int)tif[k]; }
+                else { wt *= fr; ti[k] = (int)tif[k] + 1; }
+            }
+            // fill_back copies see the cube with axes 0 and 2 swapped
+            const int ci = rev ? ti[2] * 4 + ti[1] * 2 + ti[0] : ti[0] * 4 + ti[1] * 2 + ti[2];
+            float tex = mul(kCube[ci][0], v0);
+            tex = fma_(kCube[ci][1], v1, tex);
+            tex = fma_(kCube[ci][2], v2, tex);
+            acc += wt * tex;
+        }
+        out[c] = acc;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(PIX_THREADS)
+k_resolve_rgb(const Cam cam, unsigned long long* __restrict__ zbuf, const float* __restrict__ verts3d,
+              const float* __restrict__ im, long imstride, const Bg bg, float eps, int clampv,
+              float* __restrict__ rgb, int* __restrict__ face_idx) {
+    const int S = cam.S, is = 2 * S, b = blockIdx.y;
+    const int pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= S * S) return;
+    const int i = pix / S, j = pix - i * S;
+    unsigned long long* zb = zbuf + (long)b * is * is;
+    ulonglong2* r0 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i) * is + 2 * j);
+    ulonglong2* r1 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i + 1) * is + 2 * j);
+    const ulonglong2 k0 = *r0, k1 = *r1;
+    const unsigned long long empty = zkey_empty(cam.far);
+    *r0 = make_ulonglong2(empty, empty);
+    *r1 = make_ulonglong2(empty, empty);
+    const unsigned long long keys[4] = {k0.x, k0.y, k1.x, k1.y};
+    if (face_idx) {
+        int* fo = face_idx + (long)b * is * is;
+        *reinterpret_cast<int2*>(fo + (long)(2 * i) * is + 2 * j) = make_int2(zkey_face(k0.x), zkey_face(k0.y));
+        *reinterpret_cast<int2*>(fo + (long)(2 * i + 1) * is + 2 * j) = make_int2(zkey_face(k1.x), zkey_face(k1.y));
+    }
+    const float* verts_b = verts3d + (long)b * S * S * 3;
+    const float* im_b = im + (long)b * imstride;
+    float sum[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) sum[c] = 0.f;
+#pragma unroll 1
+    for (int sp = 0; sp < 4; sp++) {
+        const int face = zkey_face(keys[sp]);
+        float col[C];
+        if (face < 0) {
+#pragma unroll
+            for (int c = 0; c < C; c++) col[c] = bg.c[c];
+        } else {
+            const int r = 2 * i + (sp >> 1), xi = 2 * j + (sp & 1);
+            rgb_subpixel<C>(cam, verts_b, im_b, face, xi, is - 1 - r, zkey_depth(keys[sp]), eps, col);
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) sum[c] += col[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        float v = sum[c] * 0.25f;
+        if (clampv) v = fminf(fmaxf(v, -1.f), 1.f);
+        rgb[((long)b * C + c) * S * S + pix] = v;
+    }
+}
+
+inline dim3 pix_grid(long npix, int batch) { return dim3((unsigned)((npix + PIX_THREADS - 1) / PIX_THREADS), batch); }
+
+inline bool bad_size(int S) { return S < 2 || S > 2048; }
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int g2s_version(void) { return 100; }
+
+const char* g2s_error_string(int code) {
+    switch (code) {
+        case G2S_OK: return "ok";
+        case G2S_ERR_NULL: return "required pointer is NULL";
+        case G2S_ERR_SHAPE: return "size out of the supported range";
+        case G2S_ERR_LAUNCH: return "CUDA launch failure";
+        case G2S_ERR_UNSUPPORTED: return "unsupported mode";
+        default: return "unknown error";
+    }
+}
+
+size_t g2s_zbuffer_bytes(int n_views, int image_size) {
+    if (n_views <= 0 || image_size <= 0) return 0;
+    return (size_t)n_views * (size_t)(2 * image_size) * (size_t)(2 * image_size) * sizeof(unsigned long long);
+}
+
+int g2s_zbuffer_init(void* zbuf, int n_views, int image_size, float far_z, void* stream) {
+    if (!zbuf) return G2S_ERR_NULL;
+    if (n_views <= 0 || bad_size(image_size)) return G2S_ERR_SHAPE;
+    const long n = (long)n_views * 4 * image_size * image_size;
+    const int blocks = (int)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
+    { Launch l_(K_ZINIT, (cudaStream_t)stream); k_zbuf_init<<<blocks, 256, 0, (cudaStream_t)stream>>>((unsigned long long*)zbuf, n, zkey_empty(far_z)); }
+    return launch_status();
+}
+
+int g2s_warp_depth_fwd(const g2s_camera* cam, const float* depth, long depth_view_stride, const float* R,
+                       const float* t, int n_views, void* zbuf, float* recon_depth, int32_t* face_idx, void* stream) {
+    if (!cam || !depth || !R || !t || !zbuf || !recon_depth) return G2S_ERR_NULL;
+    if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    const Cam c = make_cam(cam);
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, 0, st>>>(c, depth, depth_view_stride, 1, R, t,
+                                                                          nullptr, (unsigned long long*)zbuf, tiles); }
+    FusedArgs fa = {};
+    { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid((long)S * S, n_views), PIX_THREADS, 0, st>>>(c, (unsigned long long*)zbuf, recon_depth,
+                                                                             face_idx, fa); }
+    return launch_status();
+}
+
+int g2s_warp_depth_bwd(const g2s_camera* cam, const float* depth, long depth_view_stride, const float* R,
+                       const float* t, int n_views, const int32_t* face_idx, const float* recon_depth,
+                       const float* grad_recon_depth, float* grad_sub_ws, float* grad_depth,
+                       long grad_depth_view_stride, float* grad_R, float* grad_t, void* stream) {
+    if (!cam || !depth || !R || !t || !face_idx || !recon_depth || !grad_recon_depth || !grad_sub_ws || !grad_depth)
+        return G2S_ERR_NULL;
+    if ((grad_R == nullptr) != (grad_t == nullptr)) return G2S_ERR_NULL;
+    if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    const Cam c = make_cam(cam);
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long n = (long)n_views * S * S;
+    { Launch l_(K_CLAMP_GRAD, st); k_clamp_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(recon_depth, grad_recon_depth, c.clamp_lo, c.clamp_hi, n,
+                                                              grad_sub_ws); }
+    { Launch l_(K_RASTER_BWD, st); k_raster_bwd<<<dim3(tiles * tiles, n_views), SPLAT_THREADS, 0, st>>>(
+        c, depth, depth_view_stride, 1, R, t, face_idx, grad_sub_ws, grad_depth, grad_depth_view_stride, grad_R, grad_t,
+        tiles); }
+    return launch_status();
+}
+
+int g2s_warp_grid_fwd(const g2s_camera* cam, const float* depth, long depth_view_stride, const float* R,
+                      const float* t, int B, int H, int W, int inverse, float* grid, void* stream) {
+    if (!cam || !depth || !R || !t || !grid) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 2 || W < 2) return G2S_ERR_SHAPE;
+    { Launch l_(K_GRID_FWD, (cudaStream_t)stream); k_warp_grid_fwd<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(
+        make_cam(cam), depth, depth_view_stride, R, t, H, W, inverse, grid); }
+    return launch_status();
+}
+
+int g2s_warp_grid_bwd(const g2s_camera* cam, const float* depth, long depth_view_stride, const float* R,
+                      const float* t, int B, int H, int W, int inverse, const float* grad_grid, float* grad_depth,
+                      float* grad_R, float* grad_t, void* stream) {
+    if (!cam || !depth || !R || !t || !grad_grid || !grad_depth) return G2S_ERR_NULL;
+    if ((grad_R == nullptr) != (grad_t == nullptr)) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 2 || W < 2) return G2S_ERR_SHAPE;
+    { Launch l_(K_GRID_BWD, (cudaStream_t)stream); k_warp_grid_bwd<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(
+        make_cam(cam), depth, depth_view_stride, R, t, H, W, inverse, grad_grid, grad_depth, grad_R, grad_t); }
+    return launch_status();
+}
+
+int g2s_normal_fwd(const g2s_camera* cam, const float* depth, int B, int H, int W, float* normal, void* stream) {
+    if (!cam || !depth || !normal) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 3 || W < 3) return G2S_ERR_SHAPE;
+    { Launch l_(K_NORMAL_FWD, (cudaStream_t)stream); k_normal_fwd<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(make_cam(cam), depth, H, W, normal); }
+    return launch_status();
+}
+
+int g2s_normal_bwd(const g2s_camera* cam, const float* depth, int B, int H, int W, const float* grad_normal,
+                   float* grad_depth, int accumulate, void* stream) {
+    if (!cam || !depth || !grad_normal || !grad_depth) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 3 || W < 3) return G2S_ERR_SHAPE;
+    { Launch l_(K_NORMAL_BWD, (cudaStream_t)stream); k_normal_bwd<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(make_cam(cam), depth, H, W,
+                                                                                     grad_normal, grad_depth, accumulate); }
+    return launch_status();
+}
+
+int g2s_sample_fwd(const float* input, long input_batch_stride, const float* grid, int B, int C, int H, int W, int Ho,
+                   int Wo, int mode, int align_corners, float* out, void* stream) {
+    if (!input || !grid || !out) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || C <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return G2S_ERR_SHAPE;
+    if (mode != 0 && mode != 1) return G2S_ERR_UNSUPPORTED;
+    { Launch l_(K_SAMPLE_FWD, (cudaStream_t)stream); k_sample_fwd<<<pix_grid((long)Ho * Wo, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(
+        input, input_batch_stride, grid, C, H, W, Ho, Wo, mode, align_corners, out); }
+    return launch_status();
+}
+
+int g2s_sample_bwd(const float* input, long input_batch_stride, const float* grid, const float* grad_out, int B, int C,
+                   int H, int W, int Ho, int Wo, int mode, int align_corners, float* grad_input,
+                   long grad_input_batch_stride, float* grad_grid, void* stream) {
+    if (!input || !grid || !grad_out) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || C <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return G2S_ERR_SHAPE;
+    if (mode != 0 && mode != 1) return G2S_ERR_UNSUPPORTED;
+    { Launch l_(K_SAMPLE_BWD, (cudaStream_t)stream); k_sample_bwd<<<pix_grid((long)Ho * Wo, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(
+        input, input_batch_stride, grid, grad_out, C, H, W, Ho, Wo, mode, align_corners, grad_input,
+        grad_input_batch_stride, grad_grid); }
+    return launch_status();
+}
+
+int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+                         const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
+                         float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx, void* stream) {
+    if (!cam || !depth || !albedo || !R || !t || !light || !zbuf || !normal_ws || !recon_im || !recon_depth)
+        return G2S_ERR_NULL;
+    const long n_views = (long)n_images * views_per_image;
+    if (n_images <= 0 || views_per_image <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    const Cam c = make_cam(cam);
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    { Launch l_(K_NORMAL_FWD, st); k_normal_fwd<<<pix_grid((long)S * S, n_images), PIX_THREADS, 0, st>>>(c, depth, S, S, normal_ws); }
+    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles, (int)n_views), SPLAT_THREADS, 0, st>>>(
+        c, depth, (long)S * S, views_per_image, R, t, nullptr, (unsigned long long*)zbuf, tiles); }
+    FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners};
+    { Launch l_(K_RESOLVE_FUSED, st); k_resolve<true><<<pix_grid((long)S * S, (int)n_views), PIX_THREADS, 0, st>>>(c, (unsigned long long*)zbuf,
+                                                                                recon_depth, face_idx, fa); }
+    return launch_status();
+}
+
+int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+                         const float* light, int n_images, int views_per_image, int align_corners,
+                         const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
+                         const float* grad_recon_im, const float* grad_recon_depth, float* grad_sub_ws,
+                         float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R,
+                         float* grad_t, float* grad_light, void* stream) {
+    if (!cam || !depth || !albedo || !R || !t || !light || !normal_ws || !recon_depth || !face_idx || !grad_recon_im ||
+        !grad_sub_ws || !grad_tex_ws || !grad_normal_ws || !grad_depth || !grad_albedo || !grad_R || !grad_t ||
+        !grad_light)
+        return G2S_ERR_NULL;
+    const long n_views = (long)n_images * views_per_image;
+    if (n_images <= 0 || views_per_image <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    const Cam c = make_cam(cam);
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * n_views * 3 * S * S, st);
+    cudaMemsetAsync(grad_R, 0, sizeof(float) * n_views * 9, st);
+    cudaMemsetAsync(grad_t, 0, sizeof(float) * n_views * 3, st);
+    cudaMemsetAsync(grad_light, 0, sizeof(float) * n_views * 5, st);
+    FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners};
+    { Launch l_(K_BWD_PIXEL, st); k_render_bwd_pixel<<<pix_grid((long)S * S, (int)n_views), PIX_THREADS, 0, st>>>(
+        c, fa, recon_depth, grad_recon_im, grad_recon_depth, grad_sub_ws, grad_tex_ws, grad_R, grad_t); }
+    { Launch l_(K_BWD_TEX, st); k_render_bwd_tex<<<pix_grid((long)S * S, n_images), PIX_THREADS, 0, st>>>(S, fa, grad_tex_ws, grad_albedo,
+                                                                              grad_normal_ws, grad_light); }
+    { Launch l_(K_NORMAL_BWD, st); k_normal_bwd<<<pix_grid((long)S * S, n_images), PIX_THREADS, 0, st>>>(c, depth, S, S, grad_normal_ws, grad_depth, 0); }
+    { Launch l_(K_RASTER_BWD, st); k_raster_bwd<<<dim3(tiles * tiles, (int)n_views), SPLAT_THREADS, 0, st>>>(
+        c, depth, (long)S * S, views_per_image, R, t, face_idx, grad_sub_ws, grad_depth, (long)S * S, grad_R, grad_t,
+        tiles); }
+    return launch_status();
+}
+
+int g2s_grid3d_fwd(const g2s_camera* cam, const float* depth, long depth_view_stride, int B, int H, int W,
+                   const int* crop, const float* R0, const float* t0, const float* R1, const float* R2, const float* t2,
+                   float* out, void* stream) {
+    if (!cam || !depth || !out) return G2S_ERR_NULL;
+    if ((R0 == nullptr) != (t0 == nullptr) || (R2 == nullptr) != (t2 == nullptr)) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 2 || W < 2) return G2S_ERR_SHAPE;
+    Crop c = {0, 0, 0, 0, 0};
+    if (crop) {
+        c.on = 1; c.top = crop[0]; c.bottom = crop[1]; c.left = crop[2]; c.right = crop[3];
+        if (c.top < 0 || c.bottom < 0 || c.left < 0 || c.right < 0 || c.top + c.bottom >= H || c.left + c.right >= W)
+            return G2S_ERR_SHAPE;
+    }
+    { Launch l_(K_GRID3D, (cudaStream_t)stream); k_grid3d<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(make_cam(cam), depth, depth_view_stride,
+                                                                                 H, W, c, R0, t0, R1, R2, t2, out); }
+    return launch_status();
+}
+
+int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const float* im, long im_view_stride,
+                       int n_views, int C, int tex_cube_size, const float* bg, int clamp, void* zbuf, float* rgb,
+                       int32_t* face_idx, void* stream) {
+    if (!cam || !vertices3d || !im || !bg || !zbuf || !rgb) return G2S_ERR_NULL;
+    if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size) || C < 1 || C > 4) return G2S_ERR_SHAPE;
+    if (tex_cube_size != 2) return G2S_ERR_UNSUPPORTED;
+    const Cam c = make_cam(cam);
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, 0, st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
+                                                                         (unsigned long long*)zbuf, tiles); }
+    Bg b4 = {{0.f, 0.f, 0.f, 0.f}};
+    for (int i = 0; i < C; i++) b4.c[i] = bg[i];
+    const float eps = 1e-3f;  // nr.Renderer.rasterizer_eps
+    unsigned long long* zb = (unsigned long long*)zbuf;
+    const dim3 g = pix_grid((long)S * S, n_views);
+    switch (C) {
+        case 1: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<1><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
+        case 2: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<2><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
+        case 3: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<3><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
+        default: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<4><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
+    }
+    return launch_status();
+}
+
+long g2s_launch_count(void) { return g_launches.load(); }
+
+int g2s_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return G2S_OK;
+}
+
+int g2s_profile_read(int max_kernels, const char** names, float* total_ms, int* launches) {
+    if (!names || !total_ms || !launches) return G2S_ERR_NULL;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    float ms[K_COUNT] = {0};
+    int cnt[K_COUNT] = {0};
+    for (auto& r : g_prof_recs) {
+        cudaEventSynchronize(r.b);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.id] += t;
+        cnt[r.id]++;
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    int n = 0;
+    for (int k = 0; k < K_COUNT && n < max_kernels; k++)
+        if (cnt[k]) { names[n] = kKernelNames[k]; total_ms[n] = ms[k]; launches[n] = cnt[k]; n++; }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+"""torch.autograd.Functions over the C ABI of csrc/libg2s_b200.so.
+
+Each Function is the drop-in for one operator of the reference's Renderer path; the bodies are hand-written
+sm_100a kernels (csrc/g2s_kernels.cu), reached through ctypes with raw device pointers and the current CUDA
+stream.  torch is used for device memory, streams and autograd bookkeeping only.  There is no CPU or
+PyTorch fallback: non-CUDA tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gan-2d-to-3d_b200: this operator runs only on CUDA tensors (no CPU fallback)")
+
+
+def _f32c(t):
+    """contiguous fp32 view/copy"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _batched_image(t):
+    """[B,...] tensor that may be an `expand`ed (batch-stride-0) view, as model.py:260-262 passes.
+    Returns (storage tensor, batch stride in elements) without materialising the expansion."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    inner = t[0]
+    if t.shape[0] > 1 and t.stride(0) == 0 and inner.is_contiguous():
+        return inner, 0
+    t = t.contiguous()
+    return t, t[0].numel()
+
+
+def _Rt(R, t, B):
+    R = _f32c(R.expand(B, 3, 3))
+    t = _f32c(t.reshape(-1, 3).expand(B, 3))
+    return R, t
+
+
+class ZBuffer:
+    """Packed-key z-buffer workspace owned by a Renderer (one per (far) value, grown on demand).
+    The forward kernels leave it re-initialised, so it is filled only when (re)allocated."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, n_views, S, far, device):
+        key = (float(far), device)
+        need = n_views * 4 * S * S
+        cur = self.buf.get(key)
+        if cur is None or cur.numel() < need:
+            lib = _lib.load()
+            cur = torch.empty(need, dtype=torch.int64, device=device)
+            # the buffer is addressed per view, so initialise it as `n_views` views of side S
+            _lib.check(lib.g2s_zbuffer_init(_p(cur), n_views, S, far, _stream()), "g2s_zbuffer_init")
+            self.buf[key] = cur
+        return cur
+
+
+# ----------------------------------------------------------------------------------------------------------
+class WarpCanonDepthFn(torch.autograd.Function):
+    """renderer.py:116-125 warp_canon_depth (+ nr.Renderer.render_depth).  Returns (recon_depth, face_idx)."""
+
+    @staticmethod
+    def forward(ctx, depth, R, t, renderer):
+        _require_cuda(depth, R, t)
+        lib = _lib.load()
+        B, H, W = depth.shape
+        S = renderer.image_size
+        if H != S or W != S:
+            raise RuntimeError("warp_canon_depth: depth must be [B,%d,%d] (image_size of the Renderer)" % (S, S))
+        dstore, dstride = _batched_image(depth)
+        Rc, tc = _Rt(R, t, B)
+        cam = renderer._camera(depth_pass=True)
+        zbuf = renderer._zbuf.get(B, S, cam.far_z, depth.device)
+        recon = torch.empty(B, S, S, device=depth.device, dtype=torch.float32)
+        fidx = torch.empty(B, 2 * S, 2 * S, device=depth.device, dtype=torch.int32)
+        _lib.check(lib.g2s_warp_depth_fwd(ctypes.byref(cam), _p(dstore), dstride, _p(Rc), _p(tc), B, _p(zbuf),
+                                          _p(recon), _p(fidx), _stream()), "g2s_warp_depth_fwd")
+        ctx.save_for_backward(dstore, Rc, tc, fidx, recon)
+        ctx.dstride = dstride
+        ctx.renderer = renderer
+        ctx.shapes = (depth.shape, R.shape, t.shape)
+        ctx.mark_non_differentiable(fidx)
+        return recon, fidx
+
+    @staticmethod
+    def backward(ctx, g_recon, _g_fidx):
+        lib = _lib.load()
+        dstore, Rc, tc, fidx, recon = ctx.saved_tensors
+        (B, S, _), Rshape, tshape = ctx.shapes
+        cam = ctx.renderer._camera(depth_pass=True)
+        g = _f32c(g_recon)
+        ws = torch.empty(B, S, S, device=g.device, dtype=torch.float32)
+        g_depth = torch.zeros(B, S, S, device=g.device, dtype=torch.float32)
+        need_view = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gR = torch.zeros(B, 3, 3, device=g.device, dtype=torch.float32) if need_view else None
+        gt = torch.zeros(B, 3, device=g.device, dtype=torch.float32) if need_view else None
+        _lib.check(lib.g2s_warp_depth_bwd(ctypes.byref(cam), _p(dstore), ctx.dstride, _p(Rc), _p(tc), B, _p(fidx),
+                                          _p(recon), _p(g), _p(ws), _p(g_depth), S * S, _p(gR), _p(gt), _stream()),
+                   "g2s_warp_depth_bwd")
+        if need_view:
+            gR = gR.sum_to_size(Rshape)
+            gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
+        return g_depth, gR, gt, None
+
+
+class WarpGridFn(torch.autograd.Function):
+    """renderer.py:104-114 get_warped_2d_grid (inverse=False) / get_inv_warped_2d_grid (inverse=True)."""
+
+    @staticmethod
+    def forward(ctx, depth, R, t, renderer, inverse):
+        _require_cuda(depth, R, t)
+        lib = _lib.load()
+        B, H, W = depth.shape
+        dstore, dstride = _batched_image(depth)
+        Rc, tc = _Rt(R, t, B)
+        cam = renderer._camera()
+        grid = torch.empty(B, H, W, 2, device=depth.device, dtype=torch.float32)
+        _lib.check(lib.g2s_warp_grid_fwd(ctypes.byref(cam), _p(dstore), dstride, _p(Rc), _p(tc), B, H, W,
+                                         int(inverse), _p(grid), _stream()), "g2s_warp_grid_fwd")
+        ctx.save_for_backward(dstore, Rc, tc)
+        ctx.meta = (dstride, renderer, int(inverse), depth.shape, R.shape, t.shape)
+        return grid
+
+    @staticmethod
+    def backward(ctx, g_grid):
+        lib = _lib.load()
+        dstore, Rc, tc = ctx.saved_tensors
+        dstride, renderer, inverse, (B, H, W), Rshape, tshape = ctx.meta
+        cam = renderer._camera()
+        g = _f32c(g_grid)
+        g_depth = torch.empty(B, H, W, device=g.device, dtype=torch.float32)
+        need_view = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gR = torch.zeros(B, 3, 3, device=g.device, dtype=torch.float32) if need_view else None
+        gt = torch.zeros(B, 3, device=g.device, dtype=torch.float32) if need_view else None
+        _lib.check(lib.g2s_warp_grid_bwd(ctypes.byref(cam), _p(dstore), dstride, _p(Rc), _p(tc), B, H, W, inverse,
+                                         _p(g), _p(g_depth), _p(gR), _p(gt), _stream()), "g2s_warp_grid_bwd")
+        if need_view:
+            gR = gR.sum_to_size(Rshape)
+            gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
+        return g_depth, gR, gt, None, None
+
+
+class NormalFromDepthFn(torch.autograd.Function):
+    """renderer.py:127-139 get_normal_from_depth."""
+
+    @staticmethod
+    def forward(ctx, depth, renderer):
+        _require_cuda(depth)
+        lib = _lib.load()
+        d = _f32c(depth)
+        B, H, W = d.shape
+        cam = renderer._camera()
+        normal = torch.empty(B, H, W, 3, device=d.device, dtype=torch.float32)
+        _lib.check(lib.g2s_normal_fwd(ctypes.byref(cam), _p(d), B, H, W, _p(normal), _stream()), "g2s_normal_fwd")
+        ctx.save_for_backward(d)
+        ctx.renderer = renderer
+        return normal
+
+    @staticmethod
+    def backward(ctx, g_normal):
+        lib = _lib.load()
+        (d,) = ctx.saved_tensors
+        B, H, W = d.shape
+        cam = ctx.renderer._camera()
+        g = _f32c(g_normal)
+        g_depth = torch.empty(B, H, W, device=d.device, dtype=torch.float32)
+        _lib.check(lib.g2s_normal_bwd(ctypes.byref(cam), _p(d), B, H, W, _p(g), _p(g_depth), 0, _stream()),
+                   "g2s_normal_bwd")
+        return g_depth, None
+
+
+_MODES = {"bilinear": 0, "nearest": 1}
+
+
+class GridSampleFn(torch.autograd.Function):
+    """F.grid_sample(input, grid, mode, padding_mode='zeros', align_corners) as the reference calls it
+    (model.py:151, 270; renderer.py:179, 223, 241, 261, 263)."""
+
+    @staticmethod
+    def forward(ctx, inp, grid, mode, align_corners):
+        _require_cuda(inp, grid)
+        if mode not in _MODES:
+            raise RuntimeError("grid_sample: mode must be 'bilinear' or 'nearest'")
+        lib = _lib.load()
+        B, C, H, W = inp.shape
+        gB, Ho, Wo, two = grid.shape
+        if gB != B or two != 2:
+            raise RuntimeError("grid_sample: grid must be [B,Ho,Wo,2] with the batch size of input")
+        istore, istride = _batched_image(inp)
+        g = _f32c(grid)
+        out = torch.empty(B, C, Ho, Wo, device=inp.device, dtype=torch.float32)
+        _lib.check(lib.g2s_sample_fwd(_p(istore), istride, _p(g), B, C, H, W, Ho, Wo, _MODES[mode],
+                                      int(bool(align_corners)), _p(out), _stream()), "g2s_sample_fwd")
+        ctx.save_for_backward(istore, g)
+        ctx.meta = (istride, (B, C, H, W), (Ho, Wo), _MODES[mode], int(bool(align_corners)))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        istore, g = ctx.saved_tensors
+        istride, (B, C, H, W), (Ho, Wo), mode, align = ctx.meta
+        go = _f32c(g_out)
+        g_in = torch.zeros(B, C, H, W, device=go.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        g_grid = torch.empty(B, Ho, Wo, 2, device=go.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.g2s_sample_bwd(_p(istore), istride, _p(g), _p(go), B, C, H, W, Ho, Wo, mode, align, _p(g_in),
+                                      C * H * W, _p(g_grid), _stream()), "g2s_sample_bwd")
+        return g_in, g_grid, None, None
+
+
+def grid_sample(inp, grid, mode="bilinear", align_corners=False):
+    return GridSampleFn.apply(inp, grid, mode, align_corners)
+
+
+class RenderChainFn(torch.autograd.Function):
+    """The fused projected-view render (model.py:243-270): normal -> shading -> warp_canon_depth ->
+    get_inv_warped_2d_grid -> grid_sample(...).clamp(-1,1), for n_images images x views_per_image views.
+    Inputs: depth [N,S,S], albedo [N,3,S,S], R [B,3,3], t [B,3], light [B,5] = (a, b, dx, dy, dz).
+    Returns (recon_im [B,3,S,S], recon_depth [B,S,S], face_idx int32 [B,2S,2S])."""
+
+    @staticmethod
+    def forward(ctx, depth, albedo, R, t, light, renderer, views_per_image, align_corners):
+        _require_cuda(depth, albedo, R, t, light)
+        lib = _lib.load()
+        N, S, _ = depth.shape
+        B = N * views_per_image
+        if S != renderer.image_size or depth.shape[2] != S or tuple(albedo.shape) != (N, 3, S, S):
+            raise RuntimeError("render_chain: depth must be [N,S,S] and albedo [N,3,S,S] with S = image_size")
+        if R.shape[0] != B or light.shape != (B, 5):
+            raise RuntimeError("render_chain: R/t/light must have n_images * views_per_image rows")
+        d, a = _f32c(depth), _f32c(albedo)
+        Rc, tc = _Rt(R, t, B)
+        L = _f32c(light)
+        cam = renderer._camera(depth_pass=True)
+        dev = d.device
+        zbuf = renderer._zbuf.get(B, S, cam.far_z, dev)
+        normal = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
+        recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
+        recon_depth = torch.empty(B, S, S, device=dev, dtype=torch.float32)
+        fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)
+        _lib.check(lib.g2s_render_fused_fwd(ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N,
+                                            views_per_image, int(bool(align_corners)), _p(zbuf), _p(normal),
+                                            _p(recon_im), _p(recon_depth), _p(fidx), _stream()),
+                   "g2s_render_fused_fwd")
+        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx)
+        ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape)
+        ctx.mark_non_differentiable(fidx)
+        return recon_im, recon_depth, fidx
+
+    @staticmethod
+    def backward(ctx, g_im, g_depth_out, _g_fidx):
+        lib = _lib.load()
+        d, a, Rc, tc, L, normal, recon_depth, fidx = ctx.saved_tensors
+        renderer, vpi, align, Rshape, tshape = ctx.meta
+        N, S, _ = d.shape
+        B = N * vpi
+        dev = d.device
+        cam = renderer._camera(depth_pass=True)
+        gi = _f32c(g_im) if g_im is not None else torch.zeros(B, 3, S, S, device=dev)
+        gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
+        ws_sub = torch.empty(B, S, S, device=dev, dtype=torch.float32)
+        ws_tex = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
+        ws_nrm = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
+        g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)
+        g_albedo = torch.empty(N, 3, S, S, device=dev, dtype=torch.float32)
+        gR = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
+        gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
+        gL = torch.empty(B, 5, device=dev, dtype=torch.float32)
+        _lib.check(lib.g2s_render_fused_bwd(ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N, vpi, align,
+                                            _p(normal), _p(recon_depth), _p(fidx), _p(gi), _p(gd_out), _p(ws_sub),
+                                            _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR), _p(gt), _p(gL),
+                                            _stream()), "g2s_render_fused_bwd")
+        gR = gR.sum_to_size(Rshape)
+        gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
+        return g_depth, g_albedo, gR, gt, gL, None, None, None

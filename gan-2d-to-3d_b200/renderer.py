@@ -1,0 +1,253 @@
+"""Drop-in for the reference's `GAN2Shape.renderer.Renderer` (GAN2Shape/renderer/renderer.py:13-277).
+
+Same constructor, same method names, same argument meaning; every operator is a torch.autograd.Function whose
+body is a hand-written sm_100a kernel behind the C ABI in include/g2s_b200.h.  Differences that are deliberate:
+  * `get_grid` / `get_face_idx` are never materialised (the reference rebuilds them on the CPU per call);
+  * `align_corners` is explicit (the reference calls F.grid_sample without it: torch >= 1.3 means False,
+    the torch 1.2 the authors pinned meant True) -- default False = what the reference code does today;
+  * `render_chain` exposes the fused projected-view render the callers compose by hand (model.py:243-270).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib, functional as Fn
+from .utils import get_transform_matrices, get_lighting_directions
+
+EPS = 1e-7  # renderer.py:10
+
+# neural_renderer module defaults used by render_depth (the ctor's near/far reach only render_rgb)
+NR_DEPTH_NEAR, NR_DEPTH_FAR = 0.1, 100.0
+
+
+class Renderer:
+    def __init__(self, cfgs, image_size, min_depth, max_depth, device="cuda", align_corners=False):
+        """renderer.py:14-54."""
+        self.image_size = image_size
+        self.min_depth = min_depth
+        self.max_depth = max_depth
+        self.rot_center_depth = cfgs.get('rot_center_depth', (self.min_depth + self.max_depth) / 2)
+        self.fov = cfgs.get('fov', 10)
+        self.tex_cube_size = cfgs.get('tex_cube_size', 2)
+        self.renderer_min_depth = cfgs.get('renderer_min_depth', 0.1)
+        self.renderer_max_depth = cfgs.get('renderer_max_depth', 10.)
+        self.align_corners = bool(align_corners)
+        self.device = torch.device(device)
+
+        fx = (self.image_size - 1) / 2 / (math.tan(self.fov / 2 * math.pi / 180))
+        fy = (self.image_size - 1) / 2 / (math.tan(self.fov / 2 * math.pi / 180))
+        cx = (self.image_size - 1) / 2
+        cy = (self.image_size - 1) / 2
+        # K and its inverse are 3x3 one-off host work (the inverse via the same LAPACK path torch-CPU uses)
+        K = torch.tensor([[fx, 0., cx], [0., fy, cy], [0., 0., 1.]], dtype=torch.float32)
+        self._set_K(K.unsqueeze(0), torch.inverse(K).unsqueeze(0), origin=True)
+        self.background_color = [1., 1., 1.]  # renderer.py:54
+        self._zbuf = Fn.ZBuffer()
+        self.rot_mat = None
+        self.trans_xyz = None
+        _lib.load()  # fail loudly at construction when the CUDA library is missing
+
+    # -- camera state ----------------------------------------------------------------------------------
+    def _set_K(self, K_host, inv_K_host, origin=False):
+        self._K_host, self._inv_K_host = K_host.clone(), inv_K_host.clone()
+        self.K = K_host.to(self.device)
+        self.inv_K = inv_K_host.to(self.device)
+        if origin:
+            self._K_origin_host, self._inv_K_origin_host = K_host.clone(), inv_K_host.clone()
+            self.K_origin, self.inv_K_origin = self.K.clone(), self.inv_K.clone()
+            # neural_renderer captures K at construction (renderer.py:47-50); downscale_K never reaches it
+            self._K_raster_host = K_host.clone()
+        self._cams = {}
+
+    def _camera(self, depth_pass=False, rgb_pass=False):
+        """struct g2s_camera for a launch.  The grid operators use the current K / inv_K; the rasteriser uses
+        the K captured at construction (as nr.Renderer does) with near/far per pass."""
+        key = (depth_pass, rgb_pass)
+        cam = self._cams.get(key)
+        if cam is None:
+            cam = _lib.Camera()
+            Ksrc = self._K_raster_host if (depth_pass or rgb_pass) else self._K_host
+            K = Ksrc.reshape(-1).tolist()
+            iK = self._inv_K_host.reshape(-1).tolist()
+            for i in range(9):
+                cam.K[i] = K[i]
+                cam.inv_K[i] = iK[i]
+            cam.rot_center_depth = self.rot_center_depth
+            if rgb_pass:
+                cam.near_z, cam.far_z = self.renderer_min_depth, self.renderer_max_depth
+            else:
+                cam.near_z, cam.far_z = NR_DEPTH_NEAR, NR_DEPTH_FAR
+            margin = (self.max_depth - self.min_depth) / 2
+            cam.clamp_lo = self.min_depth - margin
+            cam.clamp_hi = self.max_depth + margin
+            cam.image_size = self.image_size
+            self._cams[key] = cam
+        return cam
+
+    def downscale_K(self, downscale):
+        """renderer.py:56-59 (does not reach the K the rasteriser captured, as in the reference)."""
+        if downscale > 1:
+            K = torch.cat((self._K_origin_host[:, 0:2] / downscale, self._K_origin_host[:, 2:]), dim=1)
+            self._set_K(K, torch.inverse(K[0]).unsqueeze(0))
+
+    def set_transform_matrices(self, view):
+        """renderer.py:61-62."""
+        self.rot_mat, self.trans_xyz = get_transform_matrices(view)
+
+    # -- point helpers kept for API compatibility (plain torch, not on the hot path) -------------------
+    def rotate_pts(self, pts, rot_mat):
+        """renderer.py:64-69."""
+        centroid = torch.tensor([0., 0., self.rot_center_depth], device=pts.device).view(1, 1, 3)
+        return (pts - centroid).matmul(rot_mat.transpose(2, 1)) + centroid
+
+    def translate_pts(self, pts, trans_xyz):
+        """renderer.py:71-72."""
+        return pts + trans_xyz
+
+    # -- hot-path operators -------------------------------------------------------------------------
+    def get_warped_2d_grid(self, depth):
+        """renderer.py:104-108."""
+        return Fn.WarpGridFn.apply(depth, self.rot_mat, self.trans_xyz, self, False)
+
+    def get_inv_warped_2d_grid(self, depth):
+        """renderer.py:110-114."""
+        return Fn.WarpGridFn.apply(depth, self.rot_mat, self.trans_xyz, self, True)
+
+    def warp_canon_depth(self, canon_depth, return_face_idx=False):
+        """renderer.py:116-125.  `return_face_idx=True` also returns the int32 [B,2S,2S] face-index map the
+        reference API hides (image orientation, -1 = background)."""
+        recon, fidx = Fn.WarpCanonDepthFn.apply(canon_depth, self.rot_mat, self.trans_xyz, self)
+        return (recon, fidx) if return_face_idx else recon
+
+    def get_normal_from_depth(self, depth):
+        """renderer.py:127-139."""
+        return Fn.NormalFromDepthFn.apply(depth, self)
+
+    def grid_sample(self, im, grid, mode='bilinear'):
+        """nn.functional.grid_sample as the reference's callers use it (model.py:151, 270)."""
+        return Fn.grid_sample(im, grid, mode, self.align_corners)
+
+    def render_chain(self, depth, albedo, view, light, views_per_image=None):
+        """The fused projected-view render of model.py:243-270: depth [N,S,S], albedo [N,3,S,S],
+        view [N*P,6], raw light [N*P,4] -> (recon_im [N*P,3,S,S], recon_depth [N*P,S,S], face_idx)."""
+        N = depth.shape[0]
+        B = view.shape[0]
+        P = views_per_image if views_per_image is not None else B // N
+        if N * P != B:
+            raise RuntimeError("render_chain: view must have n_images * views_per_image rows")
+        self.set_transform_matrices(view)
+        a, b, d = get_lighting_directions(light)
+        light5 = torch.cat([a, b, d], 1)
+        return Fn.RenderChainFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, self, P,
+                                      self.align_corners)
+
+    # -- sweeps -----------------------------------------------------------------------------------------
+    def _view_sample(self, im, depth, view):
+        self.set_transform_matrices(view)
+        recon_depth = self.warp_canon_depth(depth)
+        grid = self.get_inv_warped_2d_grid(recon_depth)
+        return Fn.grid_sample(im, grid, 'bilinear', self.align_corners), grid
+
+    def _grid3d(self, depth, crop_mesh=None, v_before=None, rot1=None, v_after=None):
+        """depth_to_3d_grid (+crop, inverse warp by v_before, rotation rot1, warp by v_after) -> [B,H*W,3]."""
+        lib = _lib.load()
+        B, H, W = depth.shape
+        dstore, dstride = Fn._batched_image(depth)
+        dev = depth.device
+        R0 = t0 = R1 = R2 = t2 = None
+        if v_before is not None:
+            R0, t0 = get_transform_matrices(v_before)
+            R0, t0 = Fn._Rt(R0.detach(), t0.detach(), B)
+        if rot1 is not None:
+            R1 = Fn._f32c(rot1.detach().expand(B, 3, 3))
+        if v_after is not None:
+            R2, t2 = get_transform_matrices(v_after)
+            R2, t2 = Fn._Rt(R2.detach(), t2.detach(), B)
+        crop = (ctypes.c_int * 4)(*[int(c) for c in crop_mesh]) if crop_mesh is not None else None
+        out = torch.empty(B, H * W, 3, device=dev, dtype=torch.float32)
+        _lib.check(lib.g2s_grid3d_fwd(ctypes.byref(self._camera()), Fn._p(dstore), dstride, B, H, W, crop,
+                                      Fn._p(R0), Fn._p(t0), Fn._p(R1), Fn._p(R2), Fn._p(t2), Fn._p(out),
+                                      Fn._stream()), "g2s_grid3d_fwd")
+        return out
+
+    def _render_rgb(self, vertices3d, im, clamp=True, return_face_idx=False):
+        """nr.Renderer.render_rgb(vertices, get_face_idx, get_textures_from_im(im, tex_cube_size)) +
+        clamp(-1,1) (renderer.py:194-196).  Forward only (the reference never differentiates it)."""
+        lib = _lib.load()
+        B, C, H, W = im.shape
+        S = self.image_size
+        if H != S or W != S:
+            raise RuntimeError("render_rgb: image must be [B,C,%d,%d]" % (S, S))
+        if C > 4:
+            raise RuntimeError("render_rgb: at most 4 channels")
+        istore, istride = Fn._batched_image(im.detach())
+        cam = self._camera(rgb_pass=True)
+        zbuf = self._zbuf.get(B, S, cam.far_z, im.device)
+        out = torch.empty(B, C, S, S, device=im.device, dtype=torch.float32)
+        fidx = torch.empty(B, 2 * S, 2 * S, device=im.device, dtype=torch.int32) if return_face_idx else None
+        bg = (ctypes.c_float * 4)(*([self.background_color[i % 3] for i in range(4)]))
+        _lib.check(lib.g2s_render_rgb_fwd(ctypes.byref(cam), Fn._p(vertices3d), Fn._p(istore), istride, B, C,
+                                          self.tex_cube_size, bg, int(clamp), Fn._p(zbuf), Fn._p(out), Fn._p(fidx),
+                                          Fn._stream()), "g2s_render_rgb_fwd")
+        return (out, fidx) if return_face_idx else out
+
+    def render_yaw(self, im, depth, v_before=None, v_after=None, rotations=None, maxr=90, nsample=9,
+                   grid_sample=False, crop_mesh=None):
+        """renderer.py:141-198 -> [b, t, c, h, w]."""
+        b, c, h, w = im.shape
+        if rotations is None:
+            rotations = torch.linspace(-math.pi / 180 * maxr, math.pi / 180 * maxr, nsample)
+        im_trans = []
+        for i, ri in enumerate(rotations):
+            if grid_sample:
+                view = torch.tensor([0, float(ri), 0, 0, 0, 0], device=im.device, dtype=torch.float32).view(1, 6)
+                if v_before is not None:
+                    view = view - v_before
+                warped = self._view_sample(im, depth, view.expand(b, 6) if view.shape[0] == 1 else view)[0]
+            else:
+                rot_mat_i, _ = get_transform_matrices(
+                    torch.tensor([0, float(ri), 0], device=im.device, dtype=torch.float32).view(1, 3))
+                v_after_i = None
+                if v_after is not None:
+                    v_after_i = v_after[i] if len(v_after.shape) == 3 else v_after
+                verts = self._grid3d(depth, crop_mesh, v_before, rot_mat_i, v_after_i)
+                warped = self._render_rgb(verts, im)
+            im_trans += [warped]
+        return torch.stack(im_trans, 1)
+
+    def render_view(self, im, depth, v_before=None, rotations=None, maxr=[20, 90], nsample=[5, 9],
+                    grid_sample=False):
+        """renderer.py:200-250: yaw sweep, then pitch sweep -> [b, t, c, h, w]."""
+        b, c, h, w = im.shape
+        rotations_p = torch.linspace(-math.pi / 180 * maxr[0], math.pi / 180 * maxr[0], nsample[0])
+        rotations_y = torch.linspace(-math.pi / 180 * maxr[1], math.pi / 180 * maxr[1], nsample[1])
+        im_trans = []
+        for axis, angles in ((1, rotations_y), (0, rotations_p)):
+            for a in angles:
+                r3 = [0., 0., 0.]
+                r3[axis] = float(a)
+                if grid_sample:
+                    view = torch.tensor(r3 + [0., 0., 0.], device=im.device, dtype=torch.float32).view(1, 6)
+                    if v_before is not None:
+                        view = view - v_before
+                    warped = self._view_sample(im, depth, view.expand(b, 6) if view.shape[0] == 1 else view)[0]
+                else:
+                    rot_mat_i, _ = get_transform_matrices(
+                        torch.tensor(r3, device=im.device, dtype=torch.float32).view(1, 3))
+                    warped = self._render_rgb(self._grid3d(depth, None, v_before, rot_mat_i, None), im)
+                im_trans += [warped]
+        return torch.stack(im_trans, 1)
+
+    def render_given_view(self, im, depth, view, mask=None, grid_sample=True):
+        """renderer.py:252-277."""
+        if grid_sample:
+            warped, grid = self._view_sample(im, depth, view)
+            if mask is not None:
+                return warped, Fn.grid_sample(mask, grid, 'nearest', self.align_corners)
+            return warped
+        verts = self._grid3d(depth, None, None, None, view)
+        warped = self._render_rgb(verts, im)
+        if mask is not None:
+            return warped, self._render_rgb(verts, mask)
+        return warped

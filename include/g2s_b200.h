@@ -1,0 +1,164 @@
+/*
+ * g2s_b200.h -- C ABI of libg2s_b200.so: the sm_100a CUDA implementation of GAN2Shape's
+ * depth-map renderer path (reference: GAN2Shape/renderer/renderer.py, GAN2Shape/renderer/utils.py and
+ * the external `neural_renderer` rasteriser it calls).
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it is the camera struct
+ *     (host memory, copied by value into the launch);
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or freed here;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no host sync;
+ *   - re-entrant, no global state;
+ *   - returns G2S_OK (0) or a negative G2S_ERR_* code; never throws.  The reference's neural_renderer
+ *     extension reports the same class of failures through AT_ASSERTM -> RuntimeError
+ *     (CHECK_CUDA / CHECK_CONTIGUOUS); the Python host layer turns non-zero codes into RuntimeError.
+ *   - all tensors are contiguous fp32 (or int32 where stated), batch-major, row-major.
+ *
+ * Geometry conventions: S = image_size; the rasteriser works at is = 2S sub-pixels per side
+ * (neural_renderer anti_aliasing=True, the reference keeps the default); the mesh is the regular grid
+ * of utils.py:76-80 over an S x S depth map with fill_back=True: 4(S-1)^2 faces.  Face-index maps
+ * are int32 [n_views, 2S, 2S] in IMAGE orientation (row 0 = top), -1 where no face covers the
+ * sub-pixel.
+ */
+#ifndef G2S_B200_H
+#define G2S_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2S_OK 0
+#define G2S_ERR_NULL (-1)        /* a required pointer is NULL */
+#define G2S_ERR_SHAPE (-2)       /* a size is out of the supported range */
+#define G2S_ERR_LAUNCH (-3)      /* cudaGetLastError() reported a launch failure */
+#define G2S_ERR_UNSUPPORTED (-4) /* mode / flag value not implemented */
+
+/* State of one Renderer object: renderer.py:14-54 (K, inv_K, rot_center_depth, image_size) plus the
+ * rasteriser constants neural_renderer would hold (near/far) and warp_canon_depth's clamp range
+ * (renderer.py:122-124). */
+typedef struct g2s_camera {
+    float K[9];
+    float inv_K[9];
+    float rot_center_depth;
+    float near_z;    /* render_depth: 0.1 (nr module default); render_rgb: renderer_min_depth */
+    float far_z;     /* render_depth: 100 (nr module default); render_rgb: renderer_max_depth */
+    float clamp_lo;  /* min_depth - margin */
+    float clamp_hi;  /* max_depth + margin */
+    int32_t image_size;
+} g2s_camera;
+
+int g2s_version(void);
+const char *g2s_error_string(int code);
+
+/* ---- z-buffer workspace -------------------------------------------------------------------
+ * One packed 64-bit key (zp bits << 32 | face index) per sub-pixel: n_views * (2S)^2 * 8 bytes.
+ * It must be initialised once with g2s_zbuffer_init; every forward call leaves it re-initialised. */
+size_t g2s_zbuffer_bytes(int n_views, int image_size);
+int g2s_zbuffer_init(void *zbuf, int n_views, int image_size, float far_z, void *stream);
+
+/* ---- warp_canon_depth: renderer.py:116-125 (+ nr.Renderer.render_depth, renderer.py:120) -------
+ * depth: [*, S, S] with `depth_view_stride` floats between consecutive views (0 = one depth map
+ * shared by all views, the `expand`ed tensor of model.py:260-262); R [n_views,3,3], t [n_views,3].
+ * Outputs: recon_depth [n_views,S,S] (clamped), face_idx int32 [n_views,2S,2S]. */
+int g2s_warp_depth_fwd(const g2s_camera *cam, const float *depth, long depth_view_stride, const float *R,
+                       const float *t, int n_views, void *zbuf, float *recon_depth, int32_t *face_idx,
+                       void *stream);
+
+/* Backward of the above: neural_renderer's backward_depth_map (approximate x/y gradient) chained
+ * through flip / 2x2 average / clamp on one side and gather / projection / rotation on the other.
+ * grad_depth is ACCUMULATED (caller zero-fills) with `grad_depth_view_stride` floats between views
+ * (0 = sum over views into one [S,S] map); grad_R [n_views,3,3] and grad_t [n_views,3] are
+ * ACCUMULATED too (NULL to skip both). */
+int g2s_warp_depth_bwd(const g2s_camera *cam, const float *depth, long depth_view_stride, const float *R,
+                       const float *t, int n_views, const int32_t *face_idx, const float *recon_depth,
+                       const float *grad_recon_depth, float *grad_sub_ws, float *grad_depth,
+                       long grad_depth_view_stride, float *grad_R, float *grad_t, void *stream);
+
+/* ---- get_warped_2d_grid / get_inv_warped_2d_grid: renderer.py:104-114 ---------------------------
+ * depth [B,H,W] (stride as above), R/t [B,..] -> grid [B,H,W,2].  inverse != 0 selects the inverse warp. */
+int g2s_warp_grid_fwd(const g2s_camera *cam, const float *depth, long depth_view_stride, const float *R,
+                      const float *t, int B, int H, int W, int inverse, float *grid, void *stream);
+/* grad_depth [B,H,W] is WRITTEN; grad_R / grad_t ACCUMULATED (NULL to skip both). */
+int g2s_warp_grid_bwd(const g2s_camera *cam, const float *depth, long depth_view_stride, const float *R,
+                      const float *t, int B, int H, int W, int inverse, const float *grad_grid,
+                      float *grad_depth, float *grad_R, float *grad_t, void *stream);
+
+/* ---- get_normal_from_depth: renderer.py:127-139 -------------------------------------------------
+ * depth [B,H,W] -> normal [B,H,W,3]; backward WRITES grad_depth [B,H,W]. */
+int g2s_normal_fwd(const g2s_camera *cam, const float *depth, int B, int H, int W, float *normal, void *stream);
+int g2s_normal_bwd(const g2s_camera *cam, const float *depth, int B, int H, int W, const float *grad_normal,
+                   float *grad_depth, int accumulate, void *stream);
+
+/* ---- grid_sample as the reference uses it: model.py:151,270; renderer.py:179,223,241,261,263 -----
+ * input [B,C,H,W], grid [B,Ho,Wo,2] -> out [B,C,Ho,Wo]; zeros padding.
+ * mode: 0 = bilinear, 1 = nearest.  `input_batch_stride` = floats between batch items of input
+ * (0 = one image broadcast over the batch).  Backward: grad_input ACCUMULATED (caller zero-fills; NULL to
+ * skip), grad_grid WRITTEN (NULL to skip; zeros for nearest). */
+int g2s_sample_fwd(const float *input, long input_batch_stride, const float *grid, int B, int C, int H, int W,
+                   int Ho, int Wo, int mode, int align_corners, float *out, void *stream);
+int g2s_sample_bwd(const float *input, long input_batch_stride, const float *grid, const float *grad_out, int B,
+                   int C, int H, int W, int Ho, int Wo, int mode, int align_corners, float *grad_input,
+                   long grad_input_batch_stride, float *grad_grid, void *stream);
+
+/* ---- the fused projected-view render ("chain C", model.py:243-270) -------------------------------
+ * For image i (n_images of them) and its views_per_image views b:
+ *   normal   = get_normal_from_depth(depth[i])                    (renderer.py:127-139)
+ *   texture  = shade(normal, light[b], albedo[i])                 (model.py:355-360)
+ *   recon_depth[b] = warp_canon_depth(depth[i]; R[b], t[b])       (renderer.py:116-125)
+ *   grid     = get_inv_warped_2d_grid(recon_depth[b])             (renderer.py:110-114)
+ *   recon_im[b] = grid_sample(texture, grid).clamp(-1, 1)         (model.py:270)
+ * light [n_views,5] = (ambient a, diffuse b, direction dx,dy,dz) as get_lighting_directions returns.
+ * Workspaces: zbuf (g2s_zbuffer_bytes), normal_ws [n_images,S,S,3].
+ * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S]. */
+int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
+                         const float *t, const float *light, int n_images, int views_per_image,
+                         int align_corners, void *zbuf, float *normal_ws, float *recon_im, float *recon_depth,
+                         int32_t *face_idx, void *stream);
+
+/* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
+ * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [n_views,S,S],
+ * grad_tex_ws [n_views,3,S,S] (zero-filled by the call), grad_normal_ws [n_images,S,S,3].
+ * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
+ * grad_t [n_views,3], grad_light [n_views,5]. */
+int g2s_render_fused_bwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
+                         const float *t, const float *light, int n_images, int views_per_image,
+                         int align_corners, const float *normal_ws, const float *recon_depth,
+                         const int32_t *face_idx, const float *grad_recon_im, const float *grad_recon_depth,
+                         float *grad_sub_ws, float *grad_tex_ws, float *grad_normal_ws, float *grad_depth,
+                         float *grad_albedo, float *grad_R, float *grad_t, float *grad_light, void *stream);
+
+/* ---- mesh-texture render: nr.Renderer.render_rgb as renderer.py:196,230,248,272,275 call it ------
+ * vertices3d [n_views,S*S,3] (already rotated/translated 3-D grid), im [*,C,S,S] per-vertex colours
+ * (tex_cube_size 2: perspective-correct barycentric blend of the three vertex colours; 1: one colour
+ * per face) with `im_view_stride` floats between views (0 = shared), background colour bg[C] (host).
+ * Output rgb [n_views,C,S,S] = 2x2 mean of the 2S x 2S render, then clamp(-1,1) when clamp != 0.
+ * face_idx (may be NULL) as above.  C <= 4. */
+int g2s_render_rgb_fwd(const g2s_camera *cam, const float *vertices3d, const float *im, long im_view_stride,
+                       int n_views, int C, int tex_cube_size, const float *bg, int clamp, void *zbuf,
+                       float *rgb, int32_t *face_idx, void *stream);
+
+/* ---- 3-D grid helpers used by render_yaw / render_view / render_given_view ----------------------
+ * depth_to_3d_grid (renderer.py:74-80) followed by an optional inverse warp by (R0,t0)
+ * (renderer.py:164-167), then a forward rotation R1 (renderer.py:181-183) and optional (R2,t2)
+ * (renderer.py:185-192).  Any of the transforms may be NULL.  crop = {top,bottom,left,right} host
+ * ints or NULL (renderer.py:145-158).  out [B,H*W,3]. */
+int g2s_grid3d_fwd(const g2s_camera *cam, const float *depth, long depth_view_stride, int B, int H, int W,
+                   const int *crop, const float *R0, const float *t0, const float *R1, const float *R2,
+                   const float *t2, float *out, void *stream);
+
+/* ---- instrumentation (bench.py / tests; not part of the reference surface) ---------------------------
+ * g2s_launch_count: kernels launched by this library since it was loaded.
+ * g2s_profile_enable(1): record a CUDA event pair around every kernel launch on its stream;
+ * g2s_profile_read: waits for the recorded events, returns the number of distinct kernels n (<= max_kernels)
+ * and fills names[n], total_ms[n], launches[n]; clears the records. */
+long g2s_launch_count(void);
+int g2s_profile_enable(int on);
+int g2s_profile_read(int max_kernels, const char **names, float *total_ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2S_B200_H */

@@ -1,0 +1,71 @@
+"""Pins the oracle (oracle/renderer_oracle.py) against the reference's own, unmodified renderer.py / utils.py run on
+torch-CPU (oracle/ref_shim.py), and against the committed golden vectors that the same reference code produced.
+The reference tree only exists in the build container; the golden part runs everywhere."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, oracle_renderer, rel_err
+from oracle import nr_port, ref_shim, renderer_oracle as ro
+from g2s_b200 import synthetic
+
+needs_ref = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+
+
+def _ref_utils():
+    import sys
+    ref_shim.load()
+    return sys.modules["_g2s_reference_renderer.utils"]
+
+
+@needs_ref
+@pytest.mark.parametrize("S,P,rot", [(16, 3, 60.0), (32, 2, 200.0)])
+def test_oracle_bit_exact_vs_reference(S, P, rot):
+    case = synthetic.make_case(S, P, seed=5, rot_deg=rot)
+    ref, orc = ref_shim.make_renderer(S), oracle_renderer(S)
+    assert torch.equal(ref.K, orc.K) and torch.equal(ref.inv_K, orc.inv_K)
+    ref.set_transform_matrices(case["view"]); orc.set_transform_matrices(case["view"])
+    assert torch.equal(ref.rot_mat, orc.rot_mat) and torch.equal(ref.trans_xyz, orc.trans_xyz)
+    d = case["depth"].expand(P, S, S)
+    a = ref.warp_canon_depth(d); fa = nr_port.LAST["face_index_map"].clone()
+    b = orc.warp_canon_depth(d); fb = nr_port.LAST["face_index_map"].clone()
+    assert torch.equal(a, b) and torch.equal(fa, fb)
+    assert torch.equal(ref.get_inv_warped_2d_grid(a), orc.get_inv_warped_2d_grid(b))
+    assert torch.equal(ref.get_warped_2d_grid(d), orc.get_warped_2d_grid(d))
+    assert torch.allclose(ref.get_normal_from_depth(case["depth"]), orc.get_normal_from_depth(case["depth"]), atol=3e-7)
+    assert torch.equal(_ref_utils().get_face_idx(2, S, S), ro.get_face_idx(2, S, S))
+    im = case["albedo"]
+    assert torch.equal(_ref_utils().get_textures_from_im(im, 2), ro.get_textures_from_im(im, 2))
+    with torch.no_grad():
+        ya = ref.render_yaw(im, case["depth"], maxr=30, nsample=2)
+        yb = orc.render_yaw(im, case["depth"], maxr=30, nsample=2)
+        assert torch.equal(ya, yb)
+        ga = ref.render_given_view(im.expand(P, 3, S, S), d, case["view"], mask=torch.ones(P, 1, S, S))
+        gb = orc.render_given_view(im.expand(P, 3, S, S), d, case["view"], mask=torch.ones(P, 1, S, S))
+        assert torch.equal(ga[0], gb[0]) and torch.equal(ga[1], gb[1])
+
+
+@pytest.mark.parametrize("name", ["s16_p3", "s32_p2", "s32_p2_wide"])
+def test_oracle_vs_golden(name):
+    g = golden(name)
+    S, P = g["depth"].shape[-1], g["view"].shape[0]
+    orc = oracle_renderer(S)
+    depth = torch.tensor(g["depth"]).requires_grad_(True)
+    albedo = torch.tensor(g["albedo"]).requires_grad_(True)
+    view = torch.tensor(g["view"]).requires_grad_(True)
+    light = torch.tensor(g["light"]).requires_grad_(True)
+    out = orc.render_chain(depth, albedo, view, light)
+    assert np.array_equal(nr_port.LAST["face_index_map"].flip(1).numpy(), g["face_idx"])
+    assert np.array_equal(out["recon_depth"].detach().numpy(), g["recon_depth"])
+    assert np.array_equal(out["grid"].detach().numpy(), g["inv_grid"])
+    assert rel_err(out["normal"].detach(), g["normal"]) < 1e-6
+    assert rel_err(out["recon_im"].detach(), g["recon_im"]) < 1e-6
+    (out["recon_im"] * torch.tensor(g["cotangent"])).sum().backward()
+    assert rel_err(depth.grad, g["grad_depth"]) < 1e-5
+    assert rel_err(albedo.grad, g["grad_albedo"]) < 1e-5
+    assert rel_err(view.grad, g["grad_view"]) < 1e-5
+    assert rel_err(light.grad, g["grad_light"]) < 1e-5
+    with torch.no_grad():
+        yaw = orc.render_yaw(torch.tensor(g["albedo"]), torch.tensor(g["depth"]), maxr=40, nsample=3)
+    assert rel_err(yaw, g["render_yaw"]) < 1e-6
