@@ -65,3 +65,12 @@ def emu_cam(orc, S, near=0.1, far=100.0):
 
 def vp(t):
     return ctypes.c_void_p(t.data_ptr())
+
+
+def close_except_few(a, b, tol=1e-5, frac=2e-3):
+    """For whole-path comparisons where R is computed by the CUDA libm (sin/cos differ from the CPU's by an ulp):
+    a handful of rounding-decided sub-pixels may pick the neighbouring face, which changes isolated output pixels.
+    Every other element must agree to `tol` (relative to max|b|); at most `frac` of the elements may differ more."""
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    bad = (a - b).abs() > tol * b.abs().max().clamp_min(1e-30)
+    return bad.double().mean().item() <= frac
