@@ -14,7 +14,7 @@
 #include <vector>
 
 #include "../../include/g2s_b200.h"
-#include "g2s_raster.cuh"
+#include "g2s_splat.cuh"
 
 using namespace g2s;
 
@@ -88,18 +88,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int N, int THREADS>
 __device__ __forceinline__ void block_accumulate(float (&v)[N], float* dst) {
     __shared__ float red[N * (THREADS / 32)];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lin = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = lin & 31, warp = lin >> 5;
 #pragma unroll
     for (int k = 0; k < N; k++) {
         const float s = warp_sum(v[k]);
         if (lane == 0) red[warp * N + k] = s;
     }
     __syncthreads();
-    if (threadIdx.x < N) {
+    if (lin < N) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < THREADS / 32; w++) s += red[w * N + threadIdx.x];
-        if (s != 0.f) atomicAdd(&dst[threadIdx.x], s);
+        for (int w = 0; w < THREADS / 32; w++) s += red[w * N + lin];
+        if (s != 0.f) atomicAdd(&dst[lin], s);
     }
     __syncthreads();
 }
@@ -112,116 +113,35 @@ __global__ void k_zbuf_init(unsigned long long* zb, long n, unsigned long long k
     for (; i < n; i += stride) zb[i] = key;
 }
 
-// Projected (u, v, z) of the tile's vertices -> shared memory.
-template <bool FROM_VERTS>
-__device__ __forceinline__ void tile_project(const Cam& cam, const float* __restrict__ depth_b,
-                                             const float* __restrict__ verts_b, const float* sRt, int ty0,
-                                             int tx0, float* sv) {
-    const int S = cam.S;
-    for (int i = threadIdx.x; i < TV * TV; i += SPLAT_THREADS) {
-        const int vy = ty0 + i / TV, vx = tx0 + i % TV;
-        float ndc[3] = {0.f, 0.f, 0.f};
-        if (vy < S && vx < S) {
-            float q[3];
-            if (FROM_VERTS) {
-                const float* p = &verts_b[((long)vy * S + vx) * 3];
-                q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
-            } else {
-                float ray[3];
-                pixel_ray(cam, vx, vy, ray);
-                warp_point(cam, sRt, sRt + 9, ray, depth_b[vy * S + vx], q);
-            }
-            project_ndc(cam, q, ndc);
-        }
-        sv[i * 3 + 0] = ndc[0];
-        sv[i * 3 + 1] = ndc[1];
-        sv[i * 3 + 2] = ndc[2];
-    }
-}
-
-__device__ __forceinline__ void splat_one(const Tri& f, float* fi, bool& have_fi, int xi, int yi, float xp, float yp,
-                                          int is, float near, float far, uint32_t face, unsigned long long* zb) {
-    float w[3], zp;
-    if (tri_sample(f, fi, have_fi, xi, yi, xp, yp, is, near, far, w, &zp))
-        atomicMin(&zb[(long)(is - 1 - yi) * is + xi], zkey_pack(zp, face));
-}
-
-// Forward rasterisation of the grid mesh of one view into the packed-key z-buffer.
+// Forward rasterisation of the grid mesh of one view into the packed-key z-buffer (g2s_splat.cuh).
 // grid = (tiles, n_views), block = TILE*TILE threads (one per quad).
 template <bool FROM_VERTS>
-__global__ void __launch_bounds__(SPLAT_THREADS)
+__global__ void __launch_bounds__(SPLAT_THREADS, 3)
 k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
         const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
-        int tiles_x) {
-    __shared__ float sv[TV * TV * 3];
-    __shared__ float sRt[12];
-    __shared__ unsigned short squeue[SPLAT_THREADS * 4];
-    __shared__ int sqn;
-    const int tid = threadIdx.x, b = blockIdx.y, S = cam.S, is = 2 * S;
+        int tiles_x, int view0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
+    const int tid = threadIdx.x, bl = blockIdx.y, b = view0 + bl, S = cam.S, is = 2 * S;
     const int ty0 = (blockIdx.x / tiles_x) * TILE, tx0 = (blockIdx.x % tiles_x) * TILE;
     if (!FROM_VERTS) {
-        if (tid < 9) sRt[tid] = R[b * 9 + tid];
-        else if (tid < 12) sRt[tid] = t[b * 3 + tid - 9];
+        if (tid < 9) sm.sRt[tid] = R[b * 9 + tid];
+        else if (tid < 12) sm.sRt[tid] = t[b * 3 + tid - 9];
     }
-    if (tid == 0) sqn = 0;
+    if (tid == 0) sm.n_hq = sm.n_fq = sm.n_lq = 0;
     __syncthreads();
     tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
-                             FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, sRt, ty0, tx0, sv);
+                             FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, sm.sRt, ty0, tx0, sm.sv);
     __syncthreads();
-
-    unsigned long long* zb = zbuf + (long)b * is * is;
-    const int Q = (S - 1) * (S - 1);
-    const int qy = tid / TILE, qx = tid % TILE;
-    if (ty0 + qy < S - 1 && tx0 + qx < S - 1) {
-        const int qid = (ty0 + qy) * (S - 1) + tx0 + qx;
-#pragma unroll 1
-        for (int w = 0; w < 4; w++) {
-            const Tri f = tile_winding(sv, qy, qx, w);
-            if (tri_is_back(f)) continue;
-            BBox bb;
-            if (!tri_bbox(f, is, bb)) continue;
-            const int n = (bb.x1 - bb.x0 + 1) * (bb.y1 - bb.y0 + 1);
-            if (n > SMALL_BOX) {
-                squeue[atomicAdd(&sqn, 1)] = (unsigned short)(tid * 4 + w);
-                continue;
-            }
-            float fi[9];
-            bool have_fi = false;
-            const uint32_t face = (uint32_t)(w * Q + qid);
-            for (int yi = bb.y0; yi <= bb.y1; yi++) {
-                const float yp = pix_center_ndc(yi, is);
-                for (int xi = bb.x0; xi <= bb.x1; xi++)
-                    splat_one(f, fi, have_fi, xi, yi, pix_center_ndc(xi, is), yp, is, cam.near, cam.far, face, zb);
-            }
-        }
-    }
-    __syncthreads();
-    // large faces: one warp per face, lanes stride over the bounding box
-    const int nq = sqn, lane = tid & 31;
-    for (int e = tid >> 5; e < nq; e += SPLAT_THREADS / 32) {
-        const int item = squeue[e], qt = item >> 2, w = item & 3;
-        const int fqy = qt / TILE, fqx = qt % TILE;
-        const Tri f = tile_winding(sv, fqy, fqx, w);
-        BBox bb;
-        tri_bbox(f, is, bb);
-        const int bw = bb.x1 - bb.x0 + 1, n = bw * (bb.y1 - bb.y0 + 1);
-        const uint32_t face = (uint32_t)(w * Q + (ty0 + fqy) * (S - 1) + tx0 + fqx);
-        float fi[9];
-        bool have_fi = false;
-        for (int idx = lane; idx < n; idx += 32) {
-            const int yi = bb.y0 + idx / bw, xi = bb.x0 + idx % bw;
-            splat_one(f, fi, have_fi, xi, yi, pix_center_ndc(xi, is), pix_center_ndc(yi, is), is, cam.near, cam.far,
-                      face, zb);
-        }
-    }
+    FwdOps ops;
+    ops.zb = zbuf + (long)bl * is * is;
+    ops.near = cam.near; ops.far = cam.far; ops.is = is;
+    ops.pc.init(is);
+    tile_rasterise(sm, ops, cam, ty0, tx0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // shading + bilinear sampling (model.py:355-360, 270)
-
-struct LightP {
-    float a, b, dx, dy, dz;
-};
 
 __device__ __forceinline__ bool bilinear_setup(float gx, float gy, int W, int H, int align, int& x0, int& y0,
                                                float& tx, float& ty) {
@@ -233,19 +153,6 @@ __device__ __forceinline__ bool bilinear_setup(float gx, float gy, int W, int H,
     return true;
 }
 
-// shading terms at one texel; tex[c] = (albedo/2+.5)*shade*2-1
-__device__ __forceinline__ void shade_texel(const float* __restrict__ normal_img, const float* __restrict__ albedo_img,
-                                            int HW, int p, const LightP& L, float tex[3], float* shade_out,
-                                            float* ndotl_out) {
-    const float n0 = normal_img[p * 3 + 0], n1 = normal_img[p * 3 + 1], n2 = normal_img[p * 3 + 2];
-    const float ndl = n0 * L.dx + n1 * L.dy + n2 * L.dz;
-    const float sh = L.a + L.b * fmaxf(ndl, 0.f);
-#pragma unroll
-    for (int c = 0; c < 3; c++) tex[c] = (albedo_img[c * HW + p] * 0.5f + 0.5f) * sh * 2.0f - 1.0f;
-    *shade_out = sh;
-    *ndotl_out = ndl;
-}
-
 struct FusedArgs {
     const float* R;
     const float* t;
@@ -255,19 +162,78 @@ struct FusedArgs {
     float* recon_im;      // [n_views,3,S,S]
     int vpi;
     int align;
+    int view0;            // first view of this launch (chunked launches)
 };
 
+constexpr int PBX = 64, PBY = 4;   // pixel-kernel block: 64 columns x 4 rows
+
+// The 4 bilinear taps of one sample, clamped so that every load is unconditional (one round trip);
+// out-of-range taps get weight 0 (zeros padding).
+struct Taps {
+    int p[4];
+    float w[4];
+    float wx[4], wy[4];   // per-tap x / y weights (for the grid gradient)
+    bool any;
+};
+
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int W, int H, int align) {
+    Taps tp;
+    int x0 = 0, y0 = 0;
+    float tx = 0.f, ty = 0.f;
+    tp.any = bilinear_setup(gx, gy, W, H, align, x0, y0, tx, ty);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+        const bool ok = tp.any && xx >= 0 && xx < W && yy >= 0 && yy < H;
+        tp.p[k] = min(max(yy, 0), H - 1) * W + min(max(xx, 0), W - 1);
+        tp.wx[k] = ok ? ((k & 1) ? tx : 1.f - tx) : 0.f;
+        tp.wy[k] = ok ? ((k >> 1) ? ty : 1.f - ty) : 0.f;
+        tp.w[k] = tp.wx[k] * tp.wy[k];
+    }
+    return tp;
+}
+
+// shaded texture of the 4 taps: tex[k][c] = (albedo/2+.5) * (a + b*max(0, n.l)) * 2 - 1
+__device__ __forceinline__ void shade_taps(const float* __restrict__ nimg, const float* __restrict__ aimg, int HW,
+                                           const Taps& tp, const float* L, float tex[4][3]) {
+    float n[4][3], al[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            n[k][c] = __ldg(&nimg[tp.p[k] * 3 + c]);
+            al[k][c] = __ldg(&aimg[c * HW + tp.p[k]]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float ndl = n[k][0] * L[2] + n[k][1] * L[3] + n[k][2] * L[4];
+        const float sh = L[0] + L[1] * fmaxf(ndl, 0.f);
+#pragma unroll
+        for (int c = 0; c < 3; c++) tex[k][c] = (al[k][c] * 0.5f + 0.5f) * sh * 2.0f - 1.0f;
+    }
+}
+
 // z-buffer resolve: face-index map, flip + 2x2 mean + clamp -> recon_depth, z-buffer reset; when FUSED
-// also inverse warp grid + shaded bilinear sampling -> recon_im.  One thread per output pixel.
+// also inverse warp grid + shaded bilinear sampling -> recon_im.  One thread per output pixel,
+// block = 64 columns x 4 rows, grid = (cols, rows, views).
 template <bool FUSED>
-__global__ void __launch_bounds__(PIX_THREADS)
+__global__ void __launch_bounds__(PBX * PBY)
 k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restrict__ recon_depth,
           int* __restrict__ face_idx, const FusedArgs fa) {
-    const int S = cam.S, is = 2 * S, b = blockIdx.y;
-    const int pix = blockIdx.x * PIX_THREADS + threadIdx.x;
-    if (pix >= S * S) return;
-    const int i = pix / S, j = pix - i * S;
-    unsigned long long* zb = zbuf + (long)b * is * is;
+    __shared__ float sview[17];   // R[9], t[3], light[5]
+    const int S = cam.S, is = 2 * S, bl = blockIdx.z, b = fa.view0 + bl;
+    if (FUSED) {
+        const int k = threadIdx.y * PBX + threadIdx.x;
+        if (k < 9) sview[k] = fa.R[b * 9 + k];
+        else if (k < 12) sview[k] = fa.t[b * 3 + k - 9];
+        else if (k < 17) sview[k] = fa.light[b * 5 + k - 12];
+        __syncthreads();
+    }
+    const int j = blockIdx.x * PBX + threadIdx.x, i = blockIdx.y * PBY + threadIdx.y;
+    if (j >= S || i >= S) return;
+    const int pix = i * S + j;
+    unsigned long long* zb = zbuf + (long)bl * is * is;
     ulonglong2* r0 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i) * is + 2 * j);
     ulonglong2* r1 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i + 1) * is + 2 * j);
     const ulonglong2 k0 = *r0, k1 = *r1;
@@ -284,37 +250,18 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
     recon_depth[(long)b * S * S + pix] = rd;
     if (FUSED) {
         const int img = b / fa.vpi;
-        float Rm[9], tv[3], ray[3], q[3], v[3], g[2];
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&fa.R[b * 9 + k]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) tv[k] = __ldg(&fa.t[b * 3 + k]);
+        float ray[3], q[3], v[3], g[2];
         pixel_ray(cam, j, i, ray);
-        inv_warp_point(cam, Rm, tv, ray, rd, q, v);
+        inv_warp_point(cam, sview, sview + 9, ray, rd, q, v);
         point_to_grid(cam, q, S, S, g);
-        LightP L;
-        L.a = __ldg(&fa.light[b * 5 + 0]); L.b = __ldg(&fa.light[b * 5 + 1]);
-        L.dx = __ldg(&fa.light[b * 5 + 2]); L.dy = __ldg(&fa.light[b * 5 + 3]); L.dz = __ldg(&fa.light[b * 5 + 4]);
-        const float* nimg = fa.normal + (long)img * S * S * 3;
-        const float* aimg = fa.albedo + (long)img * S * S * 3;
-        float out[3] = {0.f, 0.f, 0.f};
-        int x0, y0;
-        float tx, ty;
-        if (bilinear_setup(g[0], g[1], S, S, fa.align, x0, y0, tx, ty)) {
+        const Taps tp = make_taps(g[0], g[1], S, S, fa.align);
+        float tex[4][3];
+        shade_taps(fa.normal + (long)img * S * S * 3, fa.albedo + (long)img * S * S * 3, S * S, tp, sview + 12, tex);
 #pragma unroll
-            for (int tap = 0; tap < 4; tap++) {
-                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
-                if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
-                const float wgt = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
-                float tex[3], sh, ndl;
-                shade_texel(nimg, aimg, S * S, yy * S + xx, L, tex, &sh, &ndl);
-#pragma unroll
-                for (int c = 0; c < 3; c++) out[c] += wgt * tex[c];
-            }
+        for (int c = 0; c < 3; c++) {
+            const float o = tp.w[0] * tex[0][c] + tp.w[1] * tex[1][c] + tp.w[2] * tex[2][c] + tp.w[3] * tex[3][c];
+            fa.recon_im[((long)b * 3 + c) * S * S + pix] = fminf(fmaxf(o, -1.f), 1.f);
         }
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-            fa.recon_im[((long)b * 3 + c) * S * S + pix] = fminf(fmaxf(out[c], -1.f), 1.f);
     }
 }
 
@@ -590,119 +537,48 @@ __global__ void k_clamp_grad(const float* __restrict__ recon_depth, const float*
     g_sub[i] = (rd > lo && rd < hi) ? 0.25f * grad[i] : 0.f;
 }
 
-// per-face accumulation of A_k = sum over the sub-pixels this face won of g * w_k * zp^2
-__device__ __forceinline__ void bwd_one(const Tri& f, float* fi, bool& have_fi, int xi, int yi, int is,
-                                        const int* __restrict__ fmap, const float* __restrict__ gsub, int S,
-                                        int face, float A[3], const Cam& cam) {
-    const int r = is - 1 - yi;
-    if (fmap[(long)r * is + xi] != face) return;
-    const float g = gsub[(r >> 1) * S + (xi >> 1)];
-    if (g == 0.f) return;
-    if (!have_fi) {
-        tri_face_inv(f, is, fi);
-        have_fi = true;
-    }
-    float w[3], zp = 0.f;
-    tri_weights_depth(f, fi, xi, yi, cam.near, cam.far, w, &zp);
-    const float s = g * zp * zp;
-    A[0] += s * w[0]; A[1] += s * w[1]; A[2] += s * w[2];
-}
+struct BwdSmem {
+    TileSmem t;
+    float sA[NSLOT * 3];
+    float sg[TV * TV * 3];
+};
 
-// scatter one face's gradient to its three vertices' (u,v,z) accumulators in shared memory
-__device__ __forceinline__ void bwd_face_scatter(const Tri& f, const float* fi, const float A[3], int is, float* sg,
-                                                 int qy, int qx, int w) {
-    // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
-    const float t0 = -(fi[0] / f.z0 + fi[3] / f.z1 + fi[6] / f.z2);
-    const float t1 = -(fi[1] / f.z0 + fi[4] / f.z1 + fi[7] / f.z2);
-    const float hs = 0.5f * (float)is;
-    const float z[3] = {f.z0, f.z1, f.z2};
-    // vertex slots of the winding (same order as tile_winding)
-    const int a = (qy * TV + qx) * 3, b = ((qy + 1) * TV + qx) * 3, c = (qy * TV + qx + 1) * 3,
-              d = ((qy + 1) * TV + qx + 1) * 3;
-    int v[3];
-    switch (w) {
-        case 0: v[0] = a; v[1] = b; v[2] = c; break;
-        case 1: v[0] = c; v[1] = b; v[2] = d; break;
-        case 2: v[0] = c; v[1] = b; v[2] = a; break;
-        default: v[0] = d; v[1] = b; v[2] = c; break;
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        if (A[k] == 0.f) continue;
-        atomicAdd(&sg[v[k] + 0], -t0 * A[k] * hs);
-        atomicAdd(&sg[v[k] + 1], -t1 * A[k] * hs);
-        atomicAdd(&sg[v[k] + 2], A[k] / (z[k] * z[k]));
-    }
-}
-
-// Backward rasterisation: same tiling and the same candidate boxes as k_splat; every winding collects
-// the sub-pixels it won from the face-index map, turns them into vertex (u,v,z) gradients in shared
-// memory, and the tile pushes those through projection / rotation to grad_depth, grad_R, grad_t.
-__global__ void __launch_bounds__(SPLAT_THREADS)
+// Backward rasterisation (g2s_splat.cuh): same tiling and the same candidate boxes as k_splat; every winding
+// collects the sub-pixels it won from the face-index map, the tile turns them into vertex (u,v,z) gradients in
+// shared memory and pushes those through projection / rotation to grad_depth, grad_R, grad_t.
+__global__ void __launch_bounds__(SPLAT_THREADS, 3)
 k_raster_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
              const float* __restrict__ t, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
              float* __restrict__ grad_depth, long gdstride, float* __restrict__ grad_R, float* __restrict__ grad_t,
-             int tiles_x) {
-    __shared__ float sv[TV * TV * 3];
-    __shared__ float sg[TV * TV * 3];
-    __shared__ float sRt[12];
-    __shared__ unsigned short squeue[SPLAT_THREADS * 4];
-    __shared__ int sqn;
-    const int tid = threadIdx.x, b = blockIdx.y, S = cam.S, is = 2 * S;
+             int tiles_x, int view0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    const int tid = threadIdx.x, bl = blockIdx.y, b = view0 + bl, S = cam.S, is = 2 * S;
     const int ty0 = (blockIdx.x / tiles_x) * TILE, tx0 = (blockIdx.x % tiles_x) * TILE;
+    float* sRt = sm.t.sRt;
     if (tid < 9) sRt[tid] = R[b * 9 + tid];
     else if (tid < 12) sRt[tid] = t[b * 3 + tid - 9];
-    if (tid == 0) sqn = 0;
-    for (int i = tid; i < TV * TV * 3; i += SPLAT_THREADS) sg[i] = 0.f;
+    if (tid == 0) sm.t.n_hq = sm.t.n_fq = sm.t.n_lq = 0;
+    for (int i = tid; i < TV * TV * 3; i += SPLAT_THREADS) sm.sg[i] = 0.f;
+    for (int i = tid; i < NSLOT * 3; i += SPLAT_THREADS) sm.sA[i] = 0.f;
     __syncthreads();
     const float* dimg = depth + (long)(b / vpi) * dstride;
-    tile_project<false>(cam, dimg, nullptr, sRt, ty0, tx0, sv);
+    tile_project<false>(cam, dimg, nullptr, sRt, ty0, tx0, sm.t.sv);
     __syncthreads();
-
-    const int* fmap = face_idx + (long)b * is * is;
-    const float* gs = g_sub + (long)b * S * S;
-    const int Q = (S - 1) * (S - 1);
-    const int qy = tid / TILE, qx = tid % TILE;
-    if (ty0 + qy < S - 1 && tx0 + qx < S - 1) {
-        const int qid = (ty0 + qy) * (S - 1) + tx0 + qx;
-#pragma unroll 1
-        for (int w = 0; w < 4; w++) {
-            const Tri f = tile_winding(sv, qy, qx, w);
-            if (tri_is_back(f)) continue;
-            BBox bb;
-            if (!tri_bbox(f, is, bb)) continue;
-            const int n = (bb.x1 - bb.x0 + 1) * (bb.y1 - bb.y0 + 1);
-            if (n > SMALL_BOX) {
-                squeue[atomicAdd(&sqn, 1)] = (unsigned short)(tid * 4 + w);
-                continue;
-            }
-            float fi[9], A[3] = {0.f, 0.f, 0.f};
-            bool have_fi = false;
-            const int face = w * Q + qid;
-            for (int yi = bb.y0; yi <= bb.y1; yi++)
-                for (int xi = bb.x0; xi <= bb.x1; xi++) bwd_one(f, fi, have_fi, xi, yi, is, fmap, gs, S, face, A, cam);
-            if (have_fi) bwd_face_scatter(f, fi, A, is, sg, qy, qx, w);
-        }
-    }
+    BwdOps ops;
+    ops.fmap = face_idx + (long)b * is * is;
+    ops.gsub = g_sub + (long)bl * S * S;
+    ops.sA = sm.sA; ops.sg = sm.sg;
+    ops.near = cam.near; ops.far = cam.far; ops.is = is; ops.S = S;
+    tile_rasterise(sm.t, ops, cam, ty0, tx0);
     __syncthreads();
-    const int nq = sqn, lane = tid & 31;
-    for (int e = tid >> 5; e < nq; e += SPLAT_THREADS / 32) {
-        const int item = squeue[e], qt = item >> 2, w = item & 3;
-        const int fqy = qt / TILE, fqx = qt % TILE;
-        const Tri f = tile_winding(sv, fqy, fqx, w);
-        BBox bb;
-        tri_bbox(f, is, bb);
-        const int bw = bb.x1 - bb.x0 + 1, n = bw * (bb.y1 - bb.y0 + 1);
-        const int face = w * Q + (ty0 + fqy) * (S - 1) + tx0 + fqx;
-        float fi[9], A[3] = {0.f, 0.f, 0.f};
-        bool have_fi = false;
-        for (int idx = lane; idx < n; idx += 32)
-            bwd_one(f, fi, have_fi, bb.x0 + idx % bw, bb.y0 + idx / bw, is, fmap, gs, S, face, A, cam);
-        A[0] = warp_sum(A[0]); A[1] = warp_sum(A[1]); A[2] = warp_sum(A[2]);
-        if (lane == 0 && (A[0] != 0.f || A[1] != 0.f || A[2] != 0.f)) {
-            tri_face_inv(f, is, fi);
-            bwd_face_scatter(f, fi, A, is, sg, fqy, fqx, w);
-        }
+    // per-face accumulators -> vertex (u,v,z) gradients
+    const int nf = sm.t.n_fq;
+    for (int i = tid; i < nf; i += SPLAT_THREADS) {
+        const int code = sm.t.fq[i];
+        const float* A = &sm.sA[(code & 511) * 3];
+        if (A[0] != 0.f || A[1] != 0.f || A[2] != 0.f)
+            face_scatter(&sm.t.ftab[(code & 511) * FT_STRIDE], A, is, sm.sg, code);
     }
     __syncthreads();
     // vertex chain: (u,v,z) NDC gradient -> 3-D point -> depth, R, t
@@ -711,7 +587,7 @@ k_raster_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
     for (int i = tid; i < TV * TV; i += SPLAT_THREADS) {
         const int vy = ty0 + i / TV, vx = tx0 + i % TV;
-        const float gu = sg[i * 3], gv = sg[i * 3 + 1], gz = sg[i * 3 + 2];
+        const float gu = sm.sg[i * 3], gv = sm.sg[i * 3 + 1], gz = sm.sg[i * 3 + 2];
         if (vy >= S || vx >= S || (gu == 0.f && gv == 0.f && gz == 0.f)) continue;
         float ray[3], q[3];
         pixel_ray(cam, vx, vy, ray);
@@ -748,92 +624,76 @@ k_raster_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
 // ------------------------------------------------------------------------------------------------
 // fused render backward, pixel stage: clamp(-1,1) -> shaded bilinear sampling -> inverse warp grid.
 // Writes per-view texture gradients (atomics into grad_tex_ws), the masked quarter gradient of
-// recon_depth (g_sub) and accumulates grad_R / grad_t.
-__global__ void __launch_bounds__(PIX_THREADS)
+// recon_depth (g_sub) and accumulates grad_R / grad_t.  grad_tex / g_sub are indexed by the LOCAL view
+// (chunked launches), everything else by the global view fa.view0 + blockIdx.z.
+__global__ void __launch_bounds__(PBX * PBY)
 k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ recon_depth,
                    const float* __restrict__ grad_recon_im, const float* __restrict__ grad_recon_depth,
                    float* __restrict__ g_sub, float* __restrict__ grad_tex, float* __restrict__ grad_R,
                    float* __restrict__ grad_t) {
-    const int S = cam.S, b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    __shared__ float sview[17];
+    const int S = cam.S, bl = blockIdx.z, b = fa.view0 + bl;
+    {
+        const int k = threadIdx.y * PBX + threadIdx.x;
+        if (k < 9) sview[k] = fa.R[b * 9 + k];
+        else if (k < 12) sview[k] = fa.t[b * 3 + k - 9];
+        else if (k < 17) sview[k] = fa.light[b * 5 + k - 12];
+        __syncthreads();
+    }
+    const int j = blockIdx.x * PBX + threadIdx.x, i = blockIdx.y * PBY + threadIdx.y;
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
-    if (pix < S * S) {
-        const int i = pix / S, j = pix - i * S, img = b / fa.vpi;
-        float Rm[9], tv[3], ray[3], q[3], v[3], g[2];
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rm[k] = __ldg(&fa.R[b * 9 + k]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) tv[k] = __ldg(&fa.t[b * 3 + k]);
+    if (j < S && i < S) {
+        const int pix = i * S + j, img = b / fa.vpi;
+        float ray[3], q[3], v[3], g[2];
         const float rd = recon_depth[(long)b * S * S + pix];
-        pixel_ray(cam, j, i, ray);
-        inv_warp_point(cam, Rm, tv, ray, rd, q, v);
-        point_to_grid(cam, q, S, S, g);
-        LightP L;
-        L.a = __ldg(&fa.light[b * 5 + 0]); L.b = __ldg(&fa.light[b * 5 + 1]);
-        L.dx = __ldg(&fa.light[b * 5 + 2]); L.dy = __ldg(&fa.light[b * 5 + 3]); L.dz = __ldg(&fa.light[b * 5 + 4]);
-        const float* nimg = fa.normal + (long)img * S * S * 3;
-        const float* aimg = fa.albedo + (long)img * S * S * 3;
         float G[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) G[c] = grad_recon_im[((long)b * 3 + c) * S * S + pix];
+        pixel_ray(cam, j, i, ray);
+        inv_warp_point(cam, sview, sview + 9, ray, rd, q, v);
+        point_to_grid(cam, q, S, S, g);
+        const Taps tp = make_taps(g[0], g[1], S, S, fa.align);
+        float tex[4][3];
+        shade_taps(fa.normal + (long)img * S * S * 3, fa.albedo + (long)img * S * S * 3, S * S, tp, sview + 12, tex);
         float gix = 0.f, giy = 0.f;
-        int x0, y0;
-        float tx, ty;
-        if (bilinear_setup(g[0], g[1], S, S, fa.align, x0, y0, tx, ty)) {
-            float tex[4][3], out[3] = {0.f, 0.f, 0.f};
-            bool ok[4];
+        float* gt_b = grad_tex + (long)bl * 3 * S * S;
 #pragma unroll
-            for (int tap = 0; tap < 4; tap++) {
-                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
-                ok[tap] = !(xx < 0 || xx >= S || yy < 0 || yy >= S);
-                tex[tap][0] = tex[tap][1] = tex[tap][2] = 0.f;
-                if (!ok[tap]) continue;
-                float sh, ndl;
-                shade_texel(nimg, aimg, S * S, yy * S + xx, L, tex[tap], &sh, &ndl);
-                const float wgt = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
-#pragma unroll
-                for (int c = 0; c < 3; c++) out[c] += wgt * tex[tap][c];
-            }
+        for (int c = 0; c < 3; c++) {
+            const float o = tp.w[0] * tex[0][c] + tp.w[1] * tex[1][c] + tp.w[2] * tex[2][c] + tp.w[3] * tex[3][c];
             // clamp(-1,1) passes the gradient where -1 <= x <= 1
+            const float Gc = (o >= -1.f && o <= 1.f) ? G[c] : 0.f;
+            if (Gc == 0.f) continue;
 #pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (!(out[c] >= -1.f && out[c] <= 1.f)) G[c] = 0.f;
-            float* gt_b = grad_tex + (long)b * 3 * S * S;
-#pragma unroll
-            for (int tap = 0; tap < 4; tap++) {
-                if (!ok[tap]) continue;
-                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
-                const float wx = (tap & 1) ? tx : 1.f - tx, wy = (tap >> 1) ? ty : 1.f - ty;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    if (G[c] != 0.f) atomicAdd(&gt_b[c * S * S + yy * S + xx], wx * wy * G[c]);
-                    gix += ((tap & 1) ? 1.f : -1.f) * wy * tex[tap][c] * G[c];
-                    giy += ((tap >> 1) ? 1.f : -1.f) * wx * tex[tap][c] * G[c];
-                }
+            for (int k = 0; k < 4; k++) {
+                if (tp.w[k] != 0.f) atomicAdd(&gt_b[c * S * S + tp.p[k]], tp.w[k] * Gc);
+                gix += ((k & 1) ? 1.f : -1.f) * tp.wy[k] * tex[k][c] * Gc;
+                giy += ((k >> 1) ? 1.f : -1.f) * tp.wx[k] * tex[k][c] * Gc;
             }
         }
         const float mult = fa.align ? (float)(S - 1) * 0.5f : (float)S * 0.5f;
-        float gd = warp_grid_bwd_pixel(cam, Rm, tv, j, i, S, S, rd, 1, gix * mult, giy * mult, acc);
+        float gd = warp_grid_bwd_pixel(cam, sview, sview + 9, j, i, S, S, rd, 1, gix * mult, giy * mult, acc);
         if (grad_recon_depth) gd += grad_recon_depth[(long)b * S * S + pix];
-        g_sub[(long)b * S * S + pix] = (rd > cam.clamp_lo && rd < cam.clamp_hi) ? 0.25f * gd : 0.f;
+        g_sub[(long)bl * S * S + pix] = (rd > cam.clamp_lo && rd < cam.clamp_hi) ? 0.25f * gd : 0.f;
     }
     float accR[9], acct[3];
 #pragma unroll
     for (int k = 0; k < 9; k++) accR[k] = acc[k];
 #pragma unroll
     for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
-    block_accumulate<9, PIX_THREADS>(accR, grad_R + b * 9);
-    block_accumulate<3, PIX_THREADS>(acct, grad_t + b * 3);
+    block_accumulate<9, PBX * PBY>(accR, grad_R + b * 9);
+    block_accumulate<3, PBX * PBY>(acct, grad_t + b * 3);
 }
 
-// fused render backward, texture stage: per image pixel, loop over the image's views and turn the
-// per-view texture gradients into grad_albedo, grad_normal (registers, no atomics) and grad_light
-// (warp reduction + one atomic per warp and view).
+// fused render backward, texture stage: per image pixel, loop over the image's views that fall in this
+// chunk [view0, view0+nviews) and turn the per-view texture gradients into grad_albedo, grad_normal
+// (registers, accumulated with a plain += : one thread owns one (image, pixel)) and grad_light (warp
+// reduction + one atomic per warp and view).  grid = (pixel blocks, images spanned by the chunk).
 __global__ void __launch_bounds__(PIX_THREADS)
-k_render_bwd_tex(int S, const FusedArgs fa, const float* __restrict__ grad_tex, float* __restrict__ grad_albedo,
-                 float* __restrict__ grad_normal, float* __restrict__ grad_light) {
-    const int img = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict__ grad_tex,
+                 float* __restrict__ grad_albedo, float* __restrict__ grad_normal, float* __restrict__ grad_light) {
+    const int img = fa.view0 / fa.vpi + blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
     const bool live = pix < S * S;
     const int p = live ? pix : 0;
     const float* nimg = fa.normal + (long)img * S * S * 3;
@@ -841,14 +701,14 @@ k_render_bwd_tex(int S, const FusedArgs fa, const float* __restrict__ grad_tex, 
     const float n0 = nimg[p * 3], n1 = nimg[p * 3 + 1], n2 = nimg[p * 3 + 2];
     const float al[3] = {aimg[p], aimg[S * S + p], aimg[2 * S * S + p]};
     float ga[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
-    for (int vi = 0; vi < fa.vpi; vi++) {
-        const int b = img * fa.vpi + vi;
+    const int b0 = max(img * fa.vpi, fa.view0), b1 = min((img + 1) * fa.vpi, fa.view0 + nviews);
+    for (int b = b0; b < b1; b++) {
         const float la = __ldg(&fa.light[b * 5]), lb = __ldg(&fa.light[b * 5 + 1]), dx = __ldg(&fa.light[b * 5 + 2]),
                     dy = __ldg(&fa.light[b * 5 + 3]), dz = __ldg(&fa.light[b * 5 + 4]);
         float T[3] = {0.f, 0.f, 0.f};
         if (live) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) T[c] = grad_tex[((long)b * 3 + c) * S * S + p];
+            for (int c = 0; c < 3; c++) T[c] = grad_tex[((long)(b - fa.view0) * 3 + c) * S * S + p];
         }
         const float ndl = n0 * dx + n1 * dy + n2 * dz;
         const float diff = fmaxf(ndl, 0.f);
@@ -871,12 +731,11 @@ k_render_bwd_tex(int S, const FusedArgs fa, const float* __restrict__ grad_tex, 
     }
     if (live) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) grad_albedo[((long)img * 3 + c) * S * S + p] = ga[c];
+        for (int c = 0; c < 3; c++) grad_albedo[((long)img * 3 + c) * S * S + p] += ga[c];
         float* o = grad_normal + ((long)img * S * S + p) * 3;
-        o[0] = gn[0]; o[1] = gn[1]; o[2] = gn[2];
+        o[0] += gn[0]; o[1] += gn[1]; o[2] += gn[2];
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // mesh-texture branch (render_yaw / render_view / render_given_view with grid_sample=False)
@@ -1070,6 +929,52 @@ k_resolve_rgb(const Cam cam, unsigned long long* __restrict__ zbuf, const float*
     }
 }
 
+// k_raster_bwd needs > 48 KB of shared memory: opt in once per device context
+inline void raster_smem_optin() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(k_raster_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
+        cudaFuncSetAttribute(k_splat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+        cudaFuncSetAttribute(k_splat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    });
+}
+inline size_t bwd_smem_bytes() { raster_smem_optin(); return sizeof(BwdSmem); }
+inline size_t fwd_smem_bytes() { raster_smem_optin(); return sizeof(TileSmem); }
+
+// compares the shared-reciprocal division (g2s_math.cuh dvd_y) with __fdiv_rn bit for bit on pseudo-random operands
+__global__ void k_selftest_division(unsigned long long per_thread, unsigned seed, unsigned long long* mismatches) {
+    unsigned long long x = (unsigned long long)seed * 0x9E3779B97F4A7C15ull +
+                           ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1) * 0xBF58476D1CE4E5B9ull;
+    unsigned long long bad = 0;
+    for (unsigned long long i = 0; i < per_thread; i++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+        // sign | exponent in [127-44, 127+44] | random mantissa, with a share of special mantissas
+        unsigned ma = lo & 0x7fffffu, mb = hi & 0x7fffffu;
+        const unsigned sel = (lo >> 23) & 7u;
+        if (sel == 0) ma = 0; else if (sel == 1) ma = 0x7fffffu; else if (sel == 2) mb = 0x7fffffu; else if (sel == 3) mb = 0;
+        const unsigned ea = 127u - 44u + ((hi >> 23) & 0xffu) % 89u, eb = 127u - 44u + ((lo >> 26) ^ (hi >> 25)) % 89u;
+        const float a = __uint_as_float(((lo >> 31) << 31) | (ea << 23) | ma);
+        const float b = __uint_as_float(((hi >> 31) << 31) | (eb << 23) | mb);
+        const float q0 = __fdiv_rn(a, b), q1 = dvd_y(a, b, rcp_seed(b));
+        bad += __float_as_uint(q0) != __float_as_uint(q1);
+        const float z0 = __fdiv_rn(0.0f, b), z1 = dvd_y(0.0f, b, rcp_seed(b));
+        bad += (z0 != z1);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+inline dim3 pix_grid2(int S, int views) { return dim3((S + PBX - 1) / PBX, (S + PBY - 1) / PBY, views); }
+
+// views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
+// scratch 16 S^2 B/view) stays resident in the 126 MB L2 between the kernel that writes it and the one that reads it
+inline int chunk_views_for(int S, int cap) {
+    long v = (32L << 20) / (32L * S * S);
+    if (v < 1) v = 1;
+    if (v > cap) v = cap;
+    return (int)v;
+}
+
 inline dim3 pix_grid(long npix, int batch) { return dim3((unsigned)((npix + PIX_THREADS - 1) / PIX_THREADS), batch); }
 
 inline bool bad_size(int S) { return S < 2 || S > 2048; }
@@ -1113,10 +1018,10 @@ int g2s_warp_depth_fwd(const g2s_camera* cam, const float* depth, long depth_vie
     const Cam c = make_cam(cam);
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, 0, st>>>(c, depth, depth_view_stride, 1, R, t,
-                                                                          nullptr, (unsigned long long*)zbuf, tiles); }
+    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, depth_view_stride, 1, R, t,
+                                                                          nullptr, (unsigned long long*)zbuf, tiles, 0); }
     FusedArgs fa = {};
-    { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid((long)S * S, n_views), PIX_THREADS, 0, st>>>(c, (unsigned long long*)zbuf, recon_depth,
+    { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid2(S, n_views), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, recon_depth,
                                                                              face_idx, fa); }
     return launch_status();
 }
@@ -1135,9 +1040,9 @@ int g2s_warp_depth_bwd(const g2s_camera* cam, const float* depth, long depth_vie
     const long n = (long)n_views * S * S;
     { Launch l_(K_CLAMP_GRAD, st); k_clamp_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(recon_depth, grad_recon_depth, c.clamp_lo, c.clamp_hi, n,
                                                               grad_sub_ws); }
-    { Launch l_(K_RASTER_BWD, st); k_raster_bwd<<<dim3(tiles * tiles, n_views), SPLAT_THREADS, 0, st>>>(
+    { Launch l_(K_RASTER_BWD, st); k_raster_bwd<<<dim3(tiles * tiles, n_views), SPLAT_THREADS, bwd_smem_bytes(), st>>>(
         c, depth, depth_view_stride, 1, R, t, face_idx, grad_sub_ws, grad_depth, grad_depth_view_stride, grad_R, grad_t,
-        tiles); }
+        tiles, 0); }
     return launch_status();
 }
 
@@ -1199,29 +1104,43 @@ int g2s_sample_bwd(const float* input, long input_batch_stride, const float* gri
     return launch_status();
 }
 
+int g2s_chunk_views(int image_size) { return bad_size(image_size) ? 0 : chunk_views_for(image_size, 1 << 20); }
+
 int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
-                         float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx, void* stream) {
+                         int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
+                         void* stream) {
     if (!cam || !depth || !albedo || !R || !t || !light || !zbuf || !normal_ws || !recon_im || !recon_depth)
         return G2S_ERR_NULL;
     const long n_views = (long)n_images * views_per_image;
-    if (n_images <= 0 || views_per_image <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    if (n_images <= 0 || views_per_image <= 0 || n_views > (1L << 30) || ws_views <= 0 || bad_size(cam->image_size))
+        return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_NORMAL_FWD, st); k_normal_fwd<<<pix_grid((long)S * S, n_images), PIX_THREADS, 0, st>>>(c, depth, S, S, normal_ws); }
-    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles, (int)n_views), SPLAT_THREADS, 0, st>>>(
-        c, depth, (long)S * S, views_per_image, R, t, nullptr, (unsigned long long*)zbuf, tiles); }
-    FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners};
-    { Launch l_(K_RESOLVE_FUSED, st); k_resolve<true><<<pix_grid((long)S * S, (int)n_views), PIX_THREADS, 0, st>>>(c, (unsigned long long*)zbuf,
-                                                                                recon_depth, face_idx, fa); }
+    for (int i0 = 0; i0 < n_images; i0 += 32768) {
+        const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;
+        Launch l_(K_NORMAL_FWD, st);
+        k_normal_fwd<<<pix_grid((long)S * S, ni), PIX_THREADS, 0, st>>>(c, depth + (long)i0 * S * S, S, S,
+                                                                        normal_ws + (long)i0 * S * S * 3);
+    }
+    const int chunk = ws_views < 32768 ? ws_views : 32768;
+    for (long v0 = 0; v0 < n_views; v0 += chunk) {
+        const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
+        { Launch l_(K_SPLAT, st);
+          k_splat<false><<<dim3(tiles * tiles, nv), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
+                                                                           (unsigned long long*)zbuf, tiles, (int)v0); }
+        FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0};
+        { Launch l_(K_RESOLVE_FUSED, st);
+          k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, recon_depth, face_idx, fa); }
+    }
     return launch_status();
 }
 
 int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners,
                          const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
-                         const float* grad_recon_im, const float* grad_recon_depth, float* grad_sub_ws,
+                         const float* grad_recon_im, const float* grad_recon_depth, int ws_views, float* grad_sub_ws,
                          float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R,
                          float* grad_t, float* grad_light, void* stream) {
     if (!cam || !depth || !albedo || !R || !t || !light || !normal_ws || !recon_depth || !face_idx || !grad_recon_im ||
@@ -1229,23 +1148,42 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
         !grad_light)
         return G2S_ERR_NULL;
     const long n_views = (long)n_images * views_per_image;
-    if (n_images <= 0 || views_per_image <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    if (n_images <= 0 || views_per_image <= 0 || n_views > (1L << 30) || ws_views <= 0 || bad_size(cam->image_size))
+        return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * n_views * 3 * S * S, st);
+    const size_t img_f = (size_t)S * S;
     cudaMemsetAsync(grad_R, 0, sizeof(float) * n_views * 9, st);
     cudaMemsetAsync(grad_t, 0, sizeof(float) * n_views * 3, st);
     cudaMemsetAsync(grad_light, 0, sizeof(float) * n_views * 5, st);
-    FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners};
-    { Launch l_(K_BWD_PIXEL, st); k_render_bwd_pixel<<<pix_grid((long)S * S, (int)n_views), PIX_THREADS, 0, st>>>(
-        c, fa, recon_depth, grad_recon_im, grad_recon_depth, grad_sub_ws, grad_tex_ws, grad_R, grad_t); }
-    { Launch l_(K_BWD_TEX, st); k_render_bwd_tex<<<pix_grid((long)S * S, n_images), PIX_THREADS, 0, st>>>(S, fa, grad_tex_ws, grad_albedo,
-                                                                              grad_normal_ws, grad_light); }
-    { Launch l_(K_NORMAL_BWD, st); k_normal_bwd<<<pix_grid((long)S * S, n_images), PIX_THREADS, 0, st>>>(c, depth, S, S, grad_normal_ws, grad_depth, 0); }
-    { Launch l_(K_RASTER_BWD, st); k_raster_bwd<<<dim3(tiles * tiles, (int)n_views), SPLAT_THREADS, 0, st>>>(
-        c, depth, (long)S * S, views_per_image, R, t, face_idx, grad_sub_ws, grad_depth, (long)S * S, grad_R, grad_t,
-        tiles); }
+    cudaMemsetAsync(grad_depth, 0, sizeof(float) * n_images * img_f, st);
+    cudaMemsetAsync(grad_albedo, 0, sizeof(float) * n_images * 3 * img_f, st);
+    cudaMemsetAsync(grad_normal_ws, 0, sizeof(float) * n_images * 3 * img_f, st);
+    const int chunk = ws_views < 32768 ? ws_views : 32768;
+    for (long v0 = 0; v0 < n_views; v0 += chunk) {
+        const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
+        cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * nv * 3 * img_f, st);
+        FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0};
+        { Launch l_(K_BWD_PIXEL, st);
+          k_render_bwd_pixel<<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
+                                                                         grad_sub_ws, grad_tex_ws, grad_R, grad_t); }
+        const int img_lo = (int)(v0 / views_per_image), img_hi = (int)((v0 + nv - 1) / views_per_image);
+        { Launch l_(K_BWD_TEX, st);
+          k_render_bwd_tex<<<pix_grid((long)S * S, img_hi - img_lo + 1), PIX_THREADS, 0, st>>>(S, fa, nv, grad_tex_ws, grad_albedo,
+                                                                                             grad_normal_ws, grad_light); }
+        { Launch l_(K_RASTER_BWD, st);
+          k_raster_bwd<<<dim3(tiles * tiles, nv), SPLAT_THREADS, bwd_smem_bytes(), st>>>(
+              c, depth, (long)S * S, views_per_image, R, t, face_idx, grad_sub_ws, grad_depth, (long)S * S, grad_R, grad_t,
+              tiles, (int)v0); }
+    }
+    for (int i0 = 0; i0 < n_images; i0 += 32768) {
+        const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;
+        Launch l_(K_NORMAL_BWD, st);
+        k_normal_bwd<<<pix_grid((long)S * S, ni), PIX_THREADS, 0, st>>>(c, depth + (long)i0 * S * S, S, S,
+                                                                        grad_normal_ws + (long)i0 * S * S * 3,
+                                                                        grad_depth + (long)i0 * S * S, 1);
+    }
     return launch_status();
 }
 
@@ -1275,8 +1213,8 @@ int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const flo
     const Cam c = make_cam(cam);
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, 0, st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
-                                                                         (unsigned long long*)zbuf, tiles); }
+    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
+                                                                         (unsigned long long*)zbuf, tiles, 0); }
     Bg b4 = {{0.f, 0.f, 0.f, 0.f}};
     for (int i = 0; i < C; i++) b4.c[i] = bg[i];
     const float eps = 1e-3f;  // nr.Renderer.rasterizer_eps
@@ -1288,6 +1226,14 @@ int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const flo
         case 3: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<3><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
         default: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<4><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
     }
+    return launch_status();
+}
+
+int g2s_selftest_division(unsigned long long n_pairs, unsigned seed, unsigned long long* mismatches_dev, void* stream) {
+    if (!mismatches_dev) return G2S_ERR_NULL;
+    const int blocks = 148 * 8, threads = 256;
+    const unsigned long long per = (n_pairs + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
+    k_selftest_division<<<blocks, threads, 0, (cudaStream_t)stream>>>(per, seed, mismatches_dev);
     return launch_status();
 }
 

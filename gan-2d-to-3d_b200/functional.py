@@ -249,14 +249,15 @@ class RenderChainFn(torch.autograd.Function):
         L = _f32c(light)
         cam = renderer._camera(depth_pass=True)
         dev = d.device
-        zbuf = renderer._zbuf.get(B, S, cam.far_z, dev)
+        ws_views = min(B, lib.g2s_chunk_views(S))
+        zbuf = renderer._zbuf.get(ws_views, S, cam.far_z, dev)
         normal = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
         recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
         recon_depth = torch.empty(B, S, S, device=dev, dtype=torch.float32)
         fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)
         _lib.check(lib.g2s_render_fused_fwd(ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N,
-                                            views_per_image, int(bool(align_corners)), _p(zbuf), _p(normal),
-                                            _p(recon_im), _p(recon_depth), _p(fidx), _stream()),
+                                            views_per_image, int(bool(align_corners)), _p(zbuf), ws_views,
+                                            _p(normal), _p(recon_im), _p(recon_depth), _p(fidx), _stream()),
                    "g2s_render_fused_fwd")
         ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape)
@@ -274,8 +275,9 @@ class RenderChainFn(torch.autograd.Function):
         cam = renderer._camera(depth_pass=True)
         gi = _f32c(g_im) if g_im is not None else torch.zeros(B, 3, S, S, device=dev)
         gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
-        ws_sub = torch.empty(B, S, S, device=dev, dtype=torch.float32)
-        ws_tex = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
+        ws_views = min(B, lib.g2s_chunk_views(S))
+        ws_sub = torch.empty(ws_views, S, S, device=dev, dtype=torch.float32)
+        ws_tex = torch.empty(ws_views, 3, S, S, device=dev, dtype=torch.float32)
         ws_nrm = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
         g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)
         g_albedo = torch.empty(N, 3, S, S, device=dev, dtype=torch.float32)
@@ -283,7 +285,7 @@ class RenderChainFn(torch.autograd.Function):
         gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
         gL = torch.empty(B, 5, device=dev, dtype=torch.float32)
         _lib.check(lib.g2s_render_fused_bwd(ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N, vpi, align,
-                                            _p(normal), _p(recon_depth), _p(fidx), _p(gi), _p(gd_out), _p(ws_sub),
+                                            _p(normal), _p(recon_depth), _p(fidx), _p(gi), _p(gd_out), ws_views, _p(ws_sub),
                                             _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR), _p(gt), _p(gL),
                                             _stream()), "g2s_render_fused_bwd")
         gR = gR.sum_to_size(Rshape)

@@ -8,7 +8,7 @@
  *     (host memory, copied by value into the launch);
  *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or freed here;
  *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no host sync;
- *   - re-entrant, no global state;
+ *   - re-entrant, no global state apart from the instrumentation counters at the end of this header;
  *   - returns G2S_OK (0) or a negative G2S_ERR_* code; never throws.  The reference's neural_renderer
  *     extension reports the same class of failures through AT_ASSERTM -> RuntimeError
  *     (CHECK_CUDA / CHECK_CONTIGUOUS); the Python host layer turns non-zero codes into RuntimeError.
@@ -111,23 +111,26 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  *   grid     = get_inv_warped_2d_grid(recon_depth[b])             (renderer.py:110-114)
  *   recon_im[b] = grid_sample(texture, grid).clamp(-1, 1)         (model.py:270)
  * light [n_views,5] = (ambient a, diffuse b, direction dx,dy,dz) as get_lighting_directions returns.
- * Workspaces: zbuf (g2s_zbuffer_bytes), normal_ws [n_images,S,S,3].
+ * The views are processed in chunks of `ws_views` views so that the per-chunk scratch stays L2-resident between the
+ * kernel that writes it and the kernel that reads it; g2s_chunk_views(S) returns the recommended chunk (32 MB of
+ * z-buffer).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,3].
  * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S]. */
+int g2s_chunk_views(int image_size);
 int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
-                         int align_corners, void *zbuf, float *normal_ws, float *recon_im, float *recon_depth,
-                         int32_t *face_idx, void *stream);
+                         int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
+                         float *recon_depth, int32_t *face_idx, void *stream);
 
 /* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
- * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [n_views,S,S],
- * grad_tex_ws [n_views,3,S,S] (zero-filled by the call), grad_normal_ws [n_images,S,S,3].
+ * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,S,S],
+ * grad_tex_ws [ws_views,3,S,S] (chunked like the forward), grad_normal_ws [n_images,S,S,3].
  * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
  * grad_t [n_views,3], grad_light [n_views,5]. */
 int g2s_render_fused_bwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, const float *normal_ws, const float *recon_depth,
                          const int32_t *face_idx, const float *grad_recon_im, const float *grad_recon_depth,
-                         float *grad_sub_ws, float *grad_tex_ws, float *grad_normal_ws, float *grad_depth,
+                         int ws_views, float *grad_sub_ws, float *grad_tex_ws, float *grad_normal_ws, float *grad_depth,
                          float *grad_albedo, float *grad_R, float *grad_t, float *grad_light, void *stream);
 
 /* ---- mesh-texture render: nr.Renderer.render_rgb as renderer.py:196,230,248,272,275 call it ------
@@ -155,6 +158,9 @@ int g2s_grid3d_fwd(const g2s_camera *cam, const float *depth, long depth_view_st
  * g2s_profile_read: waits for the recorded events, returns the number of distinct kernels n (<= max_kernels)
  * and fills names[n], total_ms[n], launches[n]; clears the records. */
 long g2s_launch_count(void);
+/* g2s_selftest_division: compares the kernels' shared-reciprocal division with IEEE __fdiv_rn on n_pairs pseudo-random
+ * operand pairs and ADDS the number of mismatching results to *mismatches_dev (device, caller zero-fills). */
+int g2s_selftest_division(unsigned long long n_pairs, unsigned seed, unsigned long long *mismatches_dev, void *stream);
 int g2s_profile_enable(int on);
 int g2s_profile_read(int max_kernels, const char **names, float *total_ms, int *launches);
 
