@@ -267,20 +267,22 @@ def run_ours(args):
     e2e_value = renders / (ms_e2e / args.steps * 1e-3)
     peak, peak_src = measured_peak_gbs()
     per_render = alg_bytes_per_render(S, P)
-    # per-kernel algorithmic bytes per launch (DESIGN.md "kernels"): the HBM traffic each kernel cannot avoid
+    # per-kernel algorithmic bytes per STEP (DESIGN.md "kernels"): the HBM traffic each kernel cannot avoid, i.e. its
+    # share of SURVEY.md 8(d)'s per-render budget; per launch = per step / launches per step (chunked launches)
     S2 = float(S * S)
-    kb = {"k_normal_fwd": N * (4 + 12) * S2,
-          "k_splat": N * 4 * S2,                                   # reads the depth maps; the z-buffer is an L2 workspace
-          "k_resolve_fused": B * 32 * S2 + N * 24 * S2,            # writes recon_depth+recon_im+face_idx; reads normal/albedo
-          "k_render_bwd_pixel": B * (12 + 4) * S2 + N * 24 * S2,   # reads grad_recon_im, recon_depth, normal/albedo
-          "k_render_bwd_tex": N * (24 + 24) * S2,                  # reads normal/albedo, writes grad_albedo/grad_normal
-          "k_normal_bwd": N * (12 + 4 + 4) * S2,
-          "k_raster_bwd": B * 16 * S2 + N * 8 * S2}                # reads the face-index map (+depth), writes grad_depth
+    kb = {"k_normal_fwd": N * 4 * S2,                              # reads depth; the normal map is L2-resident scratch
+          "k_splat": N * 4 * S2,                                   # reads the depth maps; the z-buffer is L2 scratch
+          "k_resolve_fused": B * 32 * S2 + N * 12 * S2,            # writes recon_depth+recon_im+face_idx; reads albedo
+          "k_render_bwd_pixel": B * (12 + 4) * S2 + N * 12 * S2,   # reads grad_recon_im, recon_depth, albedo
+          "k_render_bwd_tex": N * 12 * S2,                         # writes grad_albedo
+          "k_normal_bwd": N * (4 + 4) * S2,                        # reads depth, writes grad_depth
+          "k_raster_bwd": B * 16 * S2 + N * 4 * S2}                # reads the face-index map (+depth)
     for k in kernels:
-        k["alg_bytes_per_launch"] = kb.get(k["name"])
+        per_step = kb.get(k["name"])
         k["share_of_step"] = k["ms_per_step"] / ms_step
-        if k["alg_bytes_per_launch"]:
-            k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9
+        if per_step:
+            k["alg_bytes_per_launch"] = per_step * args.steps / k["launches"]
+            k["achieved_gbs"] = per_step / (k["ms_per_step"] * 1e-3) / 1e9
             k["frac"] = k["achieved_gbs"] / peak
     kernels.sort(key=lambda k: -k["ms_per_step"])
     dom = kernels[0] if kernels else None
