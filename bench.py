@@ -276,7 +276,8 @@ def run_ours(args):
           "k_render_bwd_pixel": B * (12 + 4) * S2 + N * 12 * S2,   # reads grad_recon_im, recon_depth, albedo
           "k_render_bwd_tex": N * 12 * S2,                         # writes grad_albedo
           "k_normal_bwd": N * (4 + 4) * S2,                        # reads depth, writes grad_depth
-          "k_raster_bwd": B * 16 * S2 + N * 4 * S2}                # reads the face-index map (+depth)
+          "k_raster_bwd_px": B * 16 * S2,                          # reads the face-index map
+          "k_project_verts": N * 4 * S2, "k_vertex_bwd": N * (4 + 4) * S2}   # depth in, grad_depth out (scratch in L2)
     for k in kernels:
         per_step = kb.get(k["name"])
         k["share_of_step"] = k["ms_per_step"] / ms_step

@@ -43,11 +43,12 @@ Cam make_cam(const g2s_camera* c) {
 // ---- instrumentation: launch counter + optional CUDA-event timing of every kernel (bench.py / tests) ----
 enum KernelId { K_ZINIT, K_SPLAT, K_RESOLVE, K_RESOLVE_FUSED, K_GRID_FWD, K_GRID_BWD, K_NORMAL_FWD, K_NORMAL_BWD,
                 K_SAMPLE_FWD, K_SAMPLE_BWD, K_CLAMP_GRAD, K_RASTER_BWD, K_BWD_PIXEL, K_BWD_TEX, K_GRID3D, K_RESOLVE_RGB,
-                K_COUNT };
+                K_PROJECT, K_VERTEX_BWD, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_zbuf_init", "k_splat", "k_resolve", "k_resolve_fused", "k_warp_grid_fwd",
                                            "k_warp_grid_bwd", "k_normal_fwd", "k_normal_bwd", "k_sample_fwd",
-                                           "k_sample_bwd", "k_clamp_grad", "k_raster_bwd", "k_render_bwd_pixel",
-                                           "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb"};
+                                           "k_sample_bwd", "k_clamp_grad", "k_raster_bwd_px", "k_render_bwd_pixel",
+                                           "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb", "k_project_verts",
+                                           "k_vertex_bwd"};
 std::atomic<long> g_launches{0};
 struct ProfRec { int id; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
@@ -128,7 +129,7 @@ k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, c
         if (tid < 9) sm.sRt[tid] = R[b * 9 + tid];
         else if (tid < 12) sm.sRt[tid] = t[b * 3 + tid - 9];
     }
-    if (tid == 0) sm.n_hq = sm.n_fq = sm.n_lq = 0;
+    if (tid == 0) sm.n_hq = sm.n_fq = sm.n_lq = sm.n_mq = 0;
     __syncthreads();
     tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
                              FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, sm.sRt, ty0, tx0, sm.sv);
@@ -537,78 +538,134 @@ __global__ void k_clamp_grad(const float* __restrict__ recon_depth, const float*
     g_sub[i] = (rd > lo && rd < hi) ? 0.25f * grad[i] : 0.f;
 }
 
-struct BwdSmem {
-    TileSmem t;
-    float sA[NSLOT * 3];
-    float sg[TV * TV * 3];
-};
+// ------------------------------------------------------------------------------------------------
+// Pixel-centric backward of the rasteriser.  The face-index map already says which face owns every sub-pixel, so
+// the backward needs no candidate scan at all: one thread per OUTPUT pixel reads its 2x2 face indices, rebuilds each
+// distinct face's 3x3 inverse from the projected vertices (k_project_verts, an L2-resident scratch), evaluates the
+// weights / z of the sub-pixels that face owns, and adds the face's (u,v,z) vertex gradients ([nr]
+// backward_depth_map, factored per face) to a per-view vertex-gradient scratch; k_vertex_bwd then pushes every
+// vertex through projection / rotation to grad_depth, grad_R, grad_t.  neural_renderer does 9 float atomics per
+// covered sub-pixel into grad_faces[B,F,3,3] and leaves the gather to autograd (index_put over 6 faces per vertex).
 
-// Backward rasterisation (g2s_splat.cuh): same tiling and the same candidate boxes as k_splat; every winding
-// collects the sub-pixels it won from the face-index map, the tile turns them into vertex (u,v,z) gradients in
-// shared memory and pushes those through projection / rotation to grad_depth, grad_R, grad_t.
-__global__ void __launch_bounds__(SPLAT_THREADS, 3)
-k_raster_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
-             const float* __restrict__ t, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
-             float* __restrict__ grad_depth, long gdstride, float* __restrict__ grad_R, float* __restrict__ grad_t,
-             int tiles_x, int view0) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-    const int tid = threadIdx.x, bl = blockIdx.y, b = view0 + bl, S = cam.S, is = 2 * S;
-    const int ty0 = (blockIdx.x / tiles_x) * TILE, tx0 = (blockIdx.x % tiles_x) * TILE;
-    float* sRt = sm.t.sRt;
-    if (tid < 9) sRt[tid] = R[b * 9 + tid];
-    else if (tid < 12) sRt[tid] = t[b * 3 + tid - 9];
-    if (tid == 0) sm.t.n_hq = sm.t.n_fq = sm.t.n_lq = 0;
-    for (int i = tid; i < TV * TV * 3; i += SPLAT_THREADS) sm.sg[i] = 0.f;
-    for (int i = tid; i < NSLOT * 3; i += SPLAT_THREADS) sm.sA[i] = 0.f;
+// projected (u, v, z) of every vertex of the chunk's views: proj [chunk, S*S, 3]
+__global__ void __launch_bounds__(PIX_THREADS)
+k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+                const float* __restrict__ t, int view0, float* __restrict__ proj) {
+    __shared__ float sRt[12];
+    const int S = cam.S, bl = blockIdx.y, b = view0 + bl;
+    if (threadIdx.x < 9) sRt[threadIdx.x] = R[b * 9 + threadIdx.x];
+    else if (threadIdx.x < 12) sRt[threadIdx.x] = t[b * 3 + threadIdx.x - 9];
     __syncthreads();
-    const float* dimg = depth + (long)(b / vpi) * dstride;
-    tile_project<false>(cam, dimg, nullptr, sRt, ty0, tx0, sm.t.sv);
-    __syncthreads();
-    BwdOps ops;
-    ops.fmap = face_idx + (long)b * is * is;
-    ops.gsub = g_sub + (long)bl * S * S;
-    ops.sA = sm.sA; ops.sg = sm.sg;
-    ops.near = cam.near; ops.far = cam.far; ops.is = is; ops.S = S;
-    tile_rasterise(sm.t, ops, cam, ty0, tx0);
-    __syncthreads();
-    // per-face accumulators -> vertex (u,v,z) gradients
-    const int nf = sm.t.n_fq;
-    for (int i = tid; i < nf; i += SPLAT_THREADS) {
-        const int code = sm.t.fq[i];
-        const float* A = &sm.sA[(code & 511) * 3];
-        if (A[0] != 0.f || A[1] != 0.f || A[2] != 0.f)
-            face_scatter(&sm.t.ftab[(code & 511) * FT_STRIDE], A, is, sm.sg, code);
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (v >= S * S) return;
+    const int vy = v / S, vx = v - vy * S;
+    float ray[3], q[3], ndc[3];
+    pixel_ray(cam, vx, vy, ray);
+    warp_point(cam, sRt, sRt + 9, ray, depth[(long)(b / vpi) * dstride + v], q);
+    project_ndc(cam, q, ndc);
+    float* o = proj + ((long)bl * S * S + v) * 3;
+    o[0] = ndc[0]; o[1] = ndc[1]; o[2] = ndc[2];
+}
+
+__global__ void __launch_bounds__(PBX * PBY)
+k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
+                const float* __restrict__ proj, float* __restrict__ vgrad, int view0) {
+    const int S = cam.S, is = 2 * S, bl = blockIdx.z, b = view0 + bl;
+    const int j = blockIdx.x * PBX + threadIdx.x, i = blockIdx.y * PBY + threadIdx.y;
+    if (j >= S || i >= S) return;
+    const float g = g_sub[(long)bl * S * S + i * S + j];
+    if (g == 0.f) return;
+    const int* fm = face_idx + (long)b * is * is;
+    const int2 r0 = *reinterpret_cast<const int2*>(fm + (long)(2 * i) * is + 2 * j);
+    const int2 r1 = *reinterpret_cast<const int2*>(fm + (long)(2 * i + 1) * is + 2 * j);
+    const int f[4] = {r0.x, r0.y, r1.x, r1.y};
+    const float* pv = proj + (long)bl * S * S * 3;
+    float* vg = vgrad + (long)bl * S * S * 3;
+    const float hs = 0.5f * (float)is;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int face = f[k];
+        if (face < 0) continue;
+        bool seen = false;
+#pragma unroll
+        for (int k2 = 0; k2 < k; k2++) seen |= f[k2] == face;
+        if (seen) continue;
+        int vidx[3];
+        face_vertices(face, S, vidx);
+        float nd[3][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            nd[m][0] = __ldg(&pv[vidx[m] * 3]); nd[m][1] = __ldg(&pv[vidx[m] * 3 + 1]); nd[m][2] = __ldg(&pv[vidx[m] * 3 + 2]);
+        }
+        float rec[FT_STRIDE];
+        face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
+        float A[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k2 = k; k2 < 4; k2++) {
+            if (f[k2] != face) continue;
+            const int xi = 2 * j + (k2 & 1), yi = is - 1 - (2 * i + (k2 >> 1));
+            float w[3], zp = 0.f;
+            record_weights_depth(rec, xi, yi, cam.near, cam.far, w, &zp);
+            const float s = g * zp * zp;
+            A[0] += s * w[0]; A[1] += s * w[1]; A[2] += s * w[2];
+        }
+        // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
+        const float z[3] = {rec[9], rec[10], rec[11]};
+        const float t0 = -(__fdiv_rn(rec[0], z[0]) + __fdiv_rn(rec[3], z[1]) + __fdiv_rn(rec[6], z[2]));
+        const float t1 = -(__fdiv_rn(rec[1], z[0]) + __fdiv_rn(rec[4], z[1]) + __fdiv_rn(rec[7], z[2]));
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            if (A[m] == 0.f) continue;
+            float* o = &vg[vidx[m] * 3];
+            atomicAdd(&o[0], -t0 * A[m] * hs);
+            atomicAdd(&o[1], -t1 * A[m] * hs);
+            atomicAdd(&o[2], __fdiv_rn(A[m], z[m] * z[m]));
+        }
     }
+}
+
+// vertex chain: (u,v,z) NDC gradient -> 3-D point -> depth, R, t.  One thread per vertex.
+__global__ void __launch_bounds__(PIX_THREADS)
+k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+             const float* __restrict__ t, int view0, const float* __restrict__ vgrad, float* __restrict__ grad_depth,
+             long gdstride, float* __restrict__ grad_R, float* __restrict__ grad_t) {
+    __shared__ float sRt[12];
+    const int S = cam.S, bl = blockIdx.y, b = view0 + bl;
+    if (threadIdx.x < 9) sRt[threadIdx.x] = R[b * 9 + threadIdx.x];
+    else if (threadIdx.x < 12) sRt[threadIdx.x] = t[b * 3 + threadIdx.x - 9];
     __syncthreads();
-    // vertex chain: (u,v,z) NDC gradient -> 3-D point -> depth, R, t
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
-    for (int i = tid; i < TV * TV; i += SPLAT_THREADS) {
-        const int vy = ty0 + i / TV, vx = tx0 + i % TV;
-        const float gu = sm.sg[i * 3], gv = sm.sg[i * 3 + 1], gz = sm.sg[i * 3 + 2];
-        if (vy >= S || vx >= S || (gu == 0.f && gv == 0.f && gz == 0.f)) continue;
-        float ray[3], q[3];
-        pixel_ray(cam, vx, vy, ray);
-        const float d = dimg[vy * S + vx];
-        warp_point(cam, sRt, sRt + 9, ray, d, q);
-        const float v[3] = {ray[0] * d, ray[1] * d, ray[2] * d - cam.rcd};
-        const float zz = q[2] + 1e-9f, iz = 1.0f / zz;
-        const float x_ = q[0] * iz, y_ = q[1] * iz;
-        const float gup = gu * (2.0f / cam.os), gvp = -gv * (2.0f / cam.os);
-        const float gx_ = gup * cam.K[0] + gvp * cam.K[3], gy_ = gup * cam.K[1] + gvp * cam.K[4];
-        const float gq[3] = {gx_ * iz, gy_ * iz, gz - (gx_ * x_ + gy_ * y_) * iz};
-        float gd = 0.f;
+    if (v < S * S) {
+        const float* gp = vgrad + ((long)bl * S * S + v) * 3;
+        const float gu = gp[0], gv = gp[1], gz = gp[2];
+        if (gu != 0.f || gv != 0.f || gz != 0.f) {
+            const int vy = v / S, vx = v - vy * S;
+            float ray[3], q[3];
+            pixel_ray(cam, vx, vy, ray);
+            const float d = depth[(long)(b / vpi) * dstride + v];
+            warp_point(cam, sRt, sRt + 9, ray, d, q);
+            const float p3[3] = {ray[0] * d, ray[1] * d, ray[2] * d - cam.rcd};
+            const float zz = q[2] + 1e-9f, iz = 1.0f / zz;
+            const float x_ = q[0] * iz, y_ = q[1] * iz;
+            const float gup = gu * (2.0f / cam.os), gvp = -gv * (2.0f / cam.os);
+            const float gx_ = gup * cam.K[0] + gvp * cam.K[3], gy_ = gup * cam.K[1] + gvp * cam.K[4];
+            const float gq[3] = {gx_ * iz, gy_ * iz, gz - (gx_ * x_ + gy_ * y_) * iz};
+            float gd = 0.f;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float gvk = gq[0] * sRt[k] + gq[1] * sRt[3 + k] + gq[2] * sRt[6 + k];
-            gd += gvk * ray[k];
+            for (int k = 0; k < 3; k++) {
+                const float gvk = gq[0] * sRt[k] + gq[1] * sRt[3 + k] + gq[2] * sRt[6 + k];
+                gd += gvk * ray[k];
 #pragma unroll
-            for (int j = 0; j < 3; j++) acc[3 * j + k] += gq[j] * v[k];
-            acc[9 + k] += gq[k];
+                for (int jj = 0; jj < 3; jj++) acc[3 * jj + k] += gq[jj] * p3[k];
+                acc[9 + k] += gq[k];
+            }
+            float* o = &grad_depth[(long)(b / vpi) * gdstride + v];
+            if (vpi == 1 && gdstride != 0) *o += gd;   // one view per depth map: this thread is the only writer
+            else atomicAdd(o, gd);
         }
-        atomicAdd(&grad_depth[(long)(b / vpi) * gdstride + vy * S + vx], gd);
     }
     if (grad_R) {
         float accR[9], acct[3];
@@ -616,8 +673,8 @@ k_raster_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
         for (int k = 0; k < 9; k++) accR[k] = acc[k];
 #pragma unroll
         for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
-        block_accumulate<9, SPLAT_THREADS>(accR, grad_R + b * 9);
-        block_accumulate<3, SPLAT_THREADS>(acct, grad_t + b * 3);
+        block_accumulate<9, PIX_THREADS>(accR, grad_R + b * 9);
+        block_accumulate<3, PIX_THREADS>(acct, grad_t + b * 3);
     }
 }
 
@@ -929,16 +986,14 @@ k_resolve_rgb(const Cam cam, unsigned long long* __restrict__ zbuf, const float*
     }
 }
 
-// k_raster_bwd needs > 48 KB of shared memory: opt in once per device context
+// k_splat needs > 48 KB of shared memory: opt in once per device context
 inline void raster_smem_optin() {
     static std::once_flag once;
     std::call_once(once, [] {
-        cudaFuncSetAttribute(k_raster_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
         cudaFuncSetAttribute(k_splat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
         cudaFuncSetAttribute(k_splat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
     });
 }
-inline size_t bwd_smem_bytes() { raster_smem_optin(); return sizeof(BwdSmem); }
 inline size_t fwd_smem_bytes() { raster_smem_optin(); return sizeof(TileSmem); }
 
 // compares the shared-reciprocal division (g2s_math.cuh dvd_y) with __fdiv_rn bit for bit on pseudo-random operands
@@ -975,9 +1030,32 @@ inline int chunk_views_for(int S, int cap) {
     return (int)v;
 }
 
+// raster backward of one chunk of views: raster_ws = [nv, 7, S, S] floats = g_sub | proj (3) | vgrad (3)
+inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
+                              const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth, long gdstride,
+                              float* grad_R, float* grad_t, cudaStream_t st);
+
 inline dim3 pix_grid(long npix, int batch) { return dim3((unsigned)((npix + PIX_THREADS - 1) / PIX_THREADS), batch); }
 
 inline bool bad_size(int S) { return S < 2 || S > 2048; }
+
+inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
+                              const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth, long gdstride,
+                              float* grad_R, float* grad_t, cudaStream_t st) {
+    const int S = c.S;
+    const size_t img = (size_t)S * S;
+    float* g_sub = raster_ws;
+    float* proj = raster_ws + (size_t)nv * img;
+    float* vgrad = proj + (size_t)nv * 3 * img;
+    cudaMemsetAsync(vgrad, 0, sizeof(float) * nv * 3 * img, st);
+    { Launch l_(K_PROJECT, st);
+      k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj); }
+    { Launch l_(K_RASTER_BWD, st);
+      k_raster_bwd_px<<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
+    { Launch l_(K_VERTEX_BWD, st);
+      k_vertex_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
+                                                                     gdstride, grad_R, grad_t); }
+}
 
 }  // namespace
 
@@ -1035,14 +1113,13 @@ int g2s_warp_depth_bwd(const g2s_camera* cam, const float* depth, long depth_vie
     if ((grad_R == nullptr) != (grad_t == nullptr)) return G2S_ERR_NULL;
     if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    const int S = c.S;
     cudaStream_t st = (cudaStream_t)stream;
     const long n = (long)n_views * S * S;
     { Launch l_(K_CLAMP_GRAD, st); k_clamp_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(recon_depth, grad_recon_depth, c.clamp_lo, c.clamp_hi, n,
                                                               grad_sub_ws); }
-    { Launch l_(K_RASTER_BWD, st); k_raster_bwd<<<dim3(tiles * tiles, n_views), SPLAT_THREADS, bwd_smem_bytes(), st>>>(
-        c, depth, depth_view_stride, 1, R, t, face_idx, grad_sub_ws, grad_depth, grad_depth_view_stride, grad_R, grad_t,
-        tiles, 0); }
+    launch_raster_bwd(c, depth, depth_view_stride, 1, R, t, face_idx, grad_sub_ws, n_views, 0, grad_depth,
+                      grad_depth_view_stride, grad_R, grad_t, st);
     return launch_status();
 }
 
@@ -1151,7 +1228,7 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
     if (n_images <= 0 || views_per_image <= 0 || n_views > (1L << 30) || ws_views <= 0 || bad_size(cam->image_size))
         return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    const int S = c.S;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t img_f = (size_t)S * S;
     cudaMemsetAsync(grad_R, 0, sizeof(float) * n_views * 9, st);
@@ -1172,10 +1249,8 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
         { Launch l_(K_BWD_TEX, st);
           k_render_bwd_tex<<<pix_grid((long)S * S, img_hi - img_lo + 1), PIX_THREADS, 0, st>>>(S, fa, nv, grad_tex_ws, grad_albedo,
                                                                                              grad_normal_ws, grad_light); }
-        { Launch l_(K_RASTER_BWD, st);
-          k_raster_bwd<<<dim3(tiles * tiles, nv), SPLAT_THREADS, bwd_smem_bytes(), st>>>(
-              c, depth, (long)S * S, views_per_image, R, t, face_idx, grad_sub_ws, grad_depth, (long)S * S, grad_R, grad_t,
-              tiles, (int)v0); }
+        launch_raster_bwd(c, depth, (long)S * S, views_per_image, R, t, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,
+                          (long)S * S, grad_R, grad_t, st);
     }
     for (int i0 = 0; i0 < n_images; i0 += 32768) {
         const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;

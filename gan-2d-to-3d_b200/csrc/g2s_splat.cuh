@@ -1,20 +1,22 @@
-// g2s_splat.cuh -- the two tile rasterisation kernels (forward splat, backward gather) of the grid mesh.
+// g2s_splat.cuh -- the forward tile rasteriser of the grid mesh (k_splat) and the per-hit arithmetic shared with
+// the pixel-centric backward (k_raster_bwd_px in g2s_kernels.cu).
 //
-// Replaces neural_renderer's forward_face_index_map (every sub-pixel loops over every face) and
-// backward_depth_map (one float atomicAdd x 9 per covered sub-pixel into grad_faces[B,F,3,3]).
+// Replaces neural_renderer's forward_face_index_map, where every sub-pixel loops over every face.
 //
-// Structure (both kernels): one CTA per TILE x TILE block of quads of one view.
+// One CTA per TILE x TILE block of quads of one view:
 //   1. project the tile's (TILE+1)^2 vertices once into shared memory (u, v, z);
-//   2. one thread per quad walks the sub-pixel boxes of its front-facing windings and runs only the
-//      cheap candidate test (forward: the three edge functions; backward: face_idx == this face).
-//      Candidates that pass are appended to a HIT QUEUE in shared memory; faces with a large box go to a
-//      second queue and are scanned by whole warps;
-//   3. the faces that own at least one hit get their 3x3 inverse computed ONCE, by consecutive threads,
-//      into a shared-memory face table;
-//   4. the hit queue is drained by consecutive threads: weights, perspective z, then the 64-bit
-//      atomicMin into the z-buffer (forward) or the per-face gradient accumulators (backward).
-// Steps 3 and 4 hold the IEEE divisions -- ~90% of the instructions -- and run fully converged; in the
-// naive per-thread form the same code ran at 3-7 active lanes per warp (ncu, profiles/).
+//   2. candidate scan -- only the cheap, exact inside test (three edge functions, loop invariants hoisted):
+//        * quads whose two triangles fit one SB x SB sub-pixel box are scanned by their owning thread with UNIFORM
+//          control flow (loop bounds = warp maxima, per-lane predicates) into two 16-bit hit masks;
+//        * triangles with a box up to MB x MB go to a queue scanned by 8-lane groups (one lane per row);
+//        * larger boxes (the 1-px depth-step walls stretch to >100 sub-pixels under yaw) are scanned by whole
+//          warps, row by row over a conservative per-row extent.
+//      Hits are appended to a HIT QUEUE in shared memory (one atomic per warp step);
+//   3. the faces that own at least one hit get their 3x3 inverse computed ONCE, by consecutive threads, into a
+//      shared-memory face table;
+//   4. the hit queue is drained by consecutive threads: weights, perspective z, 64-bit atomicMin into the z-buffer.
+// Steps 3 and 4 hold the correctly rounded divisions and run fully converged; in the first per-thread form the
+// same code ran at 3-7 active lanes per warp (ncu, profiles/r01_*).
 #pragma once
 #include "g2s_raster.cuh"
 
@@ -30,9 +32,10 @@ struct TileSmem {
     uint32_t hq_pix[HQ_CAP];
     uint16_t hq_code[HQ_CAP];
     uint16_t fq[NSLOT];
-    uint16_t lq[2 * NSLOT];
+    uint16_t lq[NSLOT];
+    uint16_t mq[NSLOT];
     float sRt[12];
-    int n_hq, n_fq, n_lq;
+    int n_hq, n_fq, n_lq, n_mq;
 };
 
 // code = slot | rev << 9, slot = quad * 2 + tri
@@ -172,9 +175,8 @@ __device__ __forceinline__ int queue_alloc(int* counter) {
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
-// What a kernel does with candidates and hits.
-//   FWD: candidate test = inside test; hit = atomicMin of the packed key.
-//   BWD: candidate test = face-index map lookup; hit = accumulate g * zp^2 * w_k per face.
+// What the forward kernel does with candidates and hits: candidate test = inside test; hit = atomicMin of the
+// packed key.  (The backward needs no scan: the face-index map already names the owner of every sub-pixel.)
 struct FwdOps {
     unsigned long long* zb;
     float near, far;
@@ -189,13 +191,28 @@ struct FwdOps {
             dx12 = sub(f.x2, f.x1); dy12 = sub(f.y2, f.y1);
             dx20 = sub(f.x0, f.x2); dy20 = sub(f.y0, f.y2);
         }
-        __device__ __forceinline__ void row(const FwdOps& o, int yi) {
-            const float yp = o.pc(yi);
+        __device__ __forceinline__ void row_y(float yp) {
             a0 = mul(sub(yp, y0), dx01); a1 = mul(sub(yp, y1), dx12); a2 = mul(sub(yp, y2), dx20);
         }
-        __device__ __forceinline__ bool test(const FwdOps& o, int xi) const {
-            const float xp = o.pc(xi);
+        __device__ __forceinline__ bool test_x(float xp) const {
             return !(a0 < mul(sub(xp, x0), dy01)) && !(a1 < mul(sub(xp, x1), dy12)) && !(a2 < mul(sub(xp, x2), dy20));
+        }
+        __device__ __forceinline__ void row(const FwdOps& o, int yi) { row_y(o.pc(yi)); }
+        __device__ __forceinline__ bool test(const FwdOps& o, int xi) const { return test_x(o.pc(xi)); }
+    };
+    // both triangles of a quad scanned over one box: bit 0 = first triangle, bit 1 = second
+    struct QuadScan {
+        Scan A, B;
+        __device__ __forceinline__ void init(const FwdOps& o, const Tri& fA, int faceA, const Tri& fB, int faceB) {
+            A.init(o, fA, faceA); B.init(o, fB, faceB);
+        }
+        __device__ __forceinline__ void row(const FwdOps& o, int yi) {
+            const float yp = o.pc(yi);
+            A.row_y(yp); B.row_y(yp);
+        }
+        __device__ __forceinline__ unsigned test(const FwdOps& o, int xi) const {
+            const float xp = o.pc(xi);
+            return (A.test_x(xp) ? 1u : 0u) | (B.test_x(xp) ? 2u : 0u);
         }
     };
     __device__ __forceinline__ void hit(const float* rec, int code, int face, int xi, int yi) const {
@@ -205,71 +222,6 @@ struct FwdOps {
     }
     __device__ __forceinline__ void hit_direct(const float* rec, int code, int face, int xi, int yi) const {
         hit(rec, code, face, xi, yi);
-    }
-};
-
-// scatter one face's accumulated A_k = sum g * zp^2 * w_k to its three vertices' (u,v,z) gradient
-// accumulators in shared memory ([nr] backward_depth_map, factored per face)
-__device__ __forceinline__ void face_scatter(const float* rec, const float A[3], int is, float* sg, int code) {
-    const float z[3] = {rec[9], rec[10], rec[11]};
-    // tmp[l] = -sum_m face_inv[m][l] / z_m
-    const float t0 = -(rec[0] / z[0] + rec[3] / z[1] + rec[6] / z[2]);
-    const float t1 = -(rec[1] / z[0] + rec[4] / z[1] + rec[7] / z[2]);
-    const float hs = 0.5f * (float)is;
-    const int quad = (code & 511) >> 1, qy = quad / TILE, qx = quad % TILE, w = (code & 1) + ((code >> 9) << 1);
-    const int a = (qy * TV + qx) * 3, b = ((qy + 1) * TV + qx) * 3, c = (qy * TV + qx + 1) * 3,
-              d = ((qy + 1) * TV + qx + 1) * 3;
-    int v[3];
-    switch (w) {
-        case 0: v[0] = a; v[1] = b; v[2] = c; break;
-        case 1: v[0] = c; v[1] = b; v[2] = d; break;
-        case 2: v[0] = c; v[1] = b; v[2] = a; break;
-        default: v[0] = d; v[1] = b; v[2] = c; break;
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        if (A[k] == 0.f) continue;
-        atomicAdd(&sg[v[k] + 0], -t0 * A[k] * hs);
-        atomicAdd(&sg[v[k] + 1], -t1 * A[k] * hs);
-        atomicAdd(&sg[v[k] + 2], A[k] / (z[k] * z[k]));
-    }
-}
-
-struct BwdOps {
-    const int* fmap;
-    const float* gsub;
-    float* sA;   // [NSLOT][3] per-face accumulators (shared memory)
-    float* sg;   // [TV*TV][3] vertex (u,v,z) gradient accumulators (shared memory)
-    float near, far;
-    int is, S;
-    struct Scan {
-        const int* row_ptr;
-        int face;
-        __device__ __forceinline__ void init(const BwdOps&, const Tri&, int face_) { face = face_; }
-        __device__ __forceinline__ void row(const BwdOps& o, int yi) { row_ptr = o.fmap + (long)(o.is - 1 - yi) * o.is; }
-        __device__ __forceinline__ bool test(const BwdOps&, int xi) const { return __ldg(&row_ptr[xi]) == face; }
-    };
-    __device__ __forceinline__ bool contrib(const float* rec, int xi, int yi, float A[3]) const {
-        const int r = is - 1 - yi;
-        const float g = gsub[(r >> 1) * S + (xi >> 1)];
-        if (g == 0.f) return false;
-        float w[3], zp = 0.f;
-        record_weights_depth(rec, xi, yi, near, far, w, &zp);
-        const float s = g * zp * zp;
-        A[0] = s * w[0]; A[1] = s * w[1]; A[2] = s * w[2];
-        return true;
-    }
-    __device__ __forceinline__ void hit(const float* rec, int code, int face, int xi, int yi) const {
-        float A[3];
-        if (!contrib(rec, xi, yi, A)) return;
-        float* acc = &sA[(code & 511) * 3];
-        atomicAdd(&acc[0], A[0]);
-        atomicAdd(&acc[1], A[1]);
-        atomicAdd(&acc[2], A[2]);
-    }
-    __device__ __forceinline__ void hit_direct(const float* rec, int code, int face, int xi, int yi) const {
-        float A[3];
-        if (contrib(rec, xi, yi, A)) face_scatter(rec, A, is, sg, code);
     }
 };
 
@@ -337,119 +289,242 @@ __device__ __forceinline__ void row_extent(const float px[3], const float py[3],
     *xb = min(bb.x1, (int)ceilf(hi + 1.0f));
 }
 
+template <class Ops>
+__device__ __noinline__ void scan_degenerate(const Ops& ops, const Tri fr, const BBox bb, int code_r, int Q, int S,
+                                             int ty0, int tx0) {
+    const int face_r = code_face(code_r, Q, S, ty0, tx0), is = 2 * S;
+    typename Ops::Scan sr;
+    sr.init(ops, fr, face_r);
+    for (int yi = bb.y0; yi <= bb.y1; yi++) {
+        sr.row(ops, yi);
+        for (int xi = bb.x0; xi <= bb.x1; xi++)
+            if (sr.test(ops, xi)) hit_inline(ops, fr, code_r, face_r, xi, yi, is);
+    }
+}
+
+// One triangle of a quad: which winding is front-facing, its box, whether both windings pass (degenerate).
+struct TriClass {
+    Tri f;        // in the order of the front winding
+    BBox bb;
+    int rev;
+    bool act, dup;
+};
+__device__ __forceinline__ TriClass classify(const float* sv, int qy, int qx, int tri, int is, bool quad_ok) {
+    TriClass c;
+    c.f = tile_winding(sv, qy, qx, tri);
+    c.bb.x0 = c.bb.y0 = 0; c.bb.x1 = c.bb.y1 = -1;
+    const bool boxed = quad_ok && tri_bbox(c.f, is, c.bb);   // the fill_back copy has the same box
+    const bool front0 = boxed && !tri_is_back(c.f);
+    const bool front1 = boxed && !tri_is_back(reversed(c.f));
+    c.rev = front0 ? 0 : 1;
+    if (c.rev) c.f = reversed(c.f);
+    c.act = front0 || front1;
+    c.dup = front0 && front1;
+    return c;
+}
+
+// queued (medium / large box) face record, aliased on the face table (which is only written after these phases)
+constexpr int REC_STRIDE = 9;   // x0,y0,x1,y1,x2,y2, box x (x0 | x1<<16), box y, code
+__device__ __forceinline__ void rec_store(float* recs, int slot, const TriClass& c, int code) {
+    float* r = &recs[slot * REC_STRIDE];
+    r[0] = c.f.x0; r[1] = c.f.y0; r[2] = c.f.x1; r[3] = c.f.y1; r[4] = c.f.x2; r[5] = c.f.y2;
+    r[6] = __uint_as_float((uint32_t)c.bb.x0 | ((uint32_t)c.bb.x1 << 16));
+    r[7] = __uint_as_float((uint32_t)c.bb.y0 | ((uint32_t)c.bb.y1 << 16));
+    r[8] = __uint_as_float((uint32_t)code);
+}
+__device__ __forceinline__ void rec_load(const float* recs, int slot, Tri& f, BBox& bb) {
+    const float* r = &recs[slot * REC_STRIDE];
+    f.x0 = r[0]; f.y0 = r[1]; f.x1 = r[2]; f.y1 = r[3]; f.x2 = r[4]; f.y2 = r[5];
+    f.z0 = f.z1 = f.z2 = 0.f;
+    const uint32_t bx = __float_as_uint(r[6]), by = __float_as_uint(r[7]);
+    bb.x0 = (int)(bx & 0xffffu); bb.x1 = (int)(bx >> 16);
+    bb.y0 = (int)(by & 0xffffu); bb.y1 = (int)(by >> 16);
+}
+
+constexpr int MB = 8;   // medium boxes: at most MB x MB sub-pixels, scanned by 8-lane groups (one lane per row)
+
+// hits of one warp step -> hit queue (one atomic per warp); every lane calls with its mask (bit k = hit at column
+// x0 + k of row yi) and code
+template <class Ops>
+__device__ __forceinline__ void push_row_masks(TileSmem& sm, const Ops& ops, unsigned mask, int x0, int yi, int code,
+                                               int face, int is) {
+    int total;
+    const int off = warp_excl_scan(__popc(mask), &total);
+    if (total == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&sm.n_hq, total);
+    base = __shfl_sync(0xffffffffu, base, 0) + off;
+    while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (base < HQ_CAP) {
+            sm.hq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)(x0 + bit);
+            sm.hq_code[base] = (uint16_t)code;
+        } else {
+            hit_inline(ops, code_tri(sm.sv, code), code, face, x0 + bit, yi, is);
+        }
+        base++;
+    }
+}
+
 // Steps 2-4 of the header comment.
 template <class Ops>
 __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, const Cam& cam, int ty0, int tx0) {
     const int tid = threadIdx.x, S = cam.S, is = 2 * S, Q = (S - 1) * (S - 1), lane = tid & 31;
     const int qy = tid / TILE, qx = tid % TILE;
     const bool quad_ok = ty0 + qy < S - 1 && tx0 + qx < S - 1;
-    // ---- small boxes: every thread scans the (at most) SB x SB box of its triangle's front winding with uniform
-    // control flow (loop bounds = warp maxima, per-lane predicates), collecting a hit mask in a register
-#pragma unroll 1
-    for (int tri = 0; tri < 2; tri++) {
-        Tri f = tile_winding(sm.sv, qy, qx, tri);
-        BBox bb;
-        const bool boxed = quad_ok && tri_bbox(f, is, bb);   // the fill_back copy has the same box
-        const bool front0 = boxed && !tri_is_back(f);
-        const bool front1 = boxed && !tri_is_back(reversed(f));
-        const int rev = front0 ? 0 : 1;
-        if (rev) f = reversed(f);
-        const bool front = front0 || front1;
-        const int bw = boxed ? bb.x1 - bb.x0 + 1 : 0, bh = boxed ? bb.y1 - bb.y0 + 1 : 0;
-        const bool large = front && (bw > SB || bh > SB);
-        const bool small = front && !large;
-        const int code = (tid * 2 + tri) | (rev << 9);
-        const int face = code_face(code, Q, S, ty0, tx0);
-        if (large) sm.lq[atomicAdd(&sm.n_lq, 1)] = (uint16_t)code;
-        typename Ops::Scan sc;
-        sc.init(ops, f, face);
-        const int mh = (int)__reduce_max_sync(0xffffffffu, small ? (unsigned)bh : 0u);
-        const int mw = (int)__reduce_max_sync(0xffffffffu, small ? (unsigned)bw : 0u);
-        unsigned mask = 0;
+    float* recs = sm.ftab;   // alias: queued-face records live where the face table will be built later
+    // ---- quads whose two triangles fit one SB x SB box: scanned by the owning thread with uniform control flow
+    {
+        TriClass A = classify(sm.sv, qy, qx, 0, is, quad_ok), B = classify(sm.sv, qy, qx, 1, is, quad_ok);
+        const int codeA = (tid * 2) | (A.rev << 9), codeB = (tid * 2 + 1) | (B.rev << 9);
+        const int faceA = A.act ? code_face(codeA, Q, S, ty0, tx0) : -2, faceB = B.act ? code_face(codeB, Q, S, ty0, tx0) : -2;
+        BBox u;
+        u.x0 = min(A.act ? A.bb.x0 : 1 << 20, B.act ? B.bb.x0 : 1 << 20);
+        u.y0 = min(A.act ? A.bb.y0 : 1 << 20, B.act ? B.bb.y0 : 1 << 20);
+        u.x1 = max(A.act ? A.bb.x1 : -1, B.act ? B.bb.x1 : -1);
+        u.y1 = max(A.act ? A.bb.y1 : -1, B.act ? B.bb.y1 : -1);
+        const int uw = u.x1 - u.x0 + 1, uh = u.y1 - u.y0 + 1;
+        const bool any_act = A.act || B.act;
+        const bool small = any_act && uw <= SB && uh <= SB;
+        if (any_act && !small) {
+            // queue each active triangle on its own: medium (<= MB x MB) for 8-lane groups, large for whole warps
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const TriClass& c = k ? B : A;
+                if (!c.act) continue;
+                const int code = k ? codeB : codeA;
+                rec_store(recs, code & 511, c, code);
+                const bool medium = c.bb.x1 - c.bb.x0 < MB && c.bb.y1 - c.bb.y0 < MB;
+                if (medium) sm.mq[atomicAdd(&sm.n_mq, 1)] = (uint16_t)code;
+                else sm.lq[atomicAdd(&sm.n_lq, 1)] = (uint16_t)code;
+            }
+        }
+        typename Ops::QuadScan qs;
+        qs.init(ops, A.f, faceA, B.f, faceB);
+        const unsigned actbits = (A.act ? 1u : 0u) | (B.act ? 2u : 0u);
+        const int mh = (int)__reduce_max_sync(0xffffffffu, small ? (unsigned)uh : 0u);
+        const int mw = (int)__reduce_max_sync(0xffffffffu, small ? (unsigned)uw : 0u);
+        unsigned maskA = 0, maskB = 0;
         for (int ry = 0; ry < mh; ry++) {
-            const int yi = min(bb.y0 + ry, is - 1);
-            sc.row(ops, small ? yi : 0);
+            qs.row(ops, small ? min(u.y0 + ry, is - 1) : 0);
             for (int rx = 0; rx < mw; rx++) {
-                const int xi = min(bb.x0 + rx, is - 1);
-                const bool in = small && ry < bh && rx < bw && sc.test(ops, small ? xi : 0);
-                mask |= (in ? 1u : 0u) << (ry * SB + rx);
+                unsigned r = qs.test(ops, small ? min(u.x0 + rx, is - 1) : 0) & actbits;
+                if (!(small && ry < uh && rx < uw)) r = 0;
+                maskA |= (r & 1u) << (ry * SB + rx);
+                maskB |= (r >> 1) << (ry * SB + rx);
             }
         }
         // queue the hits: one atomic per warp
         int total;
-        const int off = warp_excl_scan(__popc(mask), &total);
+        const int off = warp_excl_scan(__popc(maskA) + __popc(maskB), &total);
         if (total) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&sm.n_hq, total);
             base = __shfl_sync(0xffffffffu, base, 0) + off;
-            unsigned m = mask;
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const int xi = bb.x0 + (bit & (SB - 1)), yi = bb.y0 + bit / SB;
-                if (base < HQ_CAP) {
-                    sm.hq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)xi;
-                    sm.hq_code[base] = (uint16_t)code;
-                } else {
-                    hit_inline(ops, f, code, face, xi, yi, is);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                unsigned m = k ? maskB : maskA;
+                const int code = k ? codeB : codeA;
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int xi = u.x0 + (bit & (SB - 1)), yi = u.y0 + bit / SB;
+                    if (base < HQ_CAP) {
+                        sm.hq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)xi;
+                        sm.hq_code[base] = (uint16_t)code;
+                    } else {
+                        hit_inline(ops, k ? B.f : A.f, code, k ? faceB : faceA, xi, yi, is);
+                    }
+                    base++;
                 }
-                base++;
             }
-            const unsigned owners = __ballot_sync(0xffffffffu, mask != 0);
+            const int nown = (maskA ? 1 : 0) + (maskB ? 1 : 0);
+            int ftotal;
+            const int foff = warp_excl_scan(nown, &ftotal);
+            int fbase = 0;
+            if (lane == 0) fbase = atomicAdd(&sm.n_fq, ftotal);
+            fbase = __shfl_sync(0xffffffffu, fbase, 0) + foff;
+            if (maskA) sm.fq[fbase++] = (uint16_t)codeA;
+            if (maskB) sm.fq[fbase] = (uint16_t)codeB;
+        }
+        // degenerate triangles whose two windings both pass the back-face test (rounding): the reversed copy
+        // bypasses the queues and the face table, whose slot the first winding owns
+        if (A.dup) scan_degenerate(ops, reversed(A.f), A.bb, (tid * 2) | (1 << 9), Q, S, ty0, tx0);
+        if (B.dup) scan_degenerate(ops, reversed(B.f), B.bb, (tid * 2 + 1) | (1 << 9), Q, S, ty0, tx0);
+    }
+    __syncthreads();
+    // ---- medium boxes: 8-lane groups, one lane per row, uniform MB-column scan
+    const int nm = sm.n_mq;
+    for (int e0 = (tid >> 5) * 4; e0 < nm; e0 += (SPLAT_THREADS / 32) * 4) {
+        const int e = e0 + (lane >> 3), r = lane & 7;
+        const bool valid = e < nm;
+        const int code = valid ? sm.mq[e] : 0;
+        Tri f;
+        BBox bb;
+        rec_load(recs, code & 511, f, bb);
+        const int face = code_face(code, Q, S, ty0, tx0);
+        const int bw = bb.x1 - bb.x0 + 1, bh = bb.y1 - bb.y0 + 1;
+        const bool rowok = valid && r < bh;
+        typename Ops::Scan sc;
+        sc.init(ops, f, face);
+        const int yi = rowok ? bb.y0 + r : 0;
+        sc.row(ops, yi);
+        const int mw = (int)__reduce_max_sync(0xffffffffu, rowok ? (unsigned)bw : 0u);
+        unsigned mask = 0;
+        for (int rx = 0; rx < mw; rx++) {
+            const bool in = rowok && rx < bw && sc.test(ops, rowok ? min(bb.x0 + rx, is - 1) : 0);
+            mask |= (in ? 1u : 0u) << rx;
+        }
+        push_row_masks(sm, ops, mask, bb.x0, yi, code, face, is);
+        // one face-table request per face with a hit
+        const unsigned hitlanes = __ballot_sync(0xffffffffu, mask != 0);
+        const bool owner = r == 0 && ((hitlanes >> (lane & 24)) & 0xffu) != 0;
+        const unsigned owners = __ballot_sync(0xffffffffu, owner);
+        if (owners) {
             int fbase = 0;
             if (lane == 0) fbase = atomicAdd(&sm.n_fq, __popc(owners));
             fbase = __shfl_sync(0xffffffffu, fbase, 0);
-            if (mask) sm.fq[fbase + __popc(owners & ((1u << lane) - 1u))] = (uint16_t)code;
-        }
-        if (front0 && front1) {
-            // degenerate triangle whose two windings both pass the back-face test (rounding): the reversed copy
-            // bypasses the queues and the face table, whose slot the first winding owns
-            const Tri fr = reversed(f);
-            const int code_r = (tid * 2 + tri) | (1 << 9);
-            const int face_r = code_face(code_r, Q, S, ty0, tx0);
-            typename Ops::Scan sr;
-            sr.init(ops, fr, face_r);
-            for (int yi = bb.y0; yi <= bb.y1; yi++) {
-                sr.row(ops, yi);
-                for (int xi = bb.x0; xi <= bb.x1; xi++)
-                    if (sr.test(ops, xi)) hit_inline(ops, fr, code_r, face_r, xi, yi, is);
-            }
+            if (owner) sm.fq[fbase + __popc(owners & ((1u << lane) - 1u))] = (uint16_t)code;
         }
     }
-    __syncthreads();
-    // ---- large boxes: one warp per face; wide boxes row by row over a conservative per-row extent, narrow ones
-    // flattened over the box
+    // ---- large boxes: one warp per face, row by row over a conservative per-row extent, lanes across the row
     const int nl = sm.n_lq;
     for (int e = tid >> 5; e < nl; e += SPLAT_THREADS / 32) {
         const int code = sm.lq[e];
-        const Tri f = code_tri(sm.sv, code);
-        const int face = code_face(code, Q, S, ty0, tx0);
+        Tri f;
         BBox bb;
-        tri_bbox(f, is, bb);
+        rec_load(recs, code & 511, f, bb);
+        const int face = code_face(code, Q, S, ty0, tx0);
         typename Ops::Scan sc;
         sc.init(ops, f, face);
-        const int bw = bb.x1 - bb.x0 + 1, n = bw * (bb.y1 - bb.y0 + 1);
+        const float px[3] = {ndc_to_pix(f.x0, is), ndc_to_pix(f.x1, is), ndc_to_pix(f.x2, is)};
+        const float py[3] = {ndc_to_pix(f.y0, is), ndc_to_pix(f.y1, is), ndc_to_pix(f.y2, is)};
         bool any = false;
-        if (bw >= 24) {
-            const float px[3] = {ndc_to_pix(f.x0, is), ndc_to_pix(f.x1, is), ndc_to_pix(f.x2, is)};
-            const float py[3] = {ndc_to_pix(f.y0, is), ndc_to_pix(f.y1, is), ndc_to_pix(f.y2, is)};
-            for (int yi = bb.y0; yi <= bb.y1; yi++) {
-                int xa, xb;
-                row_extent(px, py, yi, bb, &xa, &xb);
-                sc.row(ops, yi);
-                for (int xi = xa + lane; xi <= xb; xi += 32)
-                    if (sc.test(ops, xi)) any |= push_hit(sm, ops, f, code, face, xi, yi, is);
-            }
-        } else {
-            const float inv_bw = 1.0f / (float)bw;
-            for (int idx = lane; idx < n; idx += 32) {
-                const int ry = (int)(((float)idx + 0.5f) * inv_bw);
-                sc.row(ops, bb.y0 + ry);
-                if (sc.test(ops, bb.x0 + idx - ry * bw))
-                    any |= push_hit(sm, ops, f, code, face, bb.x0 + idx - ry * bw, bb.y0 + ry, is);
+        for (int yi = bb.y0; yi <= bb.y1; yi++) {
+            int xa, xb;
+            row_extent(px, py, yi, bb, &xa, &xb);
+            sc.row(ops, yi);
+            for (int x0 = xa; x0 <= xb; x0 += 32) {
+                const int xi = x0 + lane;
+                const bool in = xi <= xb && sc.test(ops, min(xi, is - 1));
+                const unsigned hits = __ballot_sync(0xffffffffu, in);
+                if (hits == 0) continue;
+                any = true;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sm.n_hq, __popc(hits));
+                base = __shfl_sync(0xffffffffu, base, 0) + __popc(hits & ((1u << lane) - 1u));
+                if (in) {
+                    if (base < HQ_CAP) {
+                        sm.hq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)xi;
+                        sm.hq_code[base] = (uint16_t)code;
+                    } else {
+                        hit_inline(ops, code_tri(sm.sv, code), code, face, xi, yi, is);
+                    }
+                }
             }
         }
-        any = __any_sync(0xffffffffu, any);
         if (lane == 0 && any) sm.fq[atomicAdd(&sm.n_fq, 1)] = (uint16_t)code;
     }
     __syncthreads();

@@ -71,7 +71,8 @@ int g2s_warp_depth_fwd(const g2s_camera *cam, const float *depth, long depth_vie
  * through flip / 2x2 average / clamp on one side and gather / projection / rotation on the other.
  * grad_depth is ACCUMULATED (caller zero-fills) with `grad_depth_view_stride` floats between views
  * (0 = sum over views into one [S,S] map); grad_R [n_views,3,3] and grad_t [n_views,3] are
- * ACCUMULATED too (NULL to skip both). */
+ * ACCUMULATED too (NULL to skip both).  Workspace grad_sub_ws: n_views * 7 * S * S floats (masked quarter
+ * gradient | projected vertices | vertex gradients). */
 int g2s_warp_depth_bwd(const g2s_camera *cam, const float *depth, long depth_view_stride, const float *R,
                        const float *t, int n_views, const int32_t *face_idx, const float *recon_depth,
                        const float *grad_recon_depth, float *grad_sub_ws, float *grad_depth,
@@ -122,7 +123,7 @@ int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float 
                          float *recon_depth, int32_t *face_idx, void *stream);
 
 /* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
- * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,S,S],
+ * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,7,S,S] (as above),
  * grad_tex_ws [ws_views,3,S,S] (chunked like the forward), grad_normal_ws [n_images,S,S,3].
  * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
  * grad_t [n_views,3], grad_light [n_views,5]. */
