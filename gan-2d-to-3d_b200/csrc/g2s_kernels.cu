@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -116,20 +117,24 @@ __global__ void k_zbuf_init(unsigned long long* zb, long n, unsigned long long k
 
 // Forward rasterisation of the grid mesh of one view into the packed-key z-buffer (g2s_splat.cuh).
 // grid = (tiles, n_views), block = TILE*TILE threads (one per quad).
+#ifndef G2S_SPLAT_MINBLOCKS
+#define G2S_SPLAT_MINBLOCKS (512 / SPLAT_THREADS)
+#endif
 template <bool FROM_VERTS>
-__global__ void __launch_bounds__(SPLAT_THREADS, 3)
+__global__ void __launch_bounds__(SPLAT_THREADS, G2S_SPLAT_MINBLOCKS)
 k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
         const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
         int tiles_x, int view0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
     const int tid = threadIdx.x, bl = blockIdx.y, b = view0 + bl, S = cam.S, is = 2 * S;
-    const int ty0 = (blockIdx.x / tiles_x) * TILE, tx0 = (blockIdx.x % tiles_x) * TILE;
+    const int ty0 = (blockIdx.x / tiles_x) * TILE_H, tx0 = (blockIdx.x % tiles_x) * TILE;
     if (!FROM_VERTS) {
         if (tid < 9) sm.sRt[tid] = R[b * 9 + tid];
         else if (tid < 12) sm.sRt[tid] = t[b * 3 + tid - 9];
     }
-    if (tid == 0) sm.n_hq = sm.n_fq = sm.n_lq = sm.n_mq = 0;
+    if (tid == 0) sm.n_hq = sm.n_fq = sm.n_tq = 0;
+    if (tid < NSLOT / 32) sm.owned[tid] = 0u;
     __syncthreads();
     tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
                              FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, sm.sRt, ty0, tx0, sm.sv);
@@ -1094,9 +1099,9 @@ int g2s_warp_depth_fwd(const g2s_camera* cam, const float* depth, long depth_vie
     if (!cam || !depth || !R || !t || !zbuf || !recon_depth) return G2S_ERR_NULL;
     if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, depth_view_stride, 1, R, t,
+    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles_y, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, depth_view_stride, 1, R, t,
                                                                           nullptr, (unsigned long long*)zbuf, tiles, 0); }
     FusedArgs fa = {};
     { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid2(S, n_views), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, recon_depth,
@@ -1181,7 +1186,28 @@ int g2s_sample_bwd(const float* input, long input_batch_stride, const float* gri
     return launch_status();
 }
 
-int g2s_chunk_views(int image_size) { return bad_size(image_size) ? 0 : chunk_views_for(image_size, 1 << 20); }
+// backward scratch does not need L2 residency as much as it needs long launches (measured: fewer, larger launches
+// win): cap the chunk by scratch memory only (~1 GB)
+int g2s_chunk_views_bwd(int image_size) {
+    if (bad_size(image_size)) return 0;
+    if (const char* e = getenv("G2S_CHUNK_VIEWS_BWD_128")) {
+        const long v = atol(e) * 128L * 128L / ((long)image_size * image_size);
+        if (v >= 1) return (int)v;
+    }
+    const long per_view = 10L * image_size * image_size * 4;   // 7 S^2 (raster scratch) + 3 S^2 (texture gradient)
+    long v = (1L << 30) / per_view;
+    return (int)(v < 1 ? 1 : v);
+}
+
+int g2s_chunk_views(int image_size) {
+    if (bad_size(image_size)) return 0;
+    // tuning override (views per chunk at 128^2; scaled by (128/S)^2): G2S_CHUNK_VIEWS_128
+    if (const char* e = getenv("G2S_CHUNK_VIEWS_128")) {
+        const long v = atol(e) * 128L * 128L / ((long)image_size * image_size);
+        if (v >= 1) return (int)v;
+    }
+    return chunk_views_for(image_size, 1 << 20);
+}
 
 int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
@@ -1193,7 +1219,7 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
     if (n_images <= 0 || views_per_image <= 0 || n_views > (1L << 30) || ws_views <= 0 || bad_size(cam->image_size))
         return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
     cudaStream_t st = (cudaStream_t)stream;
     for (int i0 = 0; i0 < n_images; i0 += 32768) {
         const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;
@@ -1205,7 +1231,7 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         { Launch l_(K_SPLAT, st);
-          k_splat<false><<<dim3(tiles * tiles, nv), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
+          k_splat<false><<<dim3(tiles * tiles_y, nv), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
                                                                            (unsigned long long*)zbuf, tiles, (int)v0); }
         FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0};
         { Launch l_(K_RESOLVE_FUSED, st);
@@ -1286,9 +1312,9 @@ int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const flo
     if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size) || C < 1 || C > 4) return G2S_ERR_SHAPE;
     if (tex_cube_size != 2) return G2S_ERR_UNSUPPORTED;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE;
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(tiles * tiles, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
+    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(tiles * tiles_y, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
                                                                          (unsigned long long*)zbuf, tiles, 0); }
     Bg b4 = {{0.f, 0.f, 0.f, 0.f}};
     for (int i = 0; i < C; i++) b4.c[i] = bg[i];

@@ -12,9 +12,14 @@
 
 namespace g2s {
 
-constexpr int TILE = 16;            // quads per tile side
-constexpr int TV = TILE + 1;        // vertices per tile side
-constexpr int SPLAT_THREADS = TILE * TILE;
+#ifndef G2S_TILE_H
+#define G2S_TILE_H 16
+#endif
+constexpr int TILE = 16;             // quads per tile row
+constexpr int TILE_H = G2S_TILE_H;   // quad rows per tile
+constexpr int TV = TILE + 1;         // vertices per tile row
+constexpr int TVH = TILE_H + 1;      // vertex rows per tile
+constexpr int SPLAT_THREADS = TILE * TILE_H;   // one thread per quad
 constexpr int SMALL_BOX = 12;       // boxes up to this many sub-pixels are walked by the owning thread
 
 G2S_HD int imax(int a, int b) { return a > b ? a : b; }

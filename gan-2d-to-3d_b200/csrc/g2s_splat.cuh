@@ -22,20 +22,19 @@
 
 namespace g2s {
 
-constexpr int HQ_CAP = 2048;                 // hit-queue entries per drain
-constexpr int NSLOT = 2 * TILE * TILE;       // (quad, triangle) slots of the face table
+constexpr int HQ_CAP = 8 * SPLAT_THREADS;                 // hit-queue entries per drain
+constexpr int NSLOT = 2 * TILE * TILE_H;       // (quad, triangle) slots of the face table
 constexpr int FT_STRIDE = 16;                // fi[9], z[3], rcp_seed(z)[3], pad
 
 struct TileSmem {
     float ftab[NSLOT * FT_STRIDE];
-    float sv[TV * TV * 3];
+    float sv[TV * TVH * 3];
     uint32_t hq_pix[HQ_CAP];
     uint16_t hq_code[HQ_CAP];
     uint16_t fq[NSLOT];
-    uint16_t lq[NSLOT];
-    uint16_t mq[NSLOT];
+    unsigned owned[NSLOT / 32];
     float sRt[12];
-    int n_hq, n_fq, n_lq, n_mq;
+    int n_hq, n_fq, n_tq;
 };
 
 // code = slot | rev << 9, slot = quad * 2 + tri
@@ -60,7 +59,7 @@ __device__ __forceinline__ void tile_project(const Cam& cam, const float* __rest
                                              const float* __restrict__ verts_b, const float* sRt, int ty0,
                                              int tx0, float* sv) {
     const int S = cam.S;
-    for (int i = threadIdx.x; i < TV * TV; i += SPLAT_THREADS) {
+    for (int i = threadIdx.x; i < TV * TVH; i += SPLAT_THREADS) {
         const int vy = ty0 + i / TV, vx = tx0 + i % TV;
         float ndc[3] = {0.f, 0.f, 0.f};
         if (vy < S && vx < S) {
@@ -196,6 +195,13 @@ struct FwdOps {
         }
         __device__ __forceinline__ bool test_x(float xp) const {
             return !(a0 < mul(sub(xp, x0), dy01)) && !(a1 < mul(sub(xp, x1), dy12)) && !(a2 < mul(sub(xp, x2), dy20));
+        }
+        // per-column halves of the three edge tests, and the test from them (same values as test_x)
+        __device__ __forceinline__ void col_terms(float xp, float c[3]) const {
+            c[0] = mul(sub(xp, x0), dy01); c[1] = mul(sub(xp, x1), dy12); c[2] = mul(sub(xp, x2), dy20);
+        }
+        __device__ __forceinline__ bool test_terms(const float c[3]) const {
+            return !(a0 < c[0]) && !(a1 < c[1]) && !(a2 < c[2]);
         }
         __device__ __forceinline__ void row(const FwdOps& o, int yi) { row_y(o.pc(yi)); }
         __device__ __forceinline__ bool test(const FwdOps& o, int xi) const { return test_x(o.pc(xi)); }
@@ -341,7 +347,7 @@ __device__ __forceinline__ void rec_load(const float* recs, int slot, Tri& f, BB
     bb.y0 = (int)(by & 0xffffu); bb.y1 = (int)(by >> 16);
 }
 
-constexpr int MB = 8;   // medium boxes: at most MB x MB sub-pixels, scanned by 8-lane groups (one lane per row)
+constexpr int TQ_CAP = (NSLOT * FT_STRIDE - NSLOT * REC_STRIDE);   // row tasks that fit behind the records in the table region
 
 // hits of one warp step -> hit queue (one atomic per warp); every lane calls with its mask (bit k = hit at column
 // x0 + k of row yi) and code
@@ -368,6 +374,52 @@ __device__ __forceinline__ void push_row_masks(TileSmem& sm, const Ops& ops, uns
     }
 }
 
+// Rare path (task queue full): scan one row segment on the spot.
+template <class Ops>
+__device__ __noinline__ void scan_row_inline(const Ops& ops, const Tri f, int code, int face, int yi, int xa, int xb,
+                                             int is) {
+    typename Ops::Scan sc;
+    sc.init(ops, f, face);
+    sc.row(ops, yi);
+    for (int xi = xa; xi <= xb; xi++)
+        if (sc.test(ops, xi)) hit_inline(ops, f, code, face, xi, yi, is);
+}
+
+// Queue the rows of one face as tasks of at most 8 columns; wide boxes only queue the segments that overlap the
+// conservative per-row extent of the triangle.
+template <class Ops>
+__device__ __noinline__ void push_row_tasks(TileSmem& sm, const Ops& ops, float* recs, const TriClass c, int code,
+                                            int face, int is) {
+    rec_store(recs, code & 511, c, code);
+    uint32_t* tq = reinterpret_cast<uint32_t*>(recs + NSLOT * REC_STRIDE);
+    const int bw = c.bb.x1 - c.bb.x0 + 1, bh = c.bb.y1 - c.bb.y0 + 1;
+    const bool wide = bw > 16;
+    float px[3], py[3];
+    if (wide) {
+        px[0] = ndc_to_pix(c.f.x0, is); px[1] = ndc_to_pix(c.f.x1, is); px[2] = ndc_to_pix(c.f.x2, is);
+        py[0] = ndc_to_pix(c.f.y0, is); py[1] = ndc_to_pix(c.f.y1, is); py[2] = ndc_to_pix(c.f.y2, is);
+    }
+    for (int ry = 0; ry < bh; ry++) {
+        int s0 = 0, s1 = (bw - 1) >> 3;
+        if (wide) {
+            int xa, xb;
+            row_extent(px, py, c.bb.y0 + ry, c.bb, &xa, &xb);
+            if (xa > xb) continue;
+            s0 = (xa - c.bb.x0) >> 3; s1 = (xb - c.bb.x0) >> 3;
+        }
+        const int n = s1 - s0 + 1;
+        const int base = atomicAdd(&sm.n_tq, n);
+        for (int k = 0; k < n; k++) {
+            if (base + k < TQ_CAP) {
+                tq[base + k] = (uint32_t)code | ((uint32_t)ry << 10) | ((uint32_t)(s0 + k) << 22);
+            } else {
+                const int xa = c.bb.x0 + (s0 + k) * 8;
+                scan_row_inline(ops, c.f, code, face, c.bb.y0 + ry, xa, min(xa + 7, c.bb.x1), is);
+            }
+        }
+    }
+}
+
 // Steps 2-4 of the header comment.
 template <class Ops>
 __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, const Cam& cam, int ty0, int tx0) {
@@ -389,32 +441,53 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         const bool any_act = A.act || B.act;
         const bool small = any_act && uw <= SB && uh <= SB;
         if (any_act && !small) {
-            // queue each active triangle on its own: medium (<= MB x MB) for 8-lane groups, large for whole warps
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const TriClass& c = k ? B : A;
-                if (!c.act) continue;
-                const int code = k ? codeB : codeA;
-                rec_store(recs, code & 511, c, code);
-                const bool medium = c.bb.x1 - c.bb.x0 < MB && c.bb.y1 - c.bb.y0 < MB;
-                if (medium) sm.mq[atomicAdd(&sm.n_mq, 1)] = (uint16_t)code;
-                else sm.lq[atomicAdd(&sm.n_lq, 1)] = (uint16_t)code;
-            }
+            // everything else becomes ROW TASKS: (face, row, 8-column segment), one lane each in the next phase
+            if (A.act) push_row_tasks(sm, ops, recs, A, codeA, faceA, is);
+            if (B.act) push_row_tasks(sm, ops, recs, B, codeB, faceB, is);
         }
-        typename Ops::QuadScan qs;
-        qs.init(ops, A.f, faceA, B.f, faceB);
-        const unsigned actbits = (A.act ? 1u : 0u) | (B.act ? 2u : 0u);
+        // Hoisted scan: the inside test `!((yp-yk)*dx < (xp-xk)*dy)` splits into a per-row and a per-column term per
+        // edge, so a candidate costs six compares.  Loops are fully unrolled over the SB x SB box; rows / columns
+        // beyond the warp-wide maximum are skipped with uniform branches; per-lane validity is one mask at the end.
         const int mh = (int)__reduce_max_sync(0xffffffffu, small ? (unsigned)uh : 0u);
         const int mw = (int)__reduce_max_sync(0xffffffffu, small ? (unsigned)uw : 0u);
         unsigned maskA = 0, maskB = 0;
-        for (int ry = 0; ry < mh; ry++) {
-            qs.row(ops, small ? min(u.y0 + ry, is - 1) : 0);
-            for (int rx = 0; rx < mw; rx++) {
-                unsigned r = qs.test(ops, small ? min(u.x0 + rx, is - 1) : 0) & actbits;
-                if (!(small && ry < uh && rx < uw)) r = 0;
-                maskA |= (r & 1u) << (ry * SB + rx);
-                maskB |= (r >> 1) << (ry * SB + rx);
+        if (mh > 0) {
+            typename Ops::Scan sa, sb;
+            sa.init(ops, A.f, faceA);
+            sb.init(ops, B.f, faceB);
+            float ca[SB][3], cb[SB][3];
+#pragma unroll
+            for (int rx = 0; rx < SB; rx++) {
+                if (rx < mw) {
+                    const float xp = ops.pc(small ? min(u.x0 + rx, is - 1) : 0);
+                    sa.col_terms(xp, ca[rx]);
+                    sb.col_terms(xp, cb[rx]);
+                }
             }
+#pragma unroll
+            for (int ry = 0; ry < SB; ry++) {
+                if (ry < mh) {
+                    const float yp = ops.pc(small ? min(u.y0 + ry, is - 1) : 0);
+                    sa.row_y(yp);
+                    sb.row_y(yp);
+#pragma unroll
+                    for (int rx = 0; rx < SB; rx++) {
+                        if (rx < mw) {
+                            maskA |= (sa.test_terms(ca[rx]) ? 1u : 0u) << (ry * SB + rx);
+                            maskB |= (sb.test_terms(cb[rx]) ? 1u : 0u) << (ry * SB + rx);
+                        }
+                    }
+                }
+            }
+            // per-lane validity: inside this quad's box, triangle active
+            unsigned vm = 0;
+            if (small) {
+                const unsigned rowbits = (1u << uw) - 1u;
+                vm = rowbits | (rowbits << SB) | (rowbits << (2 * SB)) | (rowbits << (3 * SB));
+                vm &= (uh >= SB) ? 0xffffffffu : ((1u << (uh * SB)) - 1u);
+            }
+            maskA &= A.act ? vm : 0u;
+            maskB &= B.act ? vm : 0u;
         }
         // queue the hits: one atomic per warp
         int total;
@@ -455,32 +528,33 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         if (B.dup) scan_degenerate(ops, reversed(B.f), B.bb, (tid * 2 + 1) | (1 << 9), Q, S, ty0, tx0);
     }
     __syncthreads();
-    // ---- medium boxes: 8-lane groups, one lane per row, uniform MB-column scan
-    const int nm = sm.n_mq;
-    for (int e0 = (tid >> 5) * 4; e0 < nm; e0 += (SPLAT_THREADS / 32) * 4) {
-        const int e = e0 + (lane >> 3), r = lane & 7;
-        const bool valid = e < nm;
-        const int code = valid ? sm.mq[e] : 0;
+    // ---- row tasks: one lane per (face, row, 8-column segment); uniform 8-column scan
+    const int nt = min(sm.n_tq, TQ_CAP);
+    const uint32_t* tq = reinterpret_cast<const uint32_t*>(recs + NSLOT * REC_STRIDE);
+    for (int i0 = (tid >> 5) * 32; i0 < nt; i0 += SPLAT_THREADS) {
+        const int i = i0 + lane;
+        const bool valid = i < nt;
+        const uint32_t task = valid ? tq[i] : 0u;
+        const int code = (int)(task & 1023u), ry = (int)((task >> 10) & 4095u), seg = (int)(task >> 22);
         Tri f;
         BBox bb;
         rec_load(recs, code & 511, f, bb);
         const int face = code_face(code, Q, S, ty0, tx0);
-        const int bw = bb.x1 - bb.x0 + 1, bh = bb.y1 - bb.y0 + 1;
-        const bool rowok = valid && r < bh;
         typename Ops::Scan sc;
         sc.init(ops, f, face);
-        const int yi = rowok ? bb.y0 + r : 0;
+        const int yi = valid ? bb.y0 + ry : 0, x0 = valid ? bb.x0 + seg * 8 : 0;
+        const int ncol = valid ? min(8, bb.x1 - x0 + 1) : 0;
         sc.row(ops, yi);
-        const int mw = (int)__reduce_max_sync(0xffffffffu, rowok ? (unsigned)bw : 0u);
         unsigned mask = 0;
-        for (int rx = 0; rx < mw; rx++) {
-            const bool in = rowok && rx < bw && sc.test(ops, rowok ? min(bb.x0 + rx, is - 1) : 0);
+#pragma unroll
+        for (int rx = 0; rx < 8; rx++) {
+            const bool in = rx < ncol && sc.test(ops, min(x0 + rx, is - 1));
             mask |= (in ? 1u : 0u) << rx;
         }
-        push_row_masks(sm, ops, mask, bb.x0, yi, code, face, is);
-        // one face-table request per face with a hit
-        const unsigned hitlanes = __ballot_sync(0xffffffffu, mask != 0);
-        const bool owner = r == 0 && ((hitlanes >> (lane & 24)) & 0xffu) != 0;
+        push_row_masks(sm, ops, mask, x0, yi, code, face, is);
+        // the first task of a face to score a hit requests the face's table entry
+        bool owner = false;
+        if (mask) owner = ((atomicOr(&sm.owned[(code & 511) >> 5], 1u << (code & 31)) >> (code & 31)) & 1u) == 0u;
         const unsigned owners = __ballot_sync(0xffffffffu, owner);
         if (owners) {
             int fbase = 0;
@@ -488,44 +562,6 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
             fbase = __shfl_sync(0xffffffffu, fbase, 0);
             if (owner) sm.fq[fbase + __popc(owners & ((1u << lane) - 1u))] = (uint16_t)code;
         }
-    }
-    // ---- large boxes: one warp per face, row by row over a conservative per-row extent, lanes across the row
-    const int nl = sm.n_lq;
-    for (int e = tid >> 5; e < nl; e += SPLAT_THREADS / 32) {
-        const int code = sm.lq[e];
-        Tri f;
-        BBox bb;
-        rec_load(recs, code & 511, f, bb);
-        const int face = code_face(code, Q, S, ty0, tx0);
-        typename Ops::Scan sc;
-        sc.init(ops, f, face);
-        const float px[3] = {ndc_to_pix(f.x0, is), ndc_to_pix(f.x1, is), ndc_to_pix(f.x2, is)};
-        const float py[3] = {ndc_to_pix(f.y0, is), ndc_to_pix(f.y1, is), ndc_to_pix(f.y2, is)};
-        bool any = false;
-        for (int yi = bb.y0; yi <= bb.y1; yi++) {
-            int xa, xb;
-            row_extent(px, py, yi, bb, &xa, &xb);
-            sc.row(ops, yi);
-            for (int x0 = xa; x0 <= xb; x0 += 32) {
-                const int xi = x0 + lane;
-                const bool in = xi <= xb && sc.test(ops, min(xi, is - 1));
-                const unsigned hits = __ballot_sync(0xffffffffu, in);
-                if (hits == 0) continue;
-                any = true;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sm.n_hq, __popc(hits));
-                base = __shfl_sync(0xffffffffu, base, 0) + __popc(hits & ((1u << lane) - 1u));
-                if (in) {
-                    if (base < HQ_CAP) {
-                        sm.hq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)xi;
-                        sm.hq_code[base] = (uint16_t)code;
-                    } else {
-                        hit_inline(ops, code_tri(sm.sv, code), code, face, xi, yi, is);
-                    }
-                }
-            }
-        }
-        if (lane == 0 && any) sm.fq[atomicAdd(&sm.n_fq, 1)] = (uint16_t)code;
     }
     __syncthreads();
     // ---- face table: one thread per face that owns a hit

@@ -117,6 +117,7 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * z-buffer).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,3].
  * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S]. */
 int g2s_chunk_views(int image_size);
+int g2s_chunk_views_bwd(int image_size);   /* recommended ws_views of g2s_render_fused_bwd (~1 GB of scratch) */
 int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
