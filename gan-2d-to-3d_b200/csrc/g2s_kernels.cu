@@ -44,12 +44,12 @@ Cam make_cam(const g2s_camera* c) {
 // ---- instrumentation: launch counter + optional CUDA-event timing of every kernel (bench.py / tests) ----
 enum KernelId { K_ZINIT, K_SPLAT, K_RESOLVE, K_RESOLVE_FUSED, K_GRID_FWD, K_GRID_BWD, K_NORMAL_FWD, K_NORMAL_BWD,
                 K_SAMPLE_FWD, K_SAMPLE_BWD, K_CLAMP_GRAD, K_RASTER_BWD, K_BWD_PIXEL, K_BWD_TEX, K_GRID3D, K_RESOLVE_RGB,
-                K_PROJECT, K_VERTEX_BWD, K_COUNT };
+                K_PROJECT, K_VERTEX_BWD, K_VIEW, K_LIGHT, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_zbuf_init", "k_splat", "k_resolve", "k_resolve_fused", "k_warp_grid_fwd",
                                            "k_warp_grid_bwd", "k_normal_fwd", "k_normal_bwd", "k_sample_fwd",
                                            "k_sample_bwd", "k_clamp_grad", "k_raster_bwd_px", "k_render_bwd_pixel",
                                            "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb", "k_project_verts",
-                                           "k_vertex_bwd"};
+                                           "k_vertex_bwd", "k_view_fwd/bwd", "k_light_fwd/bwd"};
 std::atomic<long> g_launches{0};
 struct ProfRec { int id; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
@@ -541,6 +541,80 @@ __global__ void k_clamp_grad(const float* __restrict__ recon_depth, const float*
     if (i >= n) return;
     const float rd = recon_depth[i];
     g_sub[i] = (rd > lo && rd < hi) ? 0.25f * grad[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// view [B, 3|5|6] -> R = Rz Ry Rx [B,3,3], t [B,3]  (utils.py:33-73) and raw light [B,4] -> (a, b, dx, dy, dz)
+// (model.py:347-353): one thread per view.  The reference spends ~40 tiny ATen launches on each.
+__global__ void k_view_fwd(const float* __restrict__ view, int vw, int B, float* __restrict__ R, float* __restrict__ t) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* v = view + (long)b * vw;
+    float sx, cx, sy, cy, sz, cz;
+    sincosf(v[0], &sx, &cx);
+    sincosf(v[1], &sy, &cy);
+    sincosf(v[2], &sz, &cz);
+    float* r = R + (long)b * 9;
+    r[0] = mul(cz, cy); r[1] = add(mul(cz, mul(sy, sx)), mul(-sz, cx)); r[2] = add(mul(cz, mul(sy, cx)), mul(-sz, -sx));
+    r[3] = mul(sz, cy); r[4] = add(mul(sz, mul(sy, sx)), mul(cz, cx));  r[5] = add(mul(sz, mul(sy, cx)), mul(cz, -sx));
+    r[6] = -sy;         r[7] = mul(cy, sx);                             r[8] = mul(cy, cx);
+    float* tt = t + (long)b * 3;
+    tt[0] = vw >= 5 ? v[3] : 0.f;
+    tt[1] = vw >= 5 ? v[4] : 0.f;
+    tt[2] = vw >= 6 ? v[5] : 0.f;
+}
+
+__global__ void k_view_bwd(const float* __restrict__ view, int vw, int B, const float* __restrict__ gR,
+                           const float* __restrict__ gt, float* __restrict__ gview) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* v = view + (long)b * vw;
+    float sx, cx, sy, cy, sz, cz;
+    sincosf(v[0], &sx, &cx);
+    sincosf(v[1], &sy, &cy);
+    sincosf(v[2], &sz, &cz);
+    float g[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) g[k] = gR ? gR[(long)b * 9 + k] : 0.f;
+    const float g_sx = g[1] * cz * sy + g[2] * sz + g[4] * sz * sy - g[5] * cz + g[7] * cy;
+    const float g_cx = -g[1] * sz + g[2] * cz * sy + g[4] * cz + g[5] * sz * sy + g[8] * cy;
+    const float g_sy = g[1] * cz * sx + g[2] * cz * cx + g[4] * sz * sx + g[5] * sz * cx - g[6];
+    const float g_cy = g[0] * cz + g[3] * sz + g[7] * sx + g[8] * cx;
+    const float g_sz = -g[1] * cx + g[2] * sx + g[3] * cy + g[4] * sy * sx + g[5] * sy * cx;
+    const float g_cz = g[0] * cy + g[1] * sy * sx + g[2] * sy * cx + g[4] * cx - g[5] * sx;
+    float* o = gview + (long)b * vw;
+    o[0] = g_sx * cx - g_cx * sx;
+    o[1] = g_sy * cy - g_cy * sy;
+    o[2] = g_sz * cz - g_cz * sz;
+    if (vw >= 5) { o[3] = gt ? gt[(long)b * 3] : 0.f; o[4] = gt ? gt[(long)b * 3 + 1] : 0.f; }
+    if (vw >= 6) o[5] = gt ? gt[(long)b * 3 + 2] : 0.f;
+}
+
+__global__ void k_light_fwd(const float* __restrict__ light, int B, float* __restrict__ light5) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* l = light + (long)b * 4;
+    float* o = light5 + (long)b * 5;
+    o[0] = add(dvd(l[0], 2.0f), 0.5f);
+    o[1] = add(dvd(l[1], 2.0f), 0.5f);
+    const float n = sqrt_(add(add(mul(l[2], l[2]), mul(l[3], l[3])), 1.0f));
+    o[2] = dvd(l[2], n); o[3] = dvd(l[3], n); o[4] = dvd(1.0f, n);
+}
+
+__global__ void k_light_bwd(const float* __restrict__ light, int B, const float* __restrict__ g5,
+                            float* __restrict__ glight) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* l = light + (long)b * 4;
+    const float* g = g5 + (long)b * 5;
+    const float n = sqrtf(l[2] * l[2] + l[3] * l[3] + 1.0f), inv = 1.0f / n;
+    const float d0 = l[2] * inv, d1 = l[3] * inv, d2 = inv;
+    const float dot = d0 * g[2] + d1 * g[3] + d2 * g[4];
+    float* o = glight + (long)b * 4;
+    o[0] = 0.5f * g[0];
+    o[1] = 0.5f * g[1];
+    o[2] = (g[2] - d0 * dot) * inv;
+    o[3] = (g[3] - d1 * dot) * inv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1285,6 +1359,41 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
                                                                         grad_normal_ws + (long)i0 * S * S * 3,
                                                                         grad_depth + (long)i0 * S * S, 1);
     }
+    return launch_status();
+}
+
+int g2s_view_fwd(const float* view, int view_width, int B, float* R, float* t, void* stream) {
+    if (!view || !R || !t) return G2S_ERR_NULL;
+    if (B <= 0) return G2S_ERR_SHAPE;
+    if (view_width != 3 && view_width != 5 && view_width != 6) return G2S_ERR_UNSUPPORTED;   // utils.py:70-71
+    { Launch l_(K_VIEW, (cudaStream_t)stream);
+      k_view_fwd<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view, view_width, B, R, t); }
+    return launch_status();
+}
+
+int g2s_view_bwd(const float* view, int view_width, int B, const float* grad_R, const float* grad_t, float* grad_view,
+                 void* stream) {
+    if (!view || !grad_view) return G2S_ERR_NULL;
+    if (B <= 0) return G2S_ERR_SHAPE;
+    if (view_width != 3 && view_width != 5 && view_width != 6) return G2S_ERR_UNSUPPORTED;
+    { Launch l_(K_VIEW, (cudaStream_t)stream);
+      k_view_bwd<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view, view_width, B, grad_R, grad_t, grad_view); }
+    return launch_status();
+}
+
+int g2s_light_fwd(const float* light, int B, float* light5, void* stream) {
+    if (!light || !light5) return G2S_ERR_NULL;
+    if (B <= 0) return G2S_ERR_SHAPE;
+    { Launch l_(K_LIGHT, (cudaStream_t)stream);
+      k_light_fwd<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(light, B, light5); }
+    return launch_status();
+}
+
+int g2s_light_bwd(const float* light, int B, const float* grad_light5, float* grad_light, void* stream) {
+    if (!light || !grad_light5 || !grad_light) return G2S_ERR_NULL;
+    if (B <= 0) return G2S_ERR_SHAPE;
+    { Launch l_(K_LIGHT, (cudaStream_t)stream);
+      k_light_bwd<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(light, B, grad_light5, grad_light); }
     return launch_status();
 }
 

@@ -185,6 +185,61 @@ class NormalFromDepthFn(torch.autograd.Function):
         return g_depth, None
 
 
+class ViewToRtFn(torch.autograd.Function):
+    """utils.py:52-73 get_transform_matrices (+ :33-49 get_rotation_matrix): view [B,3|5|6] -> (R [B,3,3], t [B,1,3])."""
+
+    @staticmethod
+    def forward(ctx, view):
+        _require_cuda(view)
+        lib = _lib.load()
+        v = _f32c(view)
+        B, w = v.shape
+        if w not in (3, 5, 6):
+            raise Exception("Unsupported view size. size(1) must be either 3, 5, 6.")   # utils.py:70-71
+        R = torch.empty(B, 3, 3, device=v.device, dtype=torch.float32)
+        t = torch.empty(B, 1, 3, device=v.device, dtype=torch.float32)
+        _lib.check(lib.g2s_view_fwd(_p(v), w, B, _p(R), _p(t), _stream()), "g2s_view_fwd")
+        ctx.save_for_backward(v)
+        return R, t
+
+    @staticmethod
+    def backward(ctx, gR, gt):
+        lib = _lib.load()
+        (v,) = ctx.saved_tensors
+        B, w = v.shape
+        gR = _f32c(gR) if gR is not None else None
+        gt = _f32c(gt) if gt is not None else None
+        gv = torch.empty_like(v)
+        _lib.check(lib.g2s_view_bwd(_p(v), w, B, _p(gR), _p(gt), _p(gv), _stream()), "g2s_view_bwd")
+        return gv
+
+
+class LightFn(torch.autograd.Function):
+    """model.py:347-353 get_lighting_directions, packed: raw light [B,4] -> [B,5] = (a, b, dx, dy, dz)."""
+
+    @staticmethod
+    def forward(ctx, light):
+        _require_cuda(light)
+        lib = _lib.load()
+        l = _f32c(light)
+        B = l.shape[0]
+        if l.shape[1] != 4:
+            raise RuntimeError("light must be [B,4]")
+        out = torch.empty(B, 5, device=l.device, dtype=torch.float32)
+        _lib.check(lib.g2s_light_fwd(_p(l), B, _p(out), _stream()), "g2s_light_fwd")
+        ctx.save_for_backward(l)
+        return out
+
+    @staticmethod
+    def backward(ctx, g5):
+        lib = _lib.load()
+        (l,) = ctx.saved_tensors
+        g = _f32c(g5)
+        gl = torch.empty_like(l)
+        _lib.check(lib.g2s_light_bwd(_p(l), l.shape[0], _p(g), _p(gl), _stream()), "g2s_light_bwd")
+        return gl
+
+
 _MODES = {"bilinear": 0, "nearest": 1}
 
 

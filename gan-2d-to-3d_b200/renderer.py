@@ -92,8 +92,12 @@ class Renderer:
             self._set_K(K, torch.inverse(K[0]).unsqueeze(0))
 
     def set_transform_matrices(self, view):
-        """renderer.py:61-62."""
-        self.rot_mat, self.trans_xyz = get_transform_matrices(view)
+        """renderer.py:61-62.  CUDA views go through one kernel (k_view_fwd/bwd); the torch mirror in utils.py is kept
+        for host-side (CPU) use of the class."""
+        if view.is_cuda:
+            self.rot_mat, self.trans_xyz = Fn.ViewToRtFn.apply(view)
+        else:
+            self.rot_mat, self.trans_xyz = get_transform_matrices(view)
 
     # -- point helpers kept for API compatibility (plain torch, not on the hot path) -------------------
     def rotate_pts(self, pts, rot_mat):
@@ -137,8 +141,7 @@ class Renderer:
         if N * P != B:
             raise RuntimeError("render_chain: view must have n_images * views_per_image rows")
         self.set_transform_matrices(view)
-        a, b, d = get_lighting_directions(light)
-        light5 = torch.cat([a, b, d], 1)
+        light5 = Fn.LightFn.apply(light)
         return Fn.RenderChainFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, self, P,
                                       self.align_corners)
 

@@ -145,6 +145,15 @@ int g2s_render_rgb_fwd(const g2s_camera *cam, const float *vertices3d, const flo
                        int n_views, int C, int tex_cube_size, const float *bg, int clamp, void *zbuf,
                        float *rgb, int32_t *face_idx, void *stream);
 
+/* ---- set_transform_matrices: utils.py:33-73 (view [B, 3|5|6] -> R = Rz Ry Rx [B,3,3], t [B,3]; other widths return
+ * G2S_ERR_UNSUPPORTED as utils.py:70-71 raises) and get_lighting_directions: model.py:347-353 (raw light [B,4] ->
+ * light5 [B,5] = ambient a, diffuse b, unit direction).  Backward: grad_R / grad_t may be NULL (zeros). */
+int g2s_view_fwd(const float *view, int view_width, int B, float *R, float *t, void *stream);
+int g2s_view_bwd(const float *view, int view_width, int B, const float *grad_R, const float *grad_t,
+                 float *grad_view, void *stream);
+int g2s_light_fwd(const float *light, int B, float *light5, void *stream);
+int g2s_light_bwd(const float *light, int B, const float *grad_light5, float *grad_light, void *stream);
+
 /* ---- 3-D grid helpers used by render_yaw / render_view / render_given_view ----------------------
  * depth_to_3d_grid (renderer.py:74-80) followed by an optional inverse warp by (R0,t0)
  * (renderer.py:164-167), then a forward rotation R1 (renderer.py:181-183) and optional (R2,t2)

@@ -352,6 +352,29 @@ def test_full_size_shard_invariance_and_determinism(S, P):
     assert torch.isfinite(whole[3]).all() and torch.isfinite(whole[4]).all()
 
 
+@pytest.mark.parametrize("w", [3, 5, 6])
+def test_view_and_light_kernels(w):
+    """set_transform_matrices (utils.py:33-73) and get_lighting_directions (model.py:347-353) as single kernels"""
+    import g2s_b200
+    torch.manual_seed(w)
+    view = (torch.rand(7, w) - 0.5) * 1.2
+    light = torch.rand(7, 4) * 2 - 1
+    v_o, l_o = view.clone().requires_grad_(True), light.clone().requires_grad_(True)
+    R_o, t_o = ro.get_transform_matrices(v_o)
+    l5_o = torch.cat(ro.get_lighting_directions(l_o), 1)
+    cR, ct, cl = torch.randn(7, 3, 3), torch.randn(7, 1, 3), torch.randn(7, 5)
+    ((R_o * cR).sum() + (t_o * ct).sum() + (l5_o * cl).sum()).backward()
+    v, l = view.cuda().requires_grad_(True), light.cuda().requires_grad_(True)
+    R, t = g2s_b200.functional.ViewToRtFn.apply(v)
+    l5 = g2s_b200.functional.LightFn.apply(l)
+    assert t.shape == (7, 1, 3)
+    assert torch.allclose(R.detach().cpu(), R_o.detach(), atol=3e-7) and torch.equal(t.detach().cpu(), t_o.detach())
+    assert torch.allclose(l5.detach().cpu(), l5_o.detach(), atol=3e-7)
+    ((R * cR.cuda()).sum() + (t * ct.cuda()).sum() + (l5 * cl.cuda()).sum()).backward()
+    assert rel_err(v.grad.cpu(), v_o.grad) < TOL
+    assert rel_err(l.grad.cpu(), l_o.grad) < TOL
+
+
 def test_shared_reciprocal_division_is_ieee_exact():
     """the kernels' division (one reciprocal shared by several quotients) must equal __fdiv_rn bit for bit"""
     import ctypes
