@@ -98,7 +98,7 @@ def cpu_reference_run(S, views, steps, warmup, threads):
     from g2s_b200 import synthetic
     from oracle import nr_port, renderer_oracle as ro
     torch.set_num_threads(threads)
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    nr_port.lib().nr_set_threads(threads)      # torchrun exports OMP_NUM_THREADS=1: pin the OpenMP team explicitly
     nr_port.MODE["raster"] = "brute"
     case = synthetic.make_case(S, views, seed=1234)
     orc = ro.OracleRenderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH)

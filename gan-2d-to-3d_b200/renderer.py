@@ -160,12 +160,12 @@ class Renderer:
         dev = depth.device
         R0 = t0 = R1 = R2 = t2 = None
         if v_before is not None:
-            R0, t0 = get_transform_matrices(v_before)
+            R0, t0 = self._views_to_Rt(v_before)
             R0, t0 = Fn._Rt(R0.detach(), t0.detach(), B)
         if rot1 is not None:
             R1 = Fn._f32c(rot1.detach().expand(B, 3, 3))
         if v_after is not None:
-            R2, t2 = get_transform_matrices(v_after)
+            R2, t2 = self._views_to_Rt(v_after)
             R2, t2 = Fn._Rt(R2.detach(), t2.detach(), B)
         crop = (ctypes.c_int * 4)(*[int(c) for c in crop_mesh]) if crop_mesh is not None else None
         out = torch.empty(B, H * W, 3, device=dev, dtype=torch.float32)
@@ -195,52 +195,59 @@ class Renderer:
                                           Fn._stream()), "g2s_render_rgb_fwd")
         return (out, fidx) if return_face_idx else out
 
+    @staticmethod
+    def _views_to_Rt(view):
+        if view.is_cuda:
+            return Fn.ViewToRtFn.apply(view)
+        return get_transform_matrices(view)
+
+    def _sweep(self, im, depth, angles, v_before=None, v_after=None, grid_sample=False, crop_mesh=None):
+        """All `t` rotations of a sweep in ONE batch of b*t views (the reference loops over them, rebuilding faces and
+        textures per iteration: renderer.py:169-197).  angles: [t,3] rotation vectors.  -> [b, t, c, h, w]."""
+        b, c, h, w = im.shape
+        T = angles.shape[0]
+        dev = im.device
+        angles = angles.to(device=dev, dtype=torch.float32)
+        rep = (lambda x: x.expand(T, *x.shape[1:])) if b == 1 else (lambda x: x.repeat_interleave(T, 0))
+        depth_bt, im_bt = rep(depth), rep(im)
+        if grid_sample:
+            view = torch.cat([angles, torch.zeros(T, 3, device=dev)], 1).repeat(b, 1)          # [b*T, 6], (b, t) order
+            if v_before is not None:
+                view = view - rep(v_before.expand(b, v_before.shape[1]))
+            warped = self._view_sample(im_bt, depth_bt, view)[0]
+        else:
+            R1, _ = self._views_to_Rt(angles)
+            R1 = R1.detach().repeat(b, 1, 1)
+            vb = rep(v_before.expand(b, v_before.shape[1])) if v_before is not None else None
+            va = None
+            if v_after is not None:
+                if len(v_after.shape) == 3:                                                   # [t, b, 6] (renderer.py:186-187)
+                    va = v_after.expand(T, b, v_after.shape[2]).transpose(0, 1).reshape(b * T, -1)
+                else:
+                    va = rep(v_after.expand(b, v_after.shape[1]))
+            verts = self._grid3d(depth_bt, crop_mesh, vb, R1, va)
+            warped = self._render_rgb(verts, im_bt)
+        return warped.reshape(b, T, c, h, w)
+
     def render_yaw(self, im, depth, v_before=None, v_after=None, rotations=None, maxr=90, nsample=9,
                    grid_sample=False, crop_mesh=None):
         """renderer.py:141-198 -> [b, t, c, h, w]."""
-        b, c, h, w = im.shape
         if rotations is None:
             rotations = torch.linspace(-math.pi / 180 * maxr, math.pi / 180 * maxr, nsample)
-        im_trans = []
-        for i, ri in enumerate(rotations):
-            if grid_sample:
-                view = torch.tensor([0, float(ri), 0, 0, 0, 0], device=im.device, dtype=torch.float32).view(1, 6)
-                if v_before is not None:
-                    view = view - v_before
-                warped = self._view_sample(im, depth, view.expand(b, 6) if view.shape[0] == 1 else view)[0]
-            else:
-                rot_mat_i, _ = get_transform_matrices(
-                    torch.tensor([0, float(ri), 0], device=im.device, dtype=torch.float32).view(1, 3))
-                v_after_i = None
-                if v_after is not None:
-                    v_after_i = v_after[i] if len(v_after.shape) == 3 else v_after
-                verts = self._grid3d(depth, crop_mesh, v_before, rot_mat_i, v_after_i)
-                warped = self._render_rgb(verts, im)
-            im_trans += [warped]
-        return torch.stack(im_trans, 1)
+        rot = torch.as_tensor(rotations, dtype=torch.float32).reshape(-1)
+        angles = torch.zeros(rot.shape[0], 3)
+        angles[:, 1] = rot.cpu()
+        return self._sweep(im, depth, angles, v_before, v_after, grid_sample, crop_mesh)
 
     def render_view(self, im, depth, v_before=None, rotations=None, maxr=[20, 90], nsample=[5, 9],
                     grid_sample=False):
         """renderer.py:200-250: yaw sweep, then pitch sweep -> [b, t, c, h, w]."""
-        b, c, h, w = im.shape
         rotations_p = torch.linspace(-math.pi / 180 * maxr[0], math.pi / 180 * maxr[0], nsample[0])
         rotations_y = torch.linspace(-math.pi / 180 * maxr[1], math.pi / 180 * maxr[1], nsample[1])
-        im_trans = []
-        for axis, angles in ((1, rotations_y), (0, rotations_p)):
-            for a in angles:
-                r3 = [0., 0., 0.]
-                r3[axis] = float(a)
-                if grid_sample:
-                    view = torch.tensor(r3 + [0., 0., 0.], device=im.device, dtype=torch.float32).view(1, 6)
-                    if v_before is not None:
-                        view = view - v_before
-                    warped = self._view_sample(im, depth, view.expand(b, 6) if view.shape[0] == 1 else view)[0]
-                else:
-                    rot_mat_i, _ = get_transform_matrices(
-                        torch.tensor(r3, device=im.device, dtype=torch.float32).view(1, 3))
-                    warped = self._render_rgb(self._grid3d(depth, None, v_before, rot_mat_i, None), im)
-                im_trans += [warped]
-        return torch.stack(im_trans, 1)
+        angles = torch.zeros(nsample[1] + nsample[0], 3)
+        angles[:nsample[1], 1] = rotations_y
+        angles[nsample[1]:, 0] = rotations_p
+        return self._sweep(im, depth, angles, v_before, None, grid_sample, None)
 
     def render_given_view(self, im, depth, view, mask=None, grid_sample=True):
         """renderer.py:252-277."""

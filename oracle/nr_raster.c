@@ -390,4 +390,19 @@ EXPORT void nr_backward_textures(const int32_t *face_index_map, const float *sam
     }
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* bench.py pins the thread count explicitly (torchrun exports OMP_NUM_THREADS=1) */
+EXPORT int nr_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 EXPORT int nr_oracle_version(void) { return 1; }

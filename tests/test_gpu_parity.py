@@ -48,6 +48,31 @@ def test_warp_canon_depth_forward_bit_exact(S, P, rot, seed):
     assert torch.equal(rd2, rd) and torch.equal(fidx2, fidx)
 
 
+def test_warp_canon_depth_256_bit_exact_and_backward():
+    """BASELINE.json face config size (256^2, 512^2 sub-pixels): one view against the oracle, forward bit-exact,
+    backward to 1e-5"""
+    S, P = 256, 1
+    case = _case(S, P, 256, 60.0)
+    orc, ren = oracle_renderer(S), _cuda_renderer(S)
+    d_o = case["depth"].clone().requires_grad_(True)
+    R_o = ro.get_transform_matrices(case["view"])[0].clone().requires_grad_(True)
+    t_o = case["view"][:, 3:].reshape(P, 1, 3).clone().requires_grad_(True)
+    orc.rot_mat, orc.trans_xyz = R_o, t_o
+    rd_o = orc.warp_canon_depth(d_o.expand(P, S, S))
+    f_o = nr_port.LAST["face_index_map"].flip(1)
+    cot = torch.randn(P, S, S)
+    (rd_o * cot).sum().backward()
+    d = case["depth"].cuda().requires_grad_(True)
+    ren.rot_mat = R_o.detach().cuda().requires_grad_(True)
+    ren.trans_xyz = t_o.detach().cuda().requires_grad_(True)
+    rd, fidx = ren.warp_canon_depth(d.expand(P, S, S), return_face_idx=True)
+    assert int((fidx.cpu() != f_o).sum()) == 0
+    assert torch.equal(rd.detach().cpu(), rd_o.detach())
+    (rd * cot.cuda()).sum().backward()
+    assert rel_err(d.grad.cpu(), d_o.grad) < TOL
+    assert rel_err(ren.rot_mat.grad.cpu(), R_o.grad) < 5e-5
+
+
 @pytest.mark.parametrize("name", ["s16_p3", "s32_p2", "s32_p2_wide"])
 def test_golden_forward(name):
     g = golden(name)
