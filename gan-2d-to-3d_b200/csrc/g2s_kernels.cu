@@ -127,8 +127,18 @@ k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, c
         int tiles_x, int view0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
-    const int tid = threadIdx.x, bl = blockIdx.y, b = view0 + bl, S = cam.S, is = 2 * S;
-    const int ty0 = (blockIdx.x / tiles_x) * TILE_H, tx0 = (blockIdx.x % tiles_x) * TILE;
+    // grid = (views, tiles): consecutive CTAs are the same tile of consecutive views.  Tile order: the left / right
+    // border columns first -- under yaw they hold the long depth-step wall faces (model.py:341-344) and take several
+    // times longer than interior tiles, so starting them first keeps them out of the launch tail.
+    const int tid = threadIdx.x, bl = blockIdx.x, b = view0 + bl, S = cam.S, is = 2 * S;
+    int tile_x, tile_y;
+    {
+        const int k = blockIdx.y, tiles_yy = gridDim.y / tiles_x;
+        if (tiles_x < 3) { tile_y = k / tiles_x; tile_x = k % tiles_x; }
+        else if (k < 2 * tiles_yy) { tile_y = k >> 1; tile_x = (k & 1) ? tiles_x - 1 : 0; }
+        else { const int r = k - 2 * tiles_yy; tile_y = r / (tiles_x - 2); tile_x = 1 + r % (tiles_x - 2); }
+    }
+    const int ty0 = tile_y * TILE_H, tx0 = tile_x * TILE;
     if (!FROM_VERTS) {
         if (tid < 9) sm.sRt[tid] = R[b * 9 + tid];
         else if (tid < 12) sm.sRt[tid] = t[b * 3 + tid - 9];
@@ -1103,16 +1113,14 @@ inline dim3 pix_grid2(int S, int views) { return dim3((S + PBX - 1) / PBX, (S + 
 // views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
 // scratch 16 S^2 B/view) stays resident in the 126 MB L2 between the kernel that writes it and the one that reads it
 inline int chunk_views_for(int S, int cap) {
+    // 32 MB of z-buffer per chunk, but never fewer than 64 views: below that the launches are too short and the
+    // tail of the rasteriser (a few heavy wall tiles) costs more than the L2 misses of a larger z-buffer (measured
+    // at 128^2 and 256^2, profiles/)
     long v = (32L << 20) / (32L * S * S);
-    if (v < 1) v = 1;
+    if (v < 64) v = 64;
     if (v > cap) v = cap;
     return (int)v;
 }
-
-// raster backward of one chunk of views: raster_ws = [nv, 7, S, S] floats = g_sub | proj (3) | vgrad (3)
-inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
-                              const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth, long gdstride,
-                              float* grad_R, float* grad_t, cudaStream_t st);
 
 inline dim3 pix_grid(long npix, int batch) { return dim3((unsigned)((npix + PIX_THREADS - 1) / PIX_THREADS), batch); }
 
@@ -1175,7 +1183,7 @@ int g2s_warp_depth_fwd(const g2s_camera* cam, const float* depth, long depth_vie
     const Cam c = make_cam(cam);
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(tiles * tiles_y, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, depth_view_stride, 1, R, t,
+    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(n_views, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, depth_view_stride, 1, R, t,
                                                                           nullptr, (unsigned long long*)zbuf, tiles, 0); }
     FusedArgs fa = {};
     { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid2(S, n_views), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, recon_depth,
@@ -1305,7 +1313,7 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         { Launch l_(K_SPLAT, st);
-          k_splat<false><<<dim3(tiles * tiles_y, nv), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
+          k_splat<false><<<dim3(nv, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
                                                                            (unsigned long long*)zbuf, tiles, (int)v0); }
         FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0};
         { Launch l_(K_RESOLVE_FUSED, st);
@@ -1423,7 +1431,7 @@ int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const flo
     const Cam c = make_cam(cam);
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(tiles * tiles_y, n_views), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
+    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(n_views, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
                                                                          (unsigned long long*)zbuf, tiles, 0); }
     Bg b4 = {{0.f, 0.f, 0.f, 0.f}};
     for (int i = 0; i < C; i++) b4.c[i] = bg[i];

@@ -22,13 +22,16 @@
 
 namespace g2s {
 
-constexpr int HQ_CAP = 8 * SPLAT_THREADS;                 // hit-queue entries per drain
+constexpr int HQ_CAP = 16 * SPLAT_THREADS;                 // hit-queue entries per drain
 constexpr int NSLOT = 2 * TILE * TILE_H;       // (quad, triangle) slots of the face table
+constexpr int TQ_CAP = 4096;                  // queued row tasks per tile
 constexpr int FT_STRIDE = 16;                // fi[9], z[3], rcp_seed(z)[3], pad
 
 struct TileSmem {
     float ftab[NSLOT * FT_STRIDE];
     float sv[TV * TVH * 3];
+    float recs[NSLOT * 9];       // queued-face records (REC_STRIDE floats each)
+    uint32_t tq[TQ_CAP];         // row tasks
     uint32_t hq_pix[HQ_CAP];
     uint16_t hq_code[HQ_CAP];
     uint16_t fq[NSLOT];
@@ -347,7 +350,6 @@ __device__ __forceinline__ void rec_load(const float* recs, int slot, Tri& f, BB
     bb.y0 = (int)(by & 0xffffu); bb.y1 = (int)(by >> 16);
 }
 
-constexpr int TQ_CAP = (NSLOT * FT_STRIDE - NSLOT * REC_STRIDE);   // row tasks that fit behind the records in the table region
 
 // hits of one warp step -> hit queue (one atomic per warp); every lane calls with its mask (bit k = hit at column
 // x0 + k of row yi) and code
@@ -391,7 +393,7 @@ template <class Ops>
 __device__ __noinline__ void push_row_tasks(TileSmem& sm, const Ops& ops, float* recs, const TriClass c, int code,
                                             int face, int is) {
     rec_store(recs, code & 511, c, code);
-    uint32_t* tq = reinterpret_cast<uint32_t*>(recs + NSLOT * REC_STRIDE);
+    uint32_t* tq = sm.tq;
     const int bw = c.bb.x1 - c.bb.x0 + 1, bh = c.bb.y1 - c.bb.y0 + 1;
     const bool wide = bw > 16;
     float px[3], py[3];
@@ -426,7 +428,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     const int tid = threadIdx.x, S = cam.S, is = 2 * S, Q = (S - 1) * (S - 1), lane = tid & 31;
     const int qy = tid / TILE, qx = tid % TILE;
     const bool quad_ok = ty0 + qy < S - 1 && tx0 + qx < S - 1;
-    float* recs = sm.ftab;   // alias: queued-face records live where the face table will be built later
+    float* recs = sm.recs;
     // ---- quads whose two triangles fit one SB x SB box: scanned by the owning thread with uniform control flow
     {
         TriClass A = classify(sm.sv, qy, qx, 0, is, quad_ok), B = classify(sm.sv, qy, qx, 1, is, quad_ok);
@@ -527,57 +529,69 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         if (A.dup) scan_degenerate(ops, reversed(A.f), A.bb, (tid * 2) | (1 << 9), Q, S, ty0, tx0);
         if (B.dup) scan_degenerate(ops, reversed(B.f), B.bb, (tid * 2 + 1) | (1 << 9), Q, S, ty0, tx0);
     }
-    __syncthreads();
-    // ---- row tasks: one lane per (face, row, 8-column segment); uniform 8-column scan
-    const int nt = min(sm.n_tq, TQ_CAP);
-    const uint32_t* tq = reinterpret_cast<const uint32_t*>(recs + NSLOT * REC_STRIDE);
-    for (int i0 = (tid >> 5) * 32; i0 < nt; i0 += SPLAT_THREADS) {
-        const int i = i0 + lane;
-        const bool valid = i < nt;
-        const uint32_t task = valid ? tq[i] : 0u;
-        const int code = (int)(task & 1023u), ry = (int)((task >> 10) & 4095u), seg = (int)(task >> 22);
-        Tri f;
-        BBox bb;
-        rec_load(recs, code & 511, f, bb);
-        const int face = code_face(code, Q, S, ty0, tx0);
-        typename Ops::Scan sc;
-        sc.init(ops, f, face);
-        const int yi = valid ? bb.y0 + ry : 0, x0 = valid ? bb.x0 + seg * 8 : 0;
-        const int ncol = valid ? min(8, bb.x1 - x0 + 1) : 0;
-        sc.row(ops, yi);
-        unsigned mask = 0;
+    // ---- rounds: scan as many queued row tasks as are guaranteed to fit the hit queue (8 hits per task at most),
+    // build the table entries of the faces that scored for the first time, drain.  One round for ordinary tiles;
+    // tiles full of long wall faces take several.
+    const uint32_t* tq = sm.tq;
+    int t0 = 0, nf_done = 0;
+    while (true) {
+        __syncthreads();
+        const int nt = min(sm.n_tq, TQ_CAP);
+        const int t1 = min(nt, t0 + (HQ_CAP - min(sm.n_hq, HQ_CAP)) / 8);
+        // row tasks: one lane per (face, row, 8-column segment); uniform 8-column scan
+        for (int i0 = t0 + (tid >> 5) * 32; i0 < t1; i0 += SPLAT_THREADS) {
+            const int i = i0 + lane;
+            const bool valid = i < t1;
+            const uint32_t task = valid ? tq[i] : 0u;
+            const int code = (int)(task & 1023u), ry = (int)((task >> 10) & 4095u), seg = (int)(task >> 22);
+            Tri f;
+            BBox bb;
+            rec_load(recs, code & 511, f, bb);
+            const int face = code_face(code, Q, S, ty0, tx0);
+            typename Ops::Scan sc;
+            sc.init(ops, f, face);
+            const int yi = valid ? bb.y0 + ry : 0, x0 = valid ? bb.x0 + seg * 8 : 0;
+            const int ncol = valid ? min(8, bb.x1 - x0 + 1) : 0;
+            sc.row(ops, yi);
+            unsigned mask = 0;
 #pragma unroll
-        for (int rx = 0; rx < 8; rx++) {
-            const bool in = rx < ncol && sc.test(ops, min(x0 + rx, is - 1));
-            mask |= (in ? 1u : 0u) << rx;
+            for (int rx = 0; rx < 8; rx++) {
+                const bool in = rx < ncol && sc.test(ops, min(x0 + rx, is - 1));
+                mask |= (in ? 1u : 0u) << rx;
+            }
+            push_row_masks(sm, ops, mask, x0, yi, code, face, is);
+            // the first task of a face to score a hit requests the face's table entry
+            bool owner = false;
+            if (mask) owner = ((atomicOr(&sm.owned[(code & 511) >> 5], 1u << (code & 31)) >> (code & 31)) & 1u) == 0u;
+            const unsigned owners = __ballot_sync(0xffffffffu, owner);
+            if (owners) {
+                int fbase = 0;
+                if (lane == 0) fbase = atomicAdd(&sm.n_fq, __popc(owners));
+                fbase = __shfl_sync(0xffffffffu, fbase, 0);
+                if (owner) sm.fq[fbase + __popc(owners & ((1u << lane) - 1u))] = (uint16_t)code;
+            }
         }
-        push_row_masks(sm, ops, mask, x0, yi, code, face, is);
-        // the first task of a face to score a hit requests the face's table entry
-        bool owner = false;
-        if (mask) owner = ((atomicOr(&sm.owned[(code & 511) >> 5], 1u << (code & 31)) >> (code & 31)) & 1u) == 0u;
-        const unsigned owners = __ballot_sync(0xffffffffu, owner);
-        if (owners) {
-            int fbase = 0;
-            if (lane == 0) fbase = atomicAdd(&sm.n_fq, __popc(owners));
-            fbase = __shfl_sync(0xffffffffu, fbase, 0);
-            if (owner) sm.fq[fbase + __popc(owners & ((1u << lane) - 1u))] = (uint16_t)code;
+        __syncthreads();
+        // face table: one thread per face that owns a hit for the first time
+        const int nf = sm.n_fq;
+        for (int i = nf_done + tid; i < nf; i += SPLAT_THREADS) {
+            const int code = sm.fq[i];
+            face_record(code_tri(sm.sv, code), is, &sm.ftab[(code & 511) * FT_STRIDE]);
         }
-    }
-    __syncthreads();
-    // ---- face table: one thread per face that owns a hit
-    const int nf = sm.n_fq;
-    for (int i = tid; i < nf; i += SPLAT_THREADS) {
-        const int code = sm.fq[i];
-        face_record(code_tri(sm.sv, code), is, &sm.ftab[(code & 511) * FT_STRIDE]);
-    }
-    __syncthreads();
-    // ---- drain the hit queue: one thread per hit
-    const int nh = min(sm.n_hq, HQ_CAP);
-    for (int i = tid; i < nh; i += SPLAT_THREADS) {
-        const int code = sm.hq_code[i];
-        const uint32_t pix = sm.hq_pix[i];
-        ops.hit(&sm.ftab[(code & 511) * FT_STRIDE], code, code_face(code, Q, S, ty0, tx0), (int)(pix & 0xffffu),
-                (int)(pix >> 16));
+        nf_done = nf;
+        __syncthreads();
+        // drain the hit queue: one thread per hit
+        const int nh = min(sm.n_hq, HQ_CAP);
+        for (int i = tid; i < nh; i += SPLAT_THREADS) {
+            const int code = sm.hq_code[i];
+            const uint32_t pix = sm.hq_pix[i];
+            ops.hit(&sm.ftab[(code & 511) * FT_STRIDE], code, code_face(code, Q, S, ty0, tx0), (int)(pix & 0xffffu),
+                    (int)(pix >> 16));
+        }
+        t0 = t1;
+        if (t0 >= nt) break;
+        __syncthreads();
+        if (tid == 0) sm.n_hq = 0;
     }
 }
 
