@@ -287,10 +287,18 @@ def run_ours(args):
             k["frac"] = k["achieved_gbs"] / peak
     kernels.sort(key=lambda k: -k["ms_per_step"])
     dom = kernels[0] if kernels else None
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same launch shape only)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)["kernels"].get(dom["name"])
+        if tj and S == 128 and dom["launches"] and B * args.steps // dom["launches"] == tj["views_per_launch"]:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     step_achieved = value / world * per_render / 1e9
     roofline = {"bound": "hbm", "kernel": dom["name"] if dom else None,
                 "achieved": dom.get("achieved_gbs") if dom else None, "peak": peak, "unit": "GB/s",
-                "frac": dom.get("frac") if dom else None, "traffic": None, "peak_source": peak_src,
+                "frac": dom.get("frac") if dom else None, "traffic": traffic, "peak_source": peak_src,
                 "kernel_share_of_step": dom["share_of_step"] if dom else None,
                 "step": {"alg_bytes_per_render": per_render, "achieved": step_achieved, "frac": step_achieved / peak,
                          "note": "whole fwd+bwd step, SURVEY.md 8(d): renders/s/GPU x (64 S^2 + 48 S^2/P) bytes"},
