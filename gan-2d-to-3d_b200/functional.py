@@ -306,7 +306,7 @@ class RenderChainFn(torch.autograd.Function):
         dev = d.device
         ws_views = min(B, lib.g2s_chunk_views(S))
         zbuf = renderer._zbuf.get(ws_views, S, cam.far_z, dev)
-        normal = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
+        normal = torch.empty(N, S, S, 8, device=dev, dtype=torch.float32)    # packed texels: normal xyz, albedo rgb, pad
         recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
         recon_depth = torch.empty(B, S, S, device=dev, dtype=torch.float32)
         fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)

@@ -114,7 +114,8 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * light [n_views,5] = (ambient a, diffuse b, direction dx,dy,dz) as get_lighting_directions returns.
  * The views are processed in chunks of `ws_views` views so that the per-chunk scratch stays L2-resident between the
  * kernel that writes it and the kernel that reads it; g2s_chunk_views(S) returns the recommended chunk (32 MB of
- * z-buffer).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,3].
+ * z-buffer).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,8] (packed texels: normal xyz,
+ * albedo rgb, 2 pad; kept for the backward).
  * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S]. */
 int g2s_chunk_views(int image_size);
 int g2s_chunk_views_bwd(int image_size);   /* recommended ws_views of g2s_render_fused_bwd (~1 GB of scratch) */
@@ -125,7 +126,8 @@ int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float 
 
 /* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
  * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,7,S,S] (as above),
- * grad_tex_ws [ws_views,3,S,S] (chunked like the forward), grad_normal_ws [n_images,S,S,3].
+ * grad_tex_ws [ws_views,3,S,S] (chunked like the forward), grad_normal_ws [n_images,S,S,8] (packed texels: normal xyz,
+ * albedo rgb, 2 pad; kept for the backward).
  * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
  * grad_t [n_views,3], grad_light [n_views,5]. */
 int g2s_render_fused_bwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
