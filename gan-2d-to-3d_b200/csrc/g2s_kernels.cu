@@ -714,8 +714,23 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         }
         // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
         const float z[3] = {rec[9], rec[10], rec[11]};
-        const float t0 = -(__fdiv_rn(rec[0], z[0]) + __fdiv_rn(rec[3], z[1]) + __fdiv_rn(rec[6], z[2]));
-        const float t1 = -(__fdiv_rn(rec[1], z[0]) + __fdiv_rn(rec[4], z[1]) + __fdiv_rn(rec[7], z[2]));
+        // six exact quotients fi[m][l] / z_m from the tabulated reciprocal seeds, one merged range check
+        float qd[6];
+        unsigned bad = 0;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            qd[m] = div_core(rec[3 * m], z[m], rec[12 + m]);
+            qd[3 + m] = div_core(rec[3 * m + 1], z[m], rec[12 + m]);
+            bad = max(bad, range_key(z[m]));
+            bad = max(bad, rec[3 * m] == 0.0f ? 0u : range_key(rec[3 * m]));
+            bad = max(bad, rec[3 * m + 1] == 0.0f ? 0u : range_key(rec[3 * m + 1]));
+        }
+        if (bad >= RANGE_SPAN) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) { qd[m] = __fdiv_rn(rec[3 * m], z[m]); qd[3 + m] = __fdiv_rn(rec[3 * m + 1], z[m]); }
+        }
+        const float t0 = -(qd[0] + qd[1] + qd[2]);
+        const float t1 = -(qd[3] + qd[4] + qd[5]);
 #pragma unroll
         for (int m = 0; m < 3; m++) {
             if (A[m] == 0.f) continue;

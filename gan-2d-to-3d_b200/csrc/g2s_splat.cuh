@@ -99,16 +99,46 @@ struct PixCenter {
     }
 };
 
+__device__ __forceinline__ unsigned range_key(float x) { return (__float_as_uint(x) & 0x7fffffffu) - 0x2B800000u; }
+constexpr unsigned RANGE_SPAN = 0x53800000u - 0x2B800000u;   // 2^-40 <= |x| < 2^40
+
+// q = RN(a / b) from a refined reciprocal seed y of b (two residual corrections; see g2s_math.cuh dvd_y); the caller
+// checks the operand ranges
+__device__ __forceinline__ float div_core(float a, float b, float y) {
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-b, q, a);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
+
+// [nr] kernel 1 (tri_face_inv) with the nine divisions sharing one reciprocal and ONE merged operand-range check;
+// out-of-range operands re-run on the IEEE path.  Same bits as tri_face_inv.
 __device__ __forceinline__ void face_record(const Tri& f, int is, float* rec) {
-    float fi[9];
-    tri_face_inv(f, is, fi);
+    const float p00 = ndc_to_pix(f.x0, is), p01 = ndc_to_pix(f.y0, is);
+    const float p10 = ndc_to_pix(f.x1, is), p11 = ndc_to_pix(f.y1, is);
+    const float p20 = ndc_to_pix(f.x2, is), p21 = ndc_to_pix(f.y2, is);
+    float a[9];
+    a[0] = sub(p11, p21); a[1] = sub(p20, p10); a[2] = sub(mul(p10, p21), mul(p20, p11));
+    a[3] = sub(p21, p01); a[4] = sub(p00, p20); a[5] = sub(mul(p20, p01), mul(p00, p21));
+    a[6] = sub(p01, p11); a[7] = sub(p10, p00); a[8] = sub(mul(p00, p11), mul(p10, p01));
+    const float den = add(add(mul(p20, sub(p01, p11)), mul(p00, sub(p11, p21))), mul(p10, sub(p21, p01)));
+    const float y = rcp_seed(den);
+    unsigned bad = range_key(den);
 #pragma unroll
-    for (int k = 0; k < 9; k++) rec[k] = fi[k];
+    for (int k = 0; k < 9; k++) {
+        rec[k] = div_core(a[k], den, y);
+        bad = max(bad, a[k] == 0.0f ? 0u : range_key(a[k]));
+    }
+    if (bad >= RANGE_SPAN) {
+        float fi[9];
+        tri_face_inv(f, is, fi);
+#pragma unroll
+        for (int k = 0; k < 9; k++) rec[k] = fi[k];
+    }
     rec[9] = f.z0; rec[10] = f.z1; rec[11] = f.z2;
     rec[12] = rcp_seed(f.z0); rec[13] = rcp_seed(f.z1); rec[14] = rcp_seed(f.z2);
 }
-
-__device__ __forceinline__ unsigned range_key(float x) { return (__float_as_uint(x) & 0x7fffffffu) - 0x2B800000u; }
 
 // Per-hit evaluation from a face record: [nr] kernel 2 after the inside test (clamped, renormalised weights and
 // perspective z).  Fast path: the seven divisions run as residual-corrected products with shared / tabulated
@@ -154,7 +184,7 @@ __device__ __forceinline__ bool record_weights_depth(const float* rec, int xi, i
         r = __fmaf_rn(-s, q, 1.0f);
         zp = __fmaf_rn(r, y, q);
     }
-    if (bad >= 0x53800000u - 0x2B800000u) {   // some operand outside [2^-40, 2^40): IEEE path
+    if (bad >= RANGE_SPAN) {   // some operand outside [2^-40, 2^40): IEEE path
         Tri f;
         f.z0 = rec[9]; f.z1 = rec[10]; f.z2 = rec[11];
         float fi[9];
