@@ -179,6 +179,8 @@ struct FusedArgs {
     int vpi;
     int align;
     int view0;            // first view of this launch (chunked launches)
+    const float* mask_in; // optional [n_images,S,S] canonical mask (NULL = all ones)
+    float* mask_out;      // optional [n_views,S,S]: grid_sample(mask, grid, mode='nearest') (renderer.py:263)
 };
 
 constexpr int PBX = 64, PBY = 4;   // pixel-kernel block: 64 columns x 4 rows
@@ -291,6 +293,13 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
         for (int c = 0; c < 3; c++) {
             const float o = tp.w[0] * tex[0][c] + tp.w[1] * tex[1][c] + tp.w[2] * tex[2][c] + tp.w[3] * tex[3][c];
             __stcs(&fa.recon_im[((long)b * 3 + c) * S * S + pix], fminf(fmaxf(o, -1.f), 1.f));
+        }
+        if (fa.mask_out) {   // nearest-neighbour warp of the canonical mask with the same grid (sample_pseudo_imgs)
+            const float ix = nearbyintf(grid_unnormalize(g[0], S, fa.align)), iy = nearbyintf(grid_unnormalize(g[1], S, fa.align));
+            const bool ok = ix >= 0.f && ix < (float)S && iy >= 0.f && iy < (float)S;
+            float m = 0.f;
+            if (ok) m = fa.mask_in ? __ldg(&fa.mask_in[(long)img * S * S + (int)iy * S + (int)ix]) : 1.0f;
+            __stcs(&fa.mask_out[(long)b * S * S + pix], m);
         }
     }
 }
@@ -1323,7 +1332,7 @@ int g2s_chunk_views(int image_size) {
 int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
                          int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
-                         void* stream) {
+                         const float* mask_in, float* mask_out, void* stream) {
     if (!cam || !depth || !albedo || !R || !t || !light || !zbuf || !normal_ws || !recon_im || !recon_depth)
         return G2S_ERR_NULL;
     const long n_views = (long)n_images * views_per_image;
@@ -1346,7 +1355,7 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
         { Launch l_(K_SPLAT, st);
           k_splat<false><<<dim3(nv, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
                                                                            (unsigned long long*)zbuf, tiles, (int)v0); }
-        FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0};
+        FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0, mask_in, mask_out};
         { Launch l_(K_RESOLVE_FUSED, st);
           k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, recon_depth, face_idx, fa); }
     }
@@ -1380,7 +1389,7 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * nv * 3 * img_f, st);
-        FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0};
+        FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
         { Launch l_(K_BWD_PIXEL, st);
           k_render_bwd_pixel<<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
                                                                          grad_sub_ws, grad_tex_ws, grad_R, grad_t); }

@@ -290,8 +290,9 @@ class RenderChainFn(torch.autograd.Function):
     Returns (recon_im [B,3,S,S], recon_depth [B,S,S], face_idx int32 [B,2S,2S])."""
 
     @staticmethod
-    def forward(ctx, depth, albedo, R, t, light, renderer, views_per_image, align_corners):
-        _require_cuda(depth, albedo, R, t, light)
+    def forward(ctx, depth, albedo, R, t, light, renderer, views_per_image, align_corners, mask=None,
+                want_mask=False):
+        _require_cuda(depth, albedo, R, t, light, mask)
         lib = _lib.load()
         N, S, _ = depth.shape
         B = N * views_per_image
@@ -310,17 +311,23 @@ class RenderChainFn(torch.autograd.Function):
         recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
         recon_depth = torch.empty(B, S, S, device=dev, dtype=torch.float32)
         fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)
+        mask_in = _f32c(mask.reshape(N, S, S)) if mask is not None else None
+        mask_out = torch.empty(B, 1, S, S, device=dev, dtype=torch.float32) if want_mask else None
         _lib.check(lib.g2s_render_fused_fwd(ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N,
                                             views_per_image, int(bool(align_corners)), _p(zbuf), ws_views,
-                                            _p(normal), _p(recon_im), _p(recon_depth), _p(fidx), _stream()),
+                                            _p(normal), _p(recon_im), _p(recon_depth), _p(fidx), _p(mask_in),
+                                            _p(mask_out), _stream()),
                    "g2s_render_fused_fwd")
         ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape)
         ctx.mark_non_differentiable(fidx)
+        if want_mask:
+            ctx.mark_non_differentiable(mask_out)
+            return recon_im, recon_depth, fidx, mask_out
         return recon_im, recon_depth, fidx
 
     @staticmethod
-    def backward(ctx, g_im, g_depth_out, _g_fidx):
+    def backward(ctx, g_im, g_depth_out, _g_fidx, _g_mask=None):
         lib = _lib.load()
         d, a, Rc, tc, L, normal, recon_depth, fidx = ctx.saved_tensors
         renderer, vpi, align, Rshape, tshape = ctx.meta
@@ -345,4 +352,4 @@ class RenderChainFn(torch.autograd.Function):
                                             _stream()), "g2s_render_fused_bwd")
         gR = gR.sum_to_size(Rshape)
         gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
-        return g_depth, g_albedo, gR, gt, gL, None, None, None
+        return g_depth, g_albedo, gR, gt, gL, None, None, None, None, None

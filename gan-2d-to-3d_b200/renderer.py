@@ -145,6 +145,22 @@ class Renderer:
         return Fn.RenderChainFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, self, P,
                                       self.align_corners)
 
+    def render_pseudo_views(self, depth, albedo, view, light_a, light_b, light_d, mask=None, views_per_image=None):
+        """Forward-only twin of render_chain used by sample_pseudo_imgs (model.py:291-328): shade the canonical
+        albedo with per-view lighting `shading = a + b * max(0, n.d)` (for the random relighting of model.py:298-309
+        pass a = light_a + alpha * rand, b = light_b + rand, d = rand_light_d), warp it to `view` as
+        render_given_view(..., grid_sample=True) does (renderer.py:257-264) and warp `mask` [N,1|3,S,S] (None = ones)
+        with mode='nearest'.  Returns (pseudo_im [B,3,S,S] clamped to [-1,1], mask [B,1,S,S]); no gradients."""
+        N, B = depth.shape[0], view.shape[0]
+        P = views_per_image if views_per_image is not None else B // N
+        with torch.no_grad():
+            self.set_transform_matrices(view)
+            light5 = torch.cat([light_a.reshape(B, 1), light_b.reshape(B, 1), light_d.reshape(B, 3)], 1)
+            m = mask[:, 0] if mask is not None else None
+            im, _, _, mask_out = Fn.RenderChainFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, self, P,
+                                                        self.align_corners, m, True)
+        return im, mask_out
+
     # -- sweeps -----------------------------------------------------------------------------------------
     def _view_sample(self, im, depth, view):
         self.set_transform_matrices(view)

@@ -116,13 +116,17 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * kernel that writes it and the kernel that reads it; g2s_chunk_views(S) returns the recommended chunk (32 MB of
  * z-buffer).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,8] (packed texels: normal xyz,
  * albedo rgb, 2 pad; kept for the backward).
- * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S]. */
+ * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S] (may be NULL).
+ * Optional (sample_pseudo_imgs, model.py:291-328 -> render_given_view(..., mask, grid_sample=True), renderer.py:257-264):
+ * mask_out [n_views,S,S] = grid_sample(mask, grid, mode='nearest') of mask_in [n_images,S,S] (NULL = all ones); pass
+ * mask_out = NULL to skip. */
 int g2s_chunk_views(int image_size);
 int g2s_chunk_views_bwd(int image_size);   /* recommended ws_views of g2s_render_fused_bwd (~1 GB of scratch) */
 int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
-                         float *recon_depth, int32_t *face_idx, void *stream);
+                         float *recon_depth, int32_t *face_idx, const float *mask_in, float *mask_out,
+                         void *stream);
 
 /* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
  * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,7,S,S] (as above),

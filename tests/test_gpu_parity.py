@@ -277,6 +277,41 @@ def test_fused_equals_composition_multi_image():
     assert rel_err(albedo.grad, ga) < TOL
 
 
+def test_render_pseudo_views_vs_oracle():
+    """sample_pseudo_imgs path (model.py:291-328): relit texture warped by render_given_view(grid_sample=True) plus the
+    nearest-neighbour mask warp, as one fused forward"""
+    S, P = 32, 5
+    case = _case(S, P, 71, 90.0)
+    orc, ren = oracle_renderer(S), _cuda_renderer(S)
+    gen = torch.Generator().manual_seed(5)
+    a = torch.rand(P, 1, generator=gen) * 0.5 + 0.3
+    b = torch.rand(P, 1, generator=gen) * 0.5 + 0.3
+    d = torch.cat([torch.rand(P, 2, generator=gen) - 0.5, torch.ones(P, 1)], 1)
+    d = d / ((d ** 2).sum(1, keepdim=True)) ** 0.5
+    mask = (torch.rand(1, 1, S, S, generator=gen) > 0.3).float()
+    R = ro.get_transform_matrices(case["view"])[0]
+    t = case["view"][:, 3:].reshape(P, 1, 3)
+    with torch.no_grad():
+        normal = orc.get_normal_from_depth(case["depth"])
+        _, tex = ro.get_shading(normal, a, b, d, case["albedo"])
+        orc.rot_mat, orc.trans_xyz = R, t
+        rd = orc.warp_canon_depth(case["depth"].expand(P, S, S))
+        grid = orc.get_inv_warped_2d_grid(rd)
+        im_o = F.grid_sample(tex, grid, mode="bilinear", align_corners=False).clamp(-1, 1)
+        m_o = F.grid_sample(mask.expand(P, 1, S, S), grid, mode="nearest", align_corners=False)
+    import g2s_b200
+    light5 = torch.cat([a, b, d], 1).cuda()
+    with torch.no_grad():
+        im, rd_c, fidx, m = g2s_b200.functional.RenderChainFn.apply(case["depth"].cuda(), case["albedo"].cuda(), R.cuda(),
+                                                                   t.cuda(), light5, ren, P, False, mask[:, 0].cuda(), True)
+        _, m1 = ren.render_pseudo_views(case["depth"].cuda(), case["albedo"].cuda(), case["view"].cuda(), a.cuda(),
+                                        b.cuda(), d.cuda())
+    assert torch.equal(rd_c.cpu(), rd)
+    assert rel_err(im.cpu(), im_o) < TOL
+    assert float((m.cpu() != m_o).float().mean()) < 2e-3      # nearest: a tap exactly between two texels may round apart
+    assert m1.shape == (P, 1, S, S) and float(m1.min()) >= 0.0 and float(m1.max()) == 1.0
+
+
 @pytest.mark.parametrize("name", ["s16_p3", "s32_p2"])
 def test_render_yaw_mesh_branch_golden(name):
     g = golden(name)
