@@ -127,7 +127,7 @@ def run_reference_arm(args):
         return
     S, P = args.size, args.views
     threads = os.cpu_count() or 1
-    views = 2 if S <= 128 else 1
+    views = 8 if S <= 128 else 2          # ~7 s (128^2) / ~30 s (256^2) of brute-force rasterisation per step on 16 cores
     steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
     value, dt = cpu_reference_run(S, views, steps, warmup, threads)
     sample = "%d step(s) x %d view(s) of one %dx%d image, fwd+bwd, brute-force face loop" % (steps, views, S, S)
@@ -304,10 +304,37 @@ def run_ours(args):
                          "note": "whole fwd+bwd step, SURVEY.md 8(d): renders/s/GPU x (64 S^2 + 48 S^2/P) bytes"},
                 "kernels": kernels}
 
+    # the literal BASELINE.json configs[1] shape, one image x P views per step: launch-bound, so also as a CUDA graph
+    single = None
+    if world == 1:
+        try:
+            from g2s_b200 import graphs
+            one = synthetic.make_case(S, P, seed=99, n_images=1)
+            one = {k: v.to(dev) for k, v in one.items()}
+            gstep = graphs.GraphedRenderStep(ren, 1, P)
+            gstep.step(one["depth"], one["albedo"], one["view"], one["light"], one["cotangent"])
+
+            def eager_one():
+                d1 = one["depth"].requires_grad_(True)
+                a1 = one["albedo"].requires_grad_(True)
+                im1 = ren.render_chain(d1, a1, one["view"], one["light"], views_per_image=P)[0]
+                torch.autograd.grad((im1 * one["cotangent"]).sum(), [d1, a1])
+
+            for _ in range(5):
+                eager_one()
+            reps = 100
+            ms_g = timed(lambda: gstep.step(), reps) / reps
+            ms_e = timed(eager_one, reps) / reps
+            single = {"workload": "1 image x %d views at %dx%d, fwd+bwd (literal configs[1] shape; launch-bound)" % (P, S, S),
+                      "cuda_graph": {"value": P / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g},
+                      "eager": {"value": P / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e}}
+        except Exception as exc:   # the headline numbers do not depend on this extra
+            single = {"error": str(exc)[:200]}
+
     threads = os.cpu_count() or 1
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        views = 2 if S <= 128 else 1
+        views = 8 if S <= 128 else 1
         v, dt = cpu_reference_run(S, views, 2, 0, threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "2 steps x %d view(s) of one %dx%d image, fwd+bwd, oracle with the reference's "
@@ -318,7 +345,8 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(args, N), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "single_image": single}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -327,7 +355,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=256, help="images per GPU per step")

@@ -10,7 +10,7 @@ Functions in `functional`.
 from .utils import (get_grid, get_rotation_matrix, get_transform_matrices, get_face_idx, get_lighting_directions,
                     get_shading)
 from .renderer import Renderer, EPS
-from . import functional, synthetic, sharding, build as _build  # noqa: F401
+from . import functional, graphs, synthetic, sharding, build as _build  # noqa: F401
 
 __all__ = ["Renderer", "get_grid", "get_rotation_matrix", "get_transform_matrices", "get_face_idx",
            "get_lighting_directions", "get_shading", "functional", "synthetic", "EPS"]

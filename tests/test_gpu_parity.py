@@ -447,6 +447,25 @@ def test_shared_reciprocal_division_is_ieee_exact():
     assert int(bad.item()) == 0
 
 
+def test_cuda_graph_step_matches_eager():
+    """forward + backward captured once into a CUDA graph (small, launch-bound batches) == eager"""
+    import g2s_b200
+    S, P = 32, 4
+    case = _case(S, P, 81, 60.0)
+    ren = _cuda_renderer(S)
+    g = g2s_b200.graphs.GraphedRenderStep(ren, 1, P)
+    dev = {k: v.cuda() for k, v in case.items()}
+    for _ in range(2):     # replay twice: the z-buffer must come back clean each time
+        im, rd, fidx, grads = g.step(dev["depth"], dev["albedo"], dev["view"], dev["light"], dev["cotangent"])
+    d, a = dev["depth"].clone().requires_grad_(True), dev["albedo"].clone().requires_grad_(True)
+    v, l = dev["view"].clone().requires_grad_(True), dev["light"].clone().requires_grad_(True)
+    im_e, rd_e, f_e = ren.render_chain(d, a, v, l, views_per_image=P)
+    (im_e * dev["cotangent"]).sum().backward()
+    assert torch.equal(fidx, f_e) and torch.equal(rd, rd_e) and torch.equal(im, im_e)
+    for gg, ref in zip(grads, (d.grad, a.grad, v.grad, l.grad)):
+        assert rel_err(gg, ref) < TOL
+
+
 def test_error_behaviour():
     import g2s_b200
     ren = _cuda_renderer(32)
