@@ -156,9 +156,11 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import g2s_b200
-    from g2s_b200 import synthetic, _lib
+    from g2s_b200 import synthetic, _lib, build as _build
 
     rank = int(os.environ.get("RANK", "0"))
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        _build.build()      # no-op when the in-tree library is up to date (building the product is not a fallback)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():

@@ -8,9 +8,11 @@ plus the caller-side helpers the fused path absorbs (get_lighting_directions, ge
 Functions in `functional`.
 """
 from .utils import (get_grid, get_rotation_matrix, get_transform_matrices, get_face_idx, get_lighting_directions,
-                    get_shading)
+                    get_shading, get_textures_from_im, vcolor_to_texture_cube, mm_normalize, rand_range,
+                    rand_posneg_range)
 from .renderer import Renderer, EPS
 from . import functional, graphs, synthetic, sharding, build as _build  # noqa: F401
 
 __all__ = ["Renderer", "get_grid", "get_rotation_matrix", "get_transform_matrices", "get_face_idx",
-           "get_lighting_directions", "get_shading", "functional", "synthetic", "EPS"]
+           "get_lighting_directions", "get_shading", "get_textures_from_im", "vcolor_to_texture_cube", "mm_normalize",
+           "rand_range", "rand_posneg_range", "functional", "graphs", "sharding", "synthetic", "EPS"]

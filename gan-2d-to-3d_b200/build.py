@@ -21,6 +21,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 def needs_build():
     if not os.path.exists(LIB):
         return True
+    if not os.path.exists(NVCC):
+        return False          # prebuilt library, no compiler on this machine
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(d) > t for d in DEPS)
 

@@ -62,6 +62,49 @@ def get_face_idx(b, h, w):
     return torch.cat([faces1, faces2], 0).repeat(b, 1, 1).int()
 
 
+# utils.py:83-95 cube coefficients: with them, trilinear sampling of the 2x2x2 texture on the simplex reproduces the
+# barycentric blend of the three vertex colours (k_resolve_rgb evaluates exactly this in registers)
+_CUBE = [[0.5, 0.5, 0.5], [0, 0, 1], [0, 1, 0], [-0.5, 0.5, 0.5], [1, 0, 0], [0.5, -0.5, 0.5], [0.5, 0.5, -0.5],
+         [0, 0, 0]]
+
+
+def vcolor_to_texture_cube(vcolors):
+    """utils.py:83-95 (compatibility only: the mesh-texture kernels never materialise the [B,F,2,2,2,C] cube)."""
+    b, c, n, f = vcolors.shape
+    coeffs = torch.tensor(_CUBE, dtype=vcolors.dtype, device=vcolors.device)
+    return coeffs.matmul(vcolors.permute(0, 2, 3, 1)).reshape(b, n, 2, 2, 2, c)
+
+
+def get_textures_from_im(im, tx_size=1):
+    """utils.py:98-109 (compatibility only)."""
+    b, c, h, w = im.shape
+    if tx_size == 1:
+        textures = torch.cat([im[:, :, :h - 1, :w - 1].reshape(b, c, -1), im[:, :, 1:, 1:].reshape(b, c, -1)], 2)
+        return textures.transpose(2, 1).reshape(b, -1, 1, 1, 1, c)
+    if tx_size == 2:
+        t1 = torch.stack([im[:, :, :h - 1, :w - 1], im[:, :, :h - 1, 1:], im[:, :, 1:, :w - 1]], -1).reshape(b, c, -1, 3)
+        t2 = torch.stack([im[:, :, 1:, :w - 1], im[:, :, :h - 1, 1:], im[:, :, 1:, 1:]], -1).reshape(b, c, -1, 3)
+        return vcolor_to_texture_cube(torch.cat([t1, t2], 2))
+    raise NotImplementedError("Currently support texture size of 1 or 2 only.")
+
+
+def mm_normalize(x, min=0, max=1):
+    """utils.py:4-10."""
+    x_min = x.min()
+    return (x - x_min) / (x.max() - x_min) * (max - min) + min
+
+
+def rand_range(size, min, max):
+    """utils.py:13-14."""
+    return torch.rand(size) * (max - min) + min
+
+
+def rand_posneg_range(size, min, max):
+    """utils.py:17-19."""
+    i = (torch.rand(size) > 0.5).type(torch.float) * 2. - 1.
+    return i * rand_range(size, min, max)
+
+
 def get_lighting_directions(lighting):
     """model.py:347-353: raw light [B,4] -> (ambient a [B,1], diffuse b [B,1], direction d [B,3])."""
     a = lighting[:, :1] / 2 + 0.5

@@ -67,6 +67,13 @@ def test_host_mirror_of_utils_matches_oracle():
     light = torch.rand(3, 4) * 2 - 1
     for a, b in zip(g2s_b200.get_lighting_directions(light), ro.get_lighting_directions(light)):
         assert torch.equal(a, b)
+    im = torch.rand(2, 3, 5, 6)
+    for tx in (1, 2):
+        assert torch.allclose(g2s_b200.get_textures_from_im(im, tx), ro.get_textures_from_im(im, tx), atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        g2s_b200.get_textures_from_im(im, 3)
+    x = torch.rand(10)
+    assert float(g2s_b200.mm_normalize(x, 2, 5).min()) == 2.0 and abs(float(g2s_b200.mm_normalize(x, 2, 5).max()) - 5.0) < 1e-6
 
 
 def test_renderer_constructs_on_cpu_and_refuses_cpu_compute():
