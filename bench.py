@@ -161,6 +161,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         _build.build()      # no-op when the in-tree library is up to date (building the product is not a fallback)
+    else:
+        for _ in range(240):            # other ranks wait for rank 0's (re)build before loading the library
+            if not _build.needs_build():
+                break
+            time.sleep(0.5)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
