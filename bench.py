@@ -294,19 +294,25 @@ def run_ours(args):
             k["frac"] = k["achieved_gbs"] / peak
     kernels.sort(key=lambda k: -k["ms_per_step"])
     dom = kernels[0] if kernels else None
-    traffic = None
+    traffic, ncu_ctx = None, None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same launch shape only)
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tj = json.load(f)["kernels"].get(dom["name"])
         if tj and S == 128 and dom["launches"] and B * args.steps // dom["launches"] == tj["views_per_launch"]:
             traffic = tj["dram_bytes_per_launch"]
+            ncu_ctx = {k: tj[k] for k in ("sm_throughput_pct", "issue_active_pct", "occupancy_pct",
+                                         "dram_throughput_pct", "registers") if k in tj}
+            ncu_ctx["source"] = "profiles/r01_ncu_full.md (committed ncu --set full capture, not measured by this run)"
     except Exception:
         traffic = None
     step_achieved = value / world * per_render / 1e9
     roofline = {"bound": "hbm", "kernel": dom["name"] if dom else None,
                 "achieved": dom.get("achieved_gbs") if dom else None, "peak": peak, "unit": "GB/s",
                 "frac": dom.get("frac") if dom else None, "traffic": traffic, "peak_source": peak_src,
-                "kernel_share_of_step": dom["share_of_step"] if dom else None,
+                "kernel_share_of_step": dom["share_of_step"] if dom else None, "ncu": ncu_ctx,
+                "note": "the dominant kernel is the rasteriser: instruction-issue / latency bound by construction (bit-exact "
+                        "reproduction of the reference's un-fused fp32 arithmetic; its z-buffer lives in L2), so its HBM "
+                        "fraction is tiny; the HBM-bound pixel kernels and the whole-step figure are under kernels[] / step",
                 "step": {"alg_bytes_per_render": per_render, "achieved": step_achieved, "frac": step_achieved / peak,
                          "note": "whole fwd+bwd step, SURVEY.md 8(d): renders/s/GPU x (64 S^2 + 48 S^2/P) bytes"},
                 "kernels": kernels}
