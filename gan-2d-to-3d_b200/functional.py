@@ -21,9 +21,19 @@ def _p(t):
 
 
 def _require_cuda(*tensors):
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("gan-2d-to-3d_b200: this operator runs only on CUDA tensors (no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the C ABI launches on the current device (one process per GPU); fail loudly instead of touching the
+            # wrong device's memory
+            raise RuntimeError("gan-2d-to-3d_b200: tensor on cuda:%d but the current device is cuda:%d "
+                               "(torch.cuda.set_device first)" % (t.device.index, cur))
 
 
 def _f32c(t):
