@@ -36,8 +36,9 @@ struct TileSmem {
     uint16_t hq_code[HQ_CAP];
     uint16_t fq[NSLOT];
     unsigned owned[NSLOT / 32];
+    uint16_t wq[NSLOT];          // wide faces whose rows a warp expands into tasks
     float sRt[12];
-    int n_hq, n_fq, n_tq;
+    int n_hq, n_fq, n_tq, n_wq;
 };
 
 // code = slot | rev << 9, slot = quad * 2 + tri
@@ -425,28 +426,59 @@ __device__ __noinline__ void push_row_tasks(TileSmem& sm, const Ops& ops, float*
     rec_store(recs, code & 511, c, code);
     uint32_t* tq = sm.tq;
     const int bw = c.bb.x1 - c.bb.x0 + 1, bh = c.bb.y1 - c.bb.y0 + 1;
-    const bool wide = bw > 16;
-    float px[3], py[3];
-    if (wide) {
-        px[0] = ndc_to_pix(c.f.x0, is); px[1] = ndc_to_pix(c.f.x1, is); px[2] = ndc_to_pix(c.f.x2, is);
-        py[0] = ndc_to_pix(c.f.y0, is); py[1] = ndc_to_pix(c.f.y1, is); py[2] = ndc_to_pix(c.f.y2, is);
+    if (bw > 16) {   // wide box: rows are expanded by a whole warp later (expand_wide_faces), one lane per row
+        sm.wq[atomicAdd(&sm.n_wq, 1)] = (uint16_t)code;
+        return;
     }
-    for (int ry = 0; ry < bh; ry++) {
-        int s0 = 0, s1 = (bw - 1) >> 3;
-        if (wide) {
-            int xa, xb;
-            row_extent(px, py, c.bb.y0 + ry, c.bb, &xa, &xb);
-            if (xa > xb) continue;
-            s0 = (xa - c.bb.x0) >> 3; s1 = (xb - c.bb.x0) >> 3;
+    const int nseg = (bw + 7) >> 3, n = bh * nseg;
+    const int base = atomicAdd(&sm.n_tq, n);
+    for (int k = 0; k < n; k++) {
+        const int ry = k / nseg, sg = k - ry * nseg;
+        if (base + k < TQ_CAP) {
+            tq[base + k] = (uint32_t)code | ((uint32_t)ry << 10) | ((uint32_t)sg << 22);
+        } else {
+            const int xa = c.bb.x0 + sg * 8;
+            scan_row_inline(ops, c.f, code, face, c.bb.y0 + ry, xa, min(xa + 7, c.bb.x1), is);
         }
-        const int n = s1 - s0 + 1;
-        const int base = atomicAdd(&sm.n_tq, n);
-        for (int k = 0; k < n; k++) {
-            if (base + k < TQ_CAP) {
-                tq[base + k] = (uint32_t)code | ((uint32_t)ry << 10) | ((uint32_t)(s0 + k) << 22);
-            } else {
-                const int xa = c.bb.x0 + (s0 + k) * 8;
-                scan_row_inline(ops, c.f, code, face, c.bb.y0 + ry, xa, min(xa + 7, c.bb.x1), is);
+    }
+}
+
+// Rows of the queued wide faces -> row tasks: one warp per face, one lane per row; a row only queues the 8-column
+// segments that overlap the conservative extent of the triangle on that row.
+template <class Ops>
+__device__ __forceinline__ void expand_wide_faces(TileSmem& sm, const Ops& ops, const float* recs, int Q, int S, int ty0,
+                                                  int tx0) {
+    const int is = 2 * S, lane = threadIdx.x & 31, nw = sm.n_wq;
+    for (int e = threadIdx.x >> 5; e < nw; e += SPLAT_THREADS / 32) {
+        const int code = sm.wq[e];
+        Tri f;
+        BBox bb;
+        rec_load(recs, code & 511, f, bb);
+        const float px[3] = {ndc_to_pix(f.x0, is), ndc_to_pix(f.x1, is), ndc_to_pix(f.x2, is)};
+        const float py[3] = {ndc_to_pix(f.y0, is), ndc_to_pix(f.y1, is), ndc_to_pix(f.y2, is)};
+        const int bh = bb.y1 - bb.y0 + 1;
+        for (int r0 = 0; r0 < bh; r0 += 32) {
+            const int ry = r0 + lane;
+            int s0 = 0, n = 0;
+            if (ry < bh) {
+                int xa, xb;
+                row_extent(px, py, bb.y0 + ry, bb, &xa, &xb);
+                if (xa <= xb) { s0 = (xa - bb.x0) >> 3; n = ((xb - bb.x0) >> 3) - s0 + 1; }
+            }
+            int total;
+            const int off = warp_excl_scan(n, &total);
+            if (total == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sm.n_tq, total);
+            base = __shfl_sync(0xffffffffu, base, 0) + off;
+            for (int k = 0; k < n; k++) {
+                if (base + k < TQ_CAP) {
+                    sm.tq[base + k] = (uint32_t)code | ((uint32_t)ry << 10) | ((uint32_t)(s0 + k) << 22);
+                } else {
+                    const int xa = bb.x0 + (s0 + k) * 8;
+                    scan_row_inline(ops, code_tri(sm.sv, code), code, code_face(code, Q, S, ty0, tx0), bb.y0 + ry, xa,
+                                    min(xa + 7, bb.x1), is);
+                }
             }
         }
     }
@@ -562,6 +594,8 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     // ---- rounds: scan as many queued row tasks as are guaranteed to fit the hit queue (8 hits per task at most),
     // build the table entries of the faces that scored for the first time, drain.  One round for ordinary tiles;
     // tiles full of long wall faces take several.
+    __syncthreads();
+    expand_wide_faces(sm, ops, recs, Q, S, ty0, tx0);
     const uint32_t* tq = sm.tq;
     int t0 = 0, nf_done = 0;
     while (true) {
