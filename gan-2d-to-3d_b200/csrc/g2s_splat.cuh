@@ -37,8 +37,9 @@ struct TileSmem {
     uint16_t fq[NSLOT];
     unsigned owned[NSLOT / 32];
     uint16_t wq[NSLOT];          // wide faces whose rows a warp expands into tasks
+    uint16_t mq[NSLOT];          // other queued faces
     float sRt[12];
-    int n_hq, n_fq, n_tq, n_wq;
+    int n_hq, n_fq, n_tq, n_wq, n_mq;
 };
 
 // code = slot | rev << 9, slot = quad * 2 + tri
@@ -424,31 +425,43 @@ template <class Ops>
 __device__ __noinline__ void push_row_tasks(TileSmem& sm, const Ops& ops, float* recs, const TriClass c, int code,
                                             int face, int is) {
     rec_store(recs, code & 511, c, code);
-    uint32_t* tq = sm.tq;
-    const int bw = c.bb.x1 - c.bb.x0 + 1, bh = c.bb.y1 - c.bb.y0 + 1;
-    if (bw > 16) {   // wide box: rows are expanded by a whole warp later (expand_wide_faces), one lane per row
-        sm.wq[atomicAdd(&sm.n_wq, 1)] = (uint16_t)code;
-        return;
-    }
-    const int nseg = (bw + 7) >> 3, n = bh * nseg;
-    const int base = atomicAdd(&sm.n_tq, n);
-    for (int k = 0; k < n; k++) {
-        const int ry = k / nseg, sg = k - ry * nseg;
-        if (base + k < TQ_CAP) {
-            tq[base + k] = (uint32_t)code | ((uint32_t)ry << 10) | ((uint32_t)sg << 22);
-        } else {
-            const int xa = c.bb.x0 + sg * 8;
-            scan_row_inline(ops, c.f, code, face, c.bb.y0 + ry, xa, min(xa + 7, c.bb.x1), is);
-        }
-    }
+    // the rows are expanded into tasks later by whole warps (expand_queued_faces): wide boxes one lane per row with
+    // per-row extents, the others one lane per face
+    const int bw = c.bb.x1 - c.bb.x0 + 1;
+    if (bw > 16) sm.wq[atomicAdd(&sm.n_wq, 1)] = (uint16_t)code;
+    else sm.mq[atomicAdd(&sm.n_mq, 1)] = (uint16_t)code;
 }
 
 // Rows of the queued wide faces -> row tasks: one warp per face, one lane per row; a row only queues the 8-column
 // segments that overlap the conservative extent of the triangle on that row.
 template <class Ops>
-__device__ __forceinline__ void expand_wide_faces(TileSmem& sm, const Ops& ops, const float* recs, int Q, int S, int ty0,
-                                                  int tx0) {
-    const int is = 2 * S, lane = threadIdx.x & 31, nw = sm.n_wq;
+__device__ __forceinline__ void expand_queued_faces(TileSmem& sm, const Ops& ops, const float* recs, int Q, int S, int ty0,
+                                                    int tx0) {
+    const int is = 2 * S, lane = threadIdx.x & 31, nw = sm.n_wq, nm = sm.n_mq;
+    // medium boxes: one lane per face, all rows x ceil(width / 8) segments
+    for (int e0 = (threadIdx.x >> 5) * 32; e0 < nm; e0 += SPLAT_THREADS) {
+        const int e = e0 + lane;
+        const int code = e < nm ? sm.mq[e] : 0;
+        Tri f;
+        BBox bb;
+        rec_load(recs, code & 511, f, bb);
+        const int nseg = (bb.x1 - bb.x0 + 8) >> 3, n = e < nm ? (bb.y1 - bb.y0 + 1) * nseg : 0;
+        int total;
+        const int off = warp_excl_scan(n, &total);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sm.n_tq, total);
+        base = __shfl_sync(0xffffffffu, base, 0) + off;
+        for (int k = 0, ry = 0, sg = 0; k < n; k++) {
+            if (base + k < TQ_CAP) {
+                sm.tq[base + k] = (uint32_t)code | ((uint32_t)ry << 10) | ((uint32_t)sg << 22);
+            } else {
+                const int xa = bb.x0 + sg * 8;
+                scan_row_inline(ops, code_tri(sm.sv, code), code, code_face(code, Q, S, ty0, tx0), bb.y0 + ry, xa,
+                                min(xa + 7, bb.x1), is);
+            }
+            if (++sg == nseg) { sg = 0; ry++; }
+        }
+    }
     for (int e = threadIdx.x >> 5; e < nw; e += SPLAT_THREADS / 32) {
         const int code = sm.wq[e];
         Tri f;
@@ -595,7 +608,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     // build the table entries of the faces that scored for the first time, drain.  One round for ordinary tiles;
     // tiles full of long wall faces take several.
     __syncthreads();
-    expand_wide_faces(sm, ops, recs, Q, S, ty0, tx0);
+    expand_queued_faces(sm, ops, recs, Q, S, ty0, tx0);
     const uint32_t* tq = sm.tq;
     int t0 = 0, nf_done = 0;
     while (true) {
