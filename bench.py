@@ -319,7 +319,7 @@ def run_ours(args):
 
     # the literal BASELINE.json configs[1] shape, one image x P views per step: launch-bound, so also as a CUDA graph
     single = None
-    if world == 1:
+    if world == 1 and not args.no_single_image:
         try:
             from g2s_b200 import graphs
             one = synthetic.make_case(S, P, seed=99, n_images=1)
@@ -375,6 +375,7 @@ def main():
     ap.add_argument("--views", type=int, default=16, help="projected pseudo-views per image")
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-image", action="store_true", help="skip the 1-image CUDA-graph extra (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
