@@ -4,15 +4,17 @@ repo-root shim:  `import g2s_b200`  (g2s_b200.py loads this package under that n
 
 Public surface (same names as the reference's GAN2Shape.renderer):
     Renderer, get_grid, get_rotation_matrix, get_transform_matrices, get_face_idx
-plus the caller-side helpers the fused path absorbs (get_lighting_directions, get_shading) and the autograd
-Functions in `functional`.
+plus the callers either side of the path (`callers`: get_clamped_depth, get_shading, PhotometricLoss with the
+validity mask, SmoothLoss -- CUDA kernels behind the same C ABI), get_lighting_directions, and the autograd Functions in
+`functional`.
 """
 from .utils import (get_grid, get_rotation_matrix, get_transform_matrices, get_face_idx, get_lighting_directions,
-                    get_shading, get_textures_from_im, vcolor_to_texture_cube, mm_normalize, rand_range,
-                    rand_posneg_range)
+                    get_textures_from_im, vcolor_to_texture_cube, mm_normalize, rand_range, rand_posneg_range)
+from .callers import get_shading, get_clamped_depth, recon_im_mask, PhotometricLoss, SmoothLoss
 from .renderer import Renderer, EPS
-from . import functional, graphs, synthetic, sharding, build as _build  # noqa: F401
+from . import functional, callers, graphs, synthetic, sharding, build as _build  # noqa: F401
 
 __all__ = ["Renderer", "get_grid", "get_rotation_matrix", "get_transform_matrices", "get_face_idx",
            "get_lighting_directions", "get_shading", "get_textures_from_im", "vcolor_to_texture_cube", "mm_normalize",
-           "rand_range", "rand_posneg_range", "functional", "graphs", "sharding", "synthetic", "EPS"]
+           "rand_range", "rand_posneg_range", "get_clamped_depth", "recon_im_mask", "PhotometricLoss", "SmoothLoss",
+           "callers", "functional", "graphs", "sharding", "synthetic", "EPS"]

@@ -51,6 +51,19 @@ SIGNATURES = {
     "g2s_view_bwd": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp]),
     "g2s_light_fwd": (_c_int, [_vp, _c_int, _vp, _vp]),
     "g2s_light_bwd": (_c_int, [_vp, _c_int, _vp, _vp, _vp]),
+    "g2s_reduce_ws_bytes": (ctypes.c_size_t, []),
+    "g2s_clamped_depth_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _c_int, _vp, _vp,
+                                       _vp, _vp]),
+    "g2s_clamped_depth_bwd": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _vp, _vp,
+                                       _vp]),
+    "g2s_shading_fwd": (_c_int, [_vp, _c_long, _vp, _vp, _c_long, _c_int, _c_int, _vp, _vp, _vp]),
+    "g2s_shading_bwd": (_c_int, [_vp, _c_long, _vp, _vp, _c_long, _c_int, _c_int, _vp, _vp, _vp, _c_long, _vp, _vp,
+                                 _c_long, _vp]),
+    "g2s_photometric_fwd": (_c_int, [_vp, _vp, _c_long, _vp, _c_float, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "g2s_photometric_bwd": (_c_int, [_vp, _vp, _c_long, _vp, _c_float, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
+                                     _vp]),
+    "g2s_smooth_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "g2s_smooth_bwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "g2s_launch_count": (_c_long, []),
     "g2s_selftest_division": (_c_int, [ctypes.c_ulonglong, ctypes.c_uint, _vp, _vp]),
     "g2s_profile_enable": (_c_int, [_c_int]),

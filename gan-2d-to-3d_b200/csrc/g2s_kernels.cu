@@ -44,12 +44,13 @@ Cam make_cam(const g2s_camera* c) {
 // ---- instrumentation: launch counter + optional CUDA-event timing of every kernel (bench.py / tests) ----
 enum KernelId { K_ZINIT, K_SPLAT, K_RESOLVE, K_RESOLVE_FUSED, K_GRID_FWD, K_GRID_BWD, K_NORMAL_FWD, K_NORMAL_BWD,
                 K_SAMPLE_FWD, K_SAMPLE_BWD, K_CLAMP_GRAD, K_RASTER_BWD, K_BWD_PIXEL, K_BWD_TEX, K_GRID3D, K_RESOLVE_RGB,
-                K_PROJECT, K_VERTEX_BWD, K_VIEW, K_LIGHT, K_COUNT };
+                K_PROJECT, K_VERTEX_BWD, K_VIEW, K_LIGHT, K_CLAMPED_DEPTH, K_SHADING, K_PHOTOMETRIC, K_SMOOTH, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_zbuf_init", "k_splat", "k_resolve", "k_resolve_fused", "k_warp_grid_fwd",
                                            "k_warp_grid_bwd", "k_normal_fwd", "k_normal_bwd", "k_sample_fwd",
                                            "k_sample_bwd", "k_clamp_grad", "k_raster_bwd_px", "k_render_bwd_pixel",
                                            "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb", "k_project_verts",
-                                           "k_vertex_bwd", "k_view_fwd/bwd", "k_light_fwd/bwd"};
+                                           "k_vertex_bwd", "k_view_fwd/bwd", "k_light_fwd/bwd", "k_clamped_depth",
+                                           "k_shading_fwd/bwd", "k_photometric", "k_smooth"};
 std::atomic<long> g_launches{0};
 struct ProfRec { int id; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
@@ -1525,3 +1526,5 @@ int g2s_profile_read(int max_kernels, const char** names, float* total_ms, int* 
 }
 
 }  // extern "C"
+
+#include "g2s_callers.cuh"

@@ -112,11 +112,3 @@ def get_lighting_directions(lighting):
     d = torch.cat([lighting[:, 2:], torch.ones(lighting.size(0), 1, device=lighting.device, dtype=lighting.dtype)], 1)
     d = d / ((d ** 2).sum(1, keepdim=True)) ** 0.5
     return a, b, d
-
-
-def get_shading(normal, lighting_a, lighting_b, lighting_d, albedo):
-    """model.py:355-360 (torch composition; the fused kernel evaluates the same formula per texel)."""
-    diffuse = (normal * lighting_d.view(-1, 1, 1, 3)).sum(3).clamp(min=0).unsqueeze(1)
-    shading = lighting_a.view(-1, 1, 1, 1) + lighting_b.view(-1, 1, 1, 1) * diffuse
-    texture = (albedo / 2 + 0.5) * shading * 2 - 1
-    return diffuse, texture

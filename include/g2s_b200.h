@@ -169,6 +169,53 @@ int g2s_grid3d_fwd(const g2s_camera *cam, const float *depth, long depth_view_st
                    const int *crop, const float *R0, const float *t0, const float *R1, const float *R2,
                    const float *t2, float *out, void *stream);
 
+/* ---- callers either side of the path -------------------------------------------
+ * Every reduction below is deterministic: per-block partial sums go to the caller-owned `reduce_ws`
+ * (g2s_reduce_ws_bytes() bytes, 8-byte aligned) and are finished in a fixed order. */
+size_t g2s_reduce_ws_bytes(void);
+
+/* get_clamped_depth + rescale_depth: model.py:337-345, 85-86.  depth_raw is n_groups groups of maps_per_group maps [H,W];
+ * the mean that is subtracted before tanh is taken per group (the reference's `view(1,-1).mean(1)` is ONE group over the
+ * whole tensor).  clamp_border: the 2 leftmost / 2 rightmost columns are blended with the reference's literal F.pad
+ * weight 1.02: depth*(1-1.02) + 1.02*border_depth.  mean_out [n_groups] is kept for the backward.  W >= 4;
+ * n_groups <= 148 (reduce_ws holds 32 partial sums per group). */
+int g2s_clamped_depth_fwd(const float *depth_raw, int n_groups, int maps_per_group, int H, int W, float min_depth,
+                          float max_depth, float border_depth, int clamp_border, void *reduce_ws, float *mean_out,
+                          float *depth, void *stream);
+int g2s_clamped_depth_bwd(const float *depth_raw, const float *mean, const float *grad_depth, int n_groups,
+                          int maps_per_group, int H, int W, float min_depth, float max_depth, int clamp_border,
+                          void *reduce_ws, float *grad_raw, void *stream);
+
+/* get_shading: model.py:355-360.  normal [*,H*W,3], albedo [*,3,H*W] with `*_view_stride` floats between views (0 = one
+ * map shared by all views), light5 [B,5] (g2s_light_fwd) -> diffuse [B,1,H*W] (may be NULL), texture [B,3,H*W].
+ * Backward: grad_diffuse / grad_texture (either may be NULL, not both); grad_normal, grad_albedo (strides as above,
+ * 0 = summed over the views) and grad_light5 [B,5] are ACCUMULATED (caller zero-fills; any may be NULL). */
+int g2s_shading_fwd(const float *normal, long normal_view_stride, const float *light5, const float *albedo,
+                    long albedo_view_stride, int B, int HW, float *diffuse, float *texture, void *stream);
+int g2s_shading_bwd(const float *normal, long normal_view_stride, const float *light5, const float *albedo,
+                    long albedo_view_stride, int B, int HW, const float *grad_diffuse, const float *grad_texture,
+                    float *grad_normal, long grad_normal_view_stride, float *grad_light5, float *grad_albedo,
+                    long grad_albedo_view_stride, void *stream);
+
+/* Validity mask + PhotometricLoss (conf_sigma=None) in one pass: model.py:146-150 / 265-269 and losses.py:39-51.
+ *   mask[b,i] = (recon_depth ? recon_depth[b,i] < depth_thresh : 1) * (mask_in ? mask_in[b,i] : 1)
+ *   loss      = sum(|im1 - im2| * mask) / (C * sum(mask))         (both NULL: the plain mean of losses.py:50)
+ * im1 [B,C,HW]; im2 [*,C,HW] with im2_batch_stride floats between items (0 = one target for all views);
+ * recon_depth, mask_in [B,HW].  out3 = {loss, numerator, denominator}; the backward reads it back as sums3 and WRITES
+ * grad_im1 and/or grad_im2 [B,C,HW] (grad_im2 needs im2_batch_stride == C*HW); grad_loss is a DEVICE scalar. */
+int g2s_photometric_fwd(const float *im1, const float *im2, long im2_batch_stride, const float *recon_depth,
+                        float depth_thresh, const float *mask_in, int B, int C, int HW, void *reduce_ws, float *out3,
+                        void *stream);
+int g2s_photometric_bwd(const float *im1, const float *im2, long im2_batch_stride, const float *recon_depth,
+                        float depth_thresh, const float *mask_in, int B, int C, int HW, const float *sums3,
+                        const float *grad_loss, float *grad_im1, float *grad_im2, void *stream);
+
+/* SmoothLoss of ONE map [M,H,W]: losses.py:54-79 (mean|dx2| + mean|dxdy| + mean|dydx| + mean|dy2|, the differences taken
+ * in the reference's order).  out5 = {loss, the four means}.  H, W >= 3.  Backward WRITES grad_map [M,H,W]; grad_loss is a
+ * DEVICE scalar. */
+int g2s_smooth_fwd(const float *map, int M, int H, int W, void *reduce_ws, float *out5, void *stream);
+int g2s_smooth_bwd(const float *map, int M, int H, int W, const float *grad_loss, float *grad_map, void *stream);
+
 /* ---- instrumentation (bench.py / tests; not part of the reference surface) ---------------------------
  * g2s_launch_count: kernels launched by this library since it was loaded.
  * g2s_profile_enable(1): record a CUDA event pair around every kernel launch on its stream;
