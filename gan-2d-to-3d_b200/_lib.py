@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libg2s_b200.so")
+# G2S_LIB: an alternative build of the same library (kernel A/B experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("G2S_LIB") or os.path.join(HERE, "csrc", "libg2s_b200.so")
 
 _c_int, _c_long, _c_float, _vp = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p
 

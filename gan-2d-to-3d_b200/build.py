@@ -36,5 +36,12 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(out, defines):
+    """Kernel A/B experiments: the same sources with extra -D flags into `out` (selected at run time with G2S_LIB=...)."""
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-o", out] + SOURCES
+    subprocess.check_call(cmd)
+    return LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -140,6 +140,12 @@ k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, c
         else { const int r = k - 2 * tiles_yy; tile_y = r / (tiles_x - 2); tile_x = 1 + r % (tiles_x - 2); }
     }
     const int ty0 = tile_y * TILE_H, tx0 = tile_x * TILE;
+#ifdef G2S_EXP_SKIP_BORDER   // timing experiment only (wrong results): which tiles the time goes to
+    if (tile_x == 0 || tile_x == tiles_x - 1) return;
+#endif
+#ifdef G2S_EXP_SKIP_INTERIOR
+    if (!(tile_x == 0 || tile_x == tiles_x - 1)) return;
+#endif
     if (!FROM_VERTS) {
         if (tid < 9) sm.sRt[tid] = R[b * 9 + tid];
         else if (tid < 12) sm.sRt[tid] = t[b * 3 + tid - 9];
@@ -184,7 +190,23 @@ struct FusedArgs {
     float* mask_out;      // optional [n_views,S,S]: grid_sample(mask, grid, mode='nearest') (renderer.py:263)
 };
 
-constexpr int PBX = 64, PBY = 4;   // pixel-kernel block: 64 columns x 4 rows
+// pixel-kernel blocks (threads = output pixels): the z-buffer resolve streams rows (64 x 4); the two backward pixel
+// kernels gather vertices / texels around a 2-D patch and run faster on square blocks (measured, profiles/r01_notes.md)
+#ifndef G2S_PBX
+#define G2S_PBX 64
+#define G2S_PBY 4
+#endif
+#ifndef G2S_RBX
+#define G2S_RBX 16
+#define G2S_RBY 8
+#endif
+#ifndef G2S_BPX
+#define G2S_BPX 16
+#define G2S_BPY 8
+#endif
+constexpr int PBX = G2S_PBX, PBY = G2S_PBY;   // k_resolve
+constexpr int RBX = G2S_RBX, RBY = G2S_RBY;   // k_raster_bwd_px
+constexpr int BPX = G2S_BPX, BPY = G2S_BPY;   // k_render_bwd_pixel
 
 // The 4 bilinear taps of one sample, clamped so that every load is unconditional (one round trip);
 // out-of-range taps get weight 0 (zeros padding).
@@ -680,29 +702,31 @@ k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, in
     o[0] = ndc[0]; o[1] = ndc[1]; o[2] = ndc[2];
 }
 
-__global__ void __launch_bounds__(PBX * PBY)
+__global__ void __launch_bounds__(RBX * RBY)
 k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
                 const float* __restrict__ proj, float* __restrict__ vgrad, int view0) {
     const int S = cam.S, is = 2 * S, bl = blockIdx.z, b = view0 + bl;
-    const int j = blockIdx.x * PBX + threadIdx.x, i = blockIdx.y * PBY + threadIdx.y;
+    const int j = blockIdx.x * RBX + threadIdx.x, i = blockIdx.y * RBY + threadIdx.y;
     if (j >= S || i >= S) return;
     const float g = g_sub[(long)bl * S * S + i * S + j];
     if (g == 0.f) return;
     const int* fm = face_idx + (long)b * is * is;
     const int2 r0 = *reinterpret_cast<const int2*>(fm + (long)(2 * i) * is + 2 * j);
     const int2 r1 = *reinterpret_cast<const int2*>(fm + (long)(2 * i + 1) * is + 2 * j);
-    const int f[4] = {r0.x, r0.y, r1.x, r1.y};
+    const int f0 = r0.x, f1 = r0.y, f2 = r1.x, f3 = r1.y;
     const float* pv = proj + (long)bl * S * S * 3;
     float* vg = vgrad + (long)bl * S * S * 3;
     const float hs = 0.5f * (float)is;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int face = f[k];
-        if (face < 0) continue;
-        bool seen = false;
-#pragma unroll
-        for (int k2 = 0; k2 < k; k2++) seen |= f[k2] == face;
-        if (seen) continue;
+    // Distinct faces of the 2x2 block, one per trip of ONE loop body (not four unrolled copies: the unrolled form ran
+    // at 17 active lanes per instruction and stalled on instruction fetch, profiles/r01_notes.md): `rem` = sub-pixels
+    // still to do; a trip takes the face of the lowest one and every other sub-pixel that shares it.
+    unsigned rem = (f0 >= 0 ? 1u : 0u) | (f1 >= 0 ? 2u : 0u) | (f2 >= 0 ? 4u : 0u) | (f3 >= 0 ? 8u : 0u);
+#pragma unroll 1
+    while (rem) {
+        const int k = __ffs(rem) - 1;
+        const int face = k == 0 ? f0 : (k == 1 ? f1 : (k == 2 ? f2 : f3));
+        unsigned mine = ((f0 == face ? 1u : 0u) | (f1 == face ? 2u : 0u) | (f2 == face ? 4u : 0u) | (f3 == face ? 8u : 0u)) & rem;
+        rem &= ~mine;
         int vidx[3];
         face_vertices(face, S, vidx);
         float nd[3][3];
@@ -710,12 +734,13 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         for (int m = 0; m < 3; m++) {
             nd[m][0] = __ldg(&pv[vidx[m] * 3]); nd[m][1] = __ldg(&pv[vidx[m] * 3 + 1]); nd[m][2] = __ldg(&pv[vidx[m] * 3 + 2]);
         }
-        float rec[FT_STRIDE];
+        float rec[15];
         face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
         float A[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k2 = k; k2 < 4; k2++) {
-            if (f[k2] != face) continue;
+#pragma unroll 1
+        while (mine) {
+            const int k2 = __ffs(mine) - 1;
+            mine &= mine - 1;
             const int xi = 2 * j + (k2 & 1), yi = is - 1 - (2 * i + (k2 >> 1));
             float w[3], zp = 0.f;
             record_weights_depth(rec, xi, yi, cam.near, cam.far, w, &zp);
@@ -811,7 +836,7 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
 // Writes per-view texture gradients (atomics into grad_tex_ws), the masked quarter gradient of
 // recon_depth (g_sub) and accumulates grad_R / grad_t.  grad_tex / g_sub are indexed by the LOCAL view
 // (chunked launches), everything else by the global view fa.view0 + blockIdx.z.
-__global__ void __launch_bounds__(PBX * PBY)
+__global__ void __launch_bounds__(BPX * BPY)
 k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ recon_depth,
                    const float* __restrict__ grad_recon_im, const float* __restrict__ grad_recon_depth,
                    float* __restrict__ g_sub, float* __restrict__ grad_tex, float* __restrict__ grad_R,
@@ -819,13 +844,13 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
     __shared__ float sview[17];
     const int S = cam.S, bl = blockIdx.z, b = fa.view0 + bl;
     {
-        const int k = threadIdx.y * PBX + threadIdx.x;
+        const int k = threadIdx.y * BPX + threadIdx.x;
         if (k < 9) sview[k] = fa.R[b * 9 + k];
         else if (k < 12) sview[k] = fa.t[b * 3 + k - 9];
         else if (k < 17) sview[k] = fa.light[b * 5 + k - 12];
         __syncthreads();
     }
-    const int j = blockIdx.x * PBX + threadIdx.x, i = blockIdx.y * PBY + threadIdx.y;
+    const int j = blockIdx.x * BPX + threadIdx.x, i = blockIdx.y * BPY + threadIdx.y;
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
@@ -867,8 +892,8 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
     for (int k = 0; k < 9; k++) accR[k] = acc[k];
 #pragma unroll
     for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
-    block_accumulate<9, PBX * PBY>(accR, grad_R + b * 9);
-    block_accumulate<3, PBX * PBY>(acct, grad_t + b * 3);
+    block_accumulate<9, BPX * BPY>(accR, grad_R + b * 9);
+    block_accumulate<3, BPX * BPY>(acct, grad_t + b * 3);
 }
 
 // fused render backward, texture stage: per image pixel, loop over the image's views that fall in this
@@ -1147,7 +1172,7 @@ __global__ void k_selftest_division(unsigned long long per_thread, unsigned seed
     if (bad) atomicAdd(mismatches, bad);
 }
 
-inline dim3 pix_grid2(int S, int views) { return dim3((S + PBX - 1) / PBX, (S + PBY - 1) / PBY, views); }
+inline dim3 pix_grid2(int S, int views, int bx = PBX, int by = PBY) { return dim3((S + bx - 1) / bx, (S + by - 1) / by, views); }
 
 // views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
 // scratch 16 S^2 B/view) stays resident in the 126 MB L2 between the kernel that writes it and the one that reads it
@@ -1177,7 +1202,7 @@ inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, in
     { Launch l_(K_PROJECT, st);
       k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj); }
     { Launch l_(K_RASTER_BWD, st);
-      k_raster_bwd_px<<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
+      k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), dim3(RBX, RBY), 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
       k_vertex_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
                                                                      gdstride, grad_R, grad_t); }
@@ -1392,7 +1417,7 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
         cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * nv * 3 * img_f, st);
         FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
         { Launch l_(K_BWD_PIXEL, st);
-          k_render_bwd_pixel<<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
+          k_render_bwd_pixel<<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
                                                                          grad_sub_ws, grad_tex_ws, grad_R, grad_t); }
         const int img_lo = (int)(v0 / views_per_image), img_hi = (int)((v0 + nv - 1) / views_per_image);
         { Launch l_(K_BWD_TEX, st);

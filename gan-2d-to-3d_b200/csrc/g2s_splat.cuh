@@ -22,10 +22,17 @@
 
 namespace g2s {
 
+#ifndef G2S_WARP_LOCAL
+#define G2S_WARP_LOCAL 1
+#endif
 constexpr int HQ_CAP = 16 * SPLAT_THREADS;                 // hit-queue entries per drain
 constexpr int NSLOT = 2 * TILE * TILE_H;       // (quad, triangle) slots of the face table
 constexpr int TQ_CAP = 4096;                  // queued row tasks per tile
-constexpr int FT_STRIDE = 16;                // fi[9], z[3], rcp_seed(z)[3], pad
+constexpr int FT_STRIDE = 17;                // fi[9], z[3], rcp_seed(z)[3], pad; ODD so that lanes on consecutive table
+                                             // entries hit distinct shared-memory banks (stride 16 was a 16/32-way conflict)
+// table entry of a (quad, triangle) code: triangle-major, so that the threads of a warp (consecutive quads) own
+// consecutive entries
+__device__ __forceinline__ int ft_index(int code) { return (code & 1) * (NSLOT / 2) + ((code & 511) >> 1); }
 
 struct TileSmem {
     float ftab[NSLOT * FT_STRIDE];
@@ -270,7 +277,7 @@ struct FwdOps {
 // triangle front-facing, which only happens for degenerate triangles).
 template <class Ops>
 __device__ __noinline__ void hit_inline(const Ops& ops, const Tri& f, int code, int face, int xi, int yi, int is) {
-    float rec[FT_STRIDE];
+    float rec[15];
     face_record(f, is, rec);
     ops.hit_direct(rec, code, face, xi, yi);
 }
@@ -566,6 +573,49 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
             maskA &= A.act ? vm : 0u;
             maskB &= B.act ? vm : 0u;
         }
+#if G2S_WARP_LOCAL
+        // Small quads never leave their warp: the hits go to the warp's PRIVATE slice of the hit queue (offsets from a
+        // warp scan, no shared-memory atomics), every lane builds the table entries of its own two triangles from the
+        // registers it already holds, and the warp drains its slice after a __syncwarp -- no CTA barrier between scan,
+        // table and drain, so the eight warps of a tile drift apart and overlap their phases (the CTA-wide form spent
+        // 23 % of its warp-cycles at barriers, profiles/r01_notes.md).
+        {
+            constexpr int WQ_CAP = HQ_CAP / (SPLAT_THREADS / 32);
+            uint32_t* wq_pix = sm.hq_pix + (tid >> 5) * WQ_CAP;
+            uint16_t* wq_code = sm.hq_code + (tid >> 5) * WQ_CAP;
+            int total;
+            int base = warp_excl_scan(__popc(maskA) + __popc(maskB), &total);
+            if (total) {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    unsigned m = k ? maskB : maskA;
+                    const int code = k ? codeB : codeA;
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int xi = u.x0 + (bit & (SB - 1)), yi = u.y0 + bit / SB;
+                        if (base < WQ_CAP) {
+                            wq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)xi;
+                            wq_code[base] = (uint16_t)code;
+                        } else {
+                            hit_inline(ops, k ? B.f : A.f, code, k ? faceB : faceA, xi, yi, is);
+                        }
+                        base++;
+                    }
+                }
+                if (maskA) face_record(A.f, is, &sm.ftab[ft_index(tid * 2) * FT_STRIDE]);
+                if (maskB) face_record(B.f, is, &sm.ftab[ft_index(tid * 2 + 1) * FT_STRIDE]);
+                __syncwarp();
+                const int nh = min(total, WQ_CAP);
+                for (int i = lane; i < nh; i += 32) {
+                    const int code = wq_code[i];
+                    const uint32_t pix = wq_pix[i];
+                    ops.hit(&sm.ftab[ft_index(code) * FT_STRIDE], code, code_face(code, Q, S, ty0, tx0), (int)(pix & 0xffffu),
+                            (int)(pix >> 16));
+                }
+            }
+        }
+#else
         // queue the hits: one atomic per warp
         int total;
         const int off = warp_excl_scan(__popc(maskA) + __popc(maskB), &total);
@@ -599,6 +649,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
             if (maskA) sm.fq[fbase++] = (uint16_t)codeA;
             if (maskB) sm.fq[fbase] = (uint16_t)codeB;
         }
+#endif
         // degenerate triangles whose two windings both pass the back-face test (rounding): the reversed copy
         // bypasses the queues and the face table, whose slot the first winding owns
         if (A.dup) scan_degenerate(ops, reversed(A.f), A.bb, (tid * 2) | (1 << 9), Q, S, ty0, tx0);
@@ -608,6 +659,9 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     // build the table entries of the faces that scored for the first time, drain.  One round for ordinary tiles;
     // tiles full of long wall faces take several.
     __syncthreads();
+#if G2S_WARP_LOCAL
+    if (sm.n_wq + sm.n_mq == 0) return;   // interior tiles: nothing but small quads
+#endif
     expand_queued_faces(sm, ops, recs, Q, S, ty0, tx0);
     const uint32_t* tq = sm.tq;
     int t0 = 0, nf_done = 0;
@@ -653,7 +707,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         const int nf = sm.n_fq;
         for (int i = nf_done + tid; i < nf; i += SPLAT_THREADS) {
             const int code = sm.fq[i];
-            face_record(code_tri(sm.sv, code), is, &sm.ftab[(code & 511) * FT_STRIDE]);
+            face_record(code_tri(sm.sv, code), is, &sm.ftab[ft_index(code) * FT_STRIDE]);
         }
         nf_done = nf;
         __syncthreads();
@@ -662,7 +716,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         for (int i = tid; i < nh; i += SPLAT_THREADS) {
             const int code = sm.hq_code[i];
             const uint32_t pix = sm.hq_pix[i];
-            ops.hit(&sm.ftab[(code & 511) * FT_STRIDE], code, code_face(code, Q, S, ty0, tx0), (int)(pix & 0xffffu),
+            ops.hit(&sm.ftab[ft_index(code) * FT_STRIDE], code, code_face(code, Q, S, ty0, tx0), (int)(pix & 0xffffu),
                     (int)(pix >> 16));
         }
         t0 = t1;
