@@ -193,11 +193,9 @@ def run_ours(args):
         for tns in (depth, albedo, view, light):
             tns.grad = None
         recon_im, recon_depth, fidx = ren.render_chain(depth, albedo, view, light, views_per_image=P)
-        loss = (recon_im * cot).sum()
-        loss.backward()
-        if world > 1:
-            dist.all_reduce(loss.detach(), op=dist.ReduceOp.SUM)   # the only exchange: the scalar loss
-        return loss
+        # the loss is a fixed device-resident cotangent on recon_im -- handed straight to the backward
+        # (no `(recon_im * cot).sum()` glue kernels in the timed region).  Whole images per rank: nothing to exchange.
+        torch.autograd.backward([recon_im], [cot])
 
     h_out = {"depth": torch.empty(N, S, S).pin_memory(), "albedo": torch.empty(N, 3, S, S).pin_memory(),
              "view": torch.empty(B, 6).pin_memory(), "light": torch.empty(B, 4).pin_memory(),
@@ -209,8 +207,8 @@ def run_ours(args):
         view = host["view"].to(dev, non_blocking=True).requires_grad_(True)
         light = host["light"].to(dev, non_blocking=True).requires_grad_(True)
         recon_im, recon_depth, fidx = ren.render_chain(depth, albedo, view, light, views_per_image=P)
-        loss = (recon_im * cot).sum()
-        loss.backward()
+        torch.autograd.backward([recon_im], [cot])
+        loss = light.grad.sum()      # a scalar that depends on every view's forward and backward (the step's "metric")
         h_out["depth"].copy_(depth.grad, non_blocking=True)
         h_out["albedo"].copy_(albedo.grad, non_blocking=True)
         h_out["view"].copy_(view.grad, non_blocking=True)
@@ -246,10 +244,11 @@ def run_ours(args):
     if sampler:
         sampler.start()
     launches0 = lib.g2s_launch_count()
-    lib.g2s_profile_enable(1)
-    ms_total = timed(step_device, args.steps)
-    lib.g2s_profile_enable(0)
+    ms_total = timed(step_device, args.steps)          # the reported number: no per-kernel events in the stream
     launches = lib.g2s_launch_count() - launches0
+    lib.g2s_profile_enable(1)                          # second pass, same steps, with a CUDA-event pair around every kernel
+    ms_profiled = timed(step_device, args.steps)
+    lib.g2s_profile_enable(0)
     clocks = sampler.stop() if sampler else None
 
     names = (ctypes.c_char_p * 32)()
@@ -331,7 +330,7 @@ def run_ours(args):
                 d1 = one["depth"].requires_grad_(True)
                 a1 = one["albedo"].requires_grad_(True)
                 im1 = ren.render_chain(d1, a1, one["view"], one["light"], views_per_image=P)[0]
-                torch.autograd.grad((im1 * one["cotangent"]).sum(), [d1, a1])
+                torch.autograd.grad([im1], [d1, a1], grad_outputs=[one["cotangent"]])
 
             for _ in range(5):
                 eager_one()
@@ -354,7 +353,7 @@ def run_ours(args):
                                   "brute-force face loop (%.1f s)" % (views, S, S, dt)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "ms_per_step_with_kernel_events": ms_profiled / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, N), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps},

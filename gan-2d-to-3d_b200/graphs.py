@@ -39,9 +39,9 @@ class GraphedRenderStep:
     def _run(self):
         im, rd, fidx = self.renderer.render_chain(self.depth, self.albedo, self.view, self.light,
                                                   views_per_image=self.P)
-        loss = (im * self.cotangent).sum()
-        grads = torch.autograd.grad(loss, [self.depth, self.albedo, self.view, self.light])
-        return im, rd, fidx, grads, loss
+        # the loss stands on the cotangent (d loss / d recon_im), handed straight to the backward
+        grads = torch.autograd.grad([im], [self.depth, self.albedo, self.view, self.light], grad_outputs=[self.cotangent])
+        return im, rd, fidx, grads
 
     def step(self, depth=None, albedo=None, view=None, light=None, cotangent=None):
         with torch.no_grad():
@@ -50,5 +50,4 @@ class GraphedRenderStep:
                 if src is not None:
                     dst.copy_(src, non_blocking=True)
         self.graph.replay()
-        im, rd, fidx, grads, loss = self.out
-        return im, rd, fidx, grads
+        return self.out
