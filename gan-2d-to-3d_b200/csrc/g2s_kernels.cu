@@ -274,24 +274,29 @@ template <bool FUSED>
 __global__ void __launch_bounds__(PBX * PBY)
 k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restrict__ recon_depth,
           int* __restrict__ face_idx, const FusedArgs fa) {
-    __shared__ float sview[17];   // R[9], t[3], light[5]
     const int S = cam.S, is = 2 * S, bl = blockIdx.z, b = fa.view0 + bl;
-    if (FUSED) {
-        const int k = threadIdx.y * PBX + threadIdx.x;
-        if (k < 9) sview[k] = fa.R[b * 9 + k];
-        else if (k < 12) sview[k] = fa.t[b * 3 + k - 9];
-        else if (k < 17) sview[k] = fa.light[b * 5 + k - 12];
-        __syncthreads();
-    }
     const int j = blockIdx.x * PBX + threadIdx.x, i = blockIdx.y * PBY + threadIdx.y;
-    if (j >= S || i >= S) return;
-    const int pix = i * S + j;
+    const bool inside = j < S && i < S;
     unsigned long long* zb = zbuf + (long)bl * is * is;
     ulonglong2* r0 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i) * is + 2 * j);
     ulonglong2* r1 = reinterpret_cast<ulonglong2*>(zb + (long)(2 * i + 1) * is + 2 * j);
     // z-buffer traffic stays in L2 (.cg); the outputs are written once and not re-read by this pass: streaming
-    // stores (.cs, evict-first) keep them from pushing the z-buffer chunk out of L2
-    const ulonglong2 k0 = __ldcg(r0), k1 = __ldcg(r1);
+    // stores (.cs, evict-first) keep them from pushing the z-buffer chunk out of L2.  The key loads are issued BEFORE
+    // anything waits on them, together with the view's R, t, light: one round trip where there were three (profiles/r01_notes.md).
+    ulonglong2 k0 = make_ulonglong2(0ull, 0ull), k1 = k0;
+    if (inside) { k0 = __ldcg(r0); k1 = __ldcg(r1); }
+    // R, t, light of the view: warp-uniform loads (one L1 transaction per warp, broadcast), no shared memory and no barrier
+    float sview[17];
+    if (FUSED) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) sview[k] = __ldg(&fa.R[b * 9 + k]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) sview[9 + k] = __ldg(&fa.t[b * 3 + k]);
+#pragma unroll
+        for (int k = 0; k < 5; k++) sview[12 + k] = __ldg(&fa.light[b * 5 + k]);
+    }
+    if (!inside) return;
+    const int pix = i * S + j;
     const unsigned long long empty = zkey_empty(cam.far);
     __stcg(r0, make_ulonglong2(empty, empty));
     __stcg(r1, make_ulonglong2(empty, empty));
@@ -843,6 +848,16 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
                    float* __restrict__ grad_t) {
     __shared__ float sview[17];
     const int S = cam.S, bl = blockIdx.z, b = fa.view0 + bl;
+    const int j = blockIdx.x * BPX + threadIdx.x, i = blockIdx.y * BPY + threadIdx.y;
+    const bool inside = j < S && i < S;
+    const int pix = i * S + j;
+    // per-pixel inputs are requested before the barrier that publishes R, t, light: one round trip instead of two
+    float rd = 0.f, G[3] = {0.f, 0.f, 0.f};
+    if (inside) {
+        rd = recon_depth[(long)b * S * S + pix];
+#pragma unroll
+        for (int c = 0; c < 3; c++) G[c] = __ldcs(&grad_recon_im[((long)b * 3 + c) * S * S + pix]);
+    }
     {
         const int k = threadIdx.y * BPX + threadIdx.x;
         if (k < 9) sview[k] = fa.R[b * 9 + k];
@@ -850,17 +865,12 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
         else if (k < 17) sview[k] = fa.light[b * 5 + k - 12];
         __syncthreads();
     }
-    const int j = blockIdx.x * BPX + threadIdx.x, i = blockIdx.y * BPY + threadIdx.y;
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
-    if (j < S && i < S) {
-        const int pix = i * S + j, img = b / fa.vpi;
+    if (inside) {
+        const int img = b / fa.vpi;
         float ray[3], q[3], v[3], g[2];
-        const float rd = recon_depth[(long)b * S * S + pix];
-        float G[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) G[c] = grad_recon_im[((long)b * 3 + c) * S * S + pix];
         pixel_ray(cam, j, i, ray);
         inv_warp_point(cam, sview, sview + 9, ray, rd, q, v);
         point_to_grid(cam, q, S, S, g);

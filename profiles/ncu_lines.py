@@ -24,6 +24,10 @@ def main():
             hdr = r
         elif hdr and r[0].isdigit():
             d = dict(zip(hdr, r))
+            try:
+                float(d["Instructions Executed"] or 0), float(d["# Samples"] or 0), float(d["Thread Instructions Executed"] or 0)
+            except ValueError:      # a source line with embedded quotes (inline asm) that the CSV export mangles
+                continue
             lines.append((fname, int(r[0]), r[1].strip(), float(d["Instructions Executed"] or 0), float(d["# Samples"] or 0),
                           float(d["Thread Instructions Executed"] or 0)))
     ti = sum(l[3] for l in lines) or 1
