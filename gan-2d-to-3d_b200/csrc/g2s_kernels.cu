@@ -81,31 +81,51 @@ struct Launch {
 
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? G2S_OK : G2S_ERR_LAUNCH; }
 
-__device__ __forceinline__ float warp_sum(float v) {
+
+// Warp sums of 2^LOG per-lane values by RECURSIVE HALVING: at every step a lane hands one half of its values to its
+// partner and keeps the other, so 2^LOG values cost 2^LOG - 1 + (5 - LOG) shuffles instead of 5 * 2^LOG butterflies
+// (16 instead of 80 for the 12 entries of grad_R | grad_t; the butterflies were 25 % of k_render_bwd_pixel's
+// instructions, profiles/r01_notes.md).  Afterwards every lane holds the warp total of value number halving_index().
+template <int LOG>
+__device__ __forceinline__ int halving_index(int lane) { return (lane >> (5 - LOG)) & ((1 << LOG) - 1); }
+template <int LOG>
+__device__ __forceinline__ float warp_reduce_halving(float (&v)[1 << LOG], int lane) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int s = 0; s < LOG; s++) {
+        const int h = (1 << LOG) >> (s + 1), bit = 16 >> s;
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int k = 0; k < h; k++) {
+            const float send = up ? v[k] : v[k + h], keep = up ? v[k + h] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int bit = 16 >> LOG; bit > 0; bit >>= 1) r += __shfl_xor_sync(0xffffffffu, r, bit);
+    return r;
 }
 
-// Sum v[0..N) over the block and atomically add the totals to dst[0..N).  All threads must call.
-template <int N, int THREADS>
-__device__ __forceinline__ void block_accumulate(float (&v)[N], float* dst) {
-    __shared__ float red[N * (THREADS / 32)];
+// Sum the per-thread grad_R (9) | grad_t (3) contributions over the block and atomically add the totals to the view's
+// grad_R / grad_t.  All threads must call.
+template <int THREADS>
+__device__ __forceinline__ void block_accumulate_Rt(const float (&acc)[12], float* grad_R, float* grad_t) {
+    __shared__ float red[(THREADS / 32) * 12];
     const int lin = threadIdx.y * blockDim.x + threadIdx.x;
     const int lane = lin & 31, warp = lin >> 5;
+    float v[16];
 #pragma unroll
-    for (int k = 0; k < N; k++) {
-        const float s = warp_sum(v[k]);
-        if (lane == 0) red[warp * N + k] = s;
-    }
+    for (int k = 0; k < 16; k++) v[k] = k < 12 ? acc[k] : 0.f;
+    const float s = warp_reduce_halving<4>(v, lane);
+    const int idx = halving_index<4>(lane);
+    if ((lane & 1) == 0 && idx < 12) red[warp * 12 + idx] = s;
     __syncthreads();
-    if (lin < N) {
-        float s = 0.f;
+    if (lin < 12) {
+        float tot = 0.f;
 #pragma unroll
-        for (int w = 0; w < THREADS / 32; w++) s += red[w * N + lin];
-        if (s != 0.f) atomicAdd(&dst[lin], s);
+        for (int w = 0; w < THREADS / 32; w++) tot += red[w * 12 + lin];
+        if (tot != 0.f) atomicAdd(lin < 9 ? &grad_R[lin] : &grad_t[lin - 9], tot);
     }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -413,13 +433,7 @@ k_warp_grid_bwd(const Cam cam, const float* __restrict__ depth, long dstride, co
             warp_grid_bwd_pixel(cam, Rm, tv, x, y, W, H, depth[(long)b * dstride + pix], inverse, G.x, G.y, acc);
     }
     if (grad_R) {
-        float accR[9], acct[3];
-#pragma unroll
-        for (int k = 0; k < 9; k++) accR[k] = acc[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
-        block_accumulate<9, PIX_THREADS>(accR, grad_R + b * 9);
-        block_accumulate<3, PIX_THREADS>(acct, grad_t + b * 3);
+        block_accumulate_Rt<PIX_THREADS>(acc, grad_R + b * 9, grad_t + b * 3);
     }
 }
 
@@ -826,13 +840,7 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
         }
     }
     if (grad_R) {
-        float accR[9], acct[3];
-#pragma unroll
-        for (int k = 0; k < 9; k++) accR[k] = acc[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
-        block_accumulate<9, PIX_THREADS>(accR, grad_R + b * 9);
-        block_accumulate<3, PIX_THREADS>(acct, grad_t + b * 3);
+        block_accumulate_Rt<PIX_THREADS>(acc, grad_R + b * 9, grad_t + b * 3);
     }
 }
 
@@ -878,32 +886,31 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
         float tex[4][3];
         shade_taps(fa.normal + (long)img * S * S * TEXEL, tp, sview + 12, tex);
         float gix = 0.f, giy = 0.f;
-        float* gt_b = grad_tex + (long)bl * 3 * S * S;
+        // per-view texture gradient, packed rgb- per texel: one 16-byte vector reduction per tap instead of three scalar ones
+        float4* gt_b = reinterpret_cast<float4*>(grad_tex) + (long)bl * S * S;
+        float Gc[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float o = tp.w[0] * tex[0][c] + tp.w[1] * tex[1][c] + tp.w[2] * tex[2][c] + tp.w[3] * tex[3][c];
             // clamp(-1,1) passes the gradient where -1 <= x <= 1
-            const float Gc = (o >= -1.f && o <= 1.f) ? G[c] : 0.f;
-            if (Gc == 0.f) continue;
+            Gc[c] = (o >= -1.f && o <= 1.f) ? G[c] : 0.f;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (tp.w[k] != 0.f) atomicAdd(&gt_b[c * S * S + tp.p[k]], tp.w[k] * Gc);
-                gix += ((k & 1) ? 1.f : -1.f) * tp.wy[k] * tex[k][c] * Gc;
-                giy += ((k >> 1) ? 1.f : -1.f) * tp.wx[k] * tex[k][c] * Gc;
+                gix += ((k & 1) ? 1.f : -1.f) * tp.wy[k] * tex[k][c] * Gc[c];
+                giy += ((k >> 1) ? 1.f : -1.f) * tp.wx[k] * tex[k][c] * Gc[c];
             }
+        }
+        if (Gc[0] != 0.f || Gc[1] != 0.f || Gc[2] != 0.f) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (tp.w[k] != 0.f) atomicAdd(&gt_b[tp.p[k]], make_float4(tp.w[k] * Gc[0], tp.w[k] * Gc[1], tp.w[k] * Gc[2], 0.f));
         }
         const float mult = fa.align ? (float)(S - 1) * 0.5f : (float)S * 0.5f;
         float gd = warp_grid_bwd_pixel(cam, sview, sview + 9, j, i, S, S, rd, 1, gix * mult, giy * mult, acc);
         if (grad_recon_depth) gd += grad_recon_depth[(long)b * S * S + pix];
         g_sub[(long)bl * S * S + pix] = (rd > cam.clamp_lo && rd < cam.clamp_hi) ? 0.25f * gd : 0.f;
     }
-    float accR[9], acct[3];
-#pragma unroll
-    for (int k = 0; k < 9; k++) accR[k] = acc[k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) acct[k] = acc[9 + k];
-    block_accumulate<9, BPX * BPY>(accR, grad_R + b * 9);
-    block_accumulate<3, BPX * BPY>(acct, grad_t + b * 3);
+    block_accumulate_Rt<BPX * BPY>(acc, grad_R + b * 9, grad_t + b * 3);
 }
 
 // fused render backward, texture stage: per image pixel, loop over the image's views that fall in this
@@ -927,8 +934,8 @@ k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict_
                     dy = __ldg(&fa.light[b * 5 + 3]), dz = __ldg(&fa.light[b * 5 + 4]);
         float T[3] = {0.f, 0.f, 0.f};
         if (live) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) T[c] = grad_tex[((long)(b - fa.view0) * 3 + c) * S * S + p];
+            const float4 t4 = __ldcs(reinterpret_cast<const float4*>(grad_tex) + (long)(b - fa.view0) * S * S + p);
+            T[0] = t4.x; T[1] = t4.y; T[2] = t4.z;
         }
         const float ndl = n0 * dx + n1 * dy + n2 * dz;
         const float diff = fmaxf(ndl, 0.f);
@@ -942,12 +949,10 @@ k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict_
         }
         const float ddiff = ndl >= 0.f ? dsh * lb : 0.f;
         gn[0] += ddiff * dx; gn[1] += ddiff * dy; gn[2] += ddiff * dz;
-        float lg[5] = {dsh, dsh * diff, ddiff * n0, ddiff * n1, ddiff * n2};
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            lg[k] = warp_sum(lg[k]);
-            if ((threadIdx.x & 31) == 0 && lg[k] != 0.f) atomicAdd(&grad_light[b * 5 + k], lg[k]);
-        }
+        float lg[8] = {dsh, dsh * diff, ddiff * n0, ddiff * n1, ddiff * n2, 0.f, 0.f, 0.f};
+        const int lane = threadIdx.x & 31, li = halving_index<3>(lane);
+        const float ls = warp_reduce_halving<3>(lg, lane);
+        if ((lane & 3) == 0 && li < 5 && ls != 0.f) atomicAdd(&grad_light[b * 5 + li], ls);
     }
     if (live) {
 #pragma unroll
@@ -1350,7 +1355,7 @@ int g2s_chunk_views_bwd(int image_size) {
         const long v = atol(e) * 128L * 128L / ((long)image_size * image_size);
         if (v >= 1) return (int)v;
     }
-    const long per_view = 10L * image_size * image_size * 4;   // 7 S^2 (raster scratch) + 3 S^2 (texture gradient)
+    const long per_view = 11L * image_size * image_size * 4;   // 7 S^2 (raster scratch) + 4 S^2 (packed texture gradient)
     long v = (1L << 30) / per_view;
     return (int)(v < 1 ? 1 : v);
 }
@@ -1424,7 +1429,7 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
     const int chunk = ws_views < 32768 ? ws_views : 32768;
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
-        cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * nv * 3 * img_f, st);
+        cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * nv * 4 * img_f, st);
         FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
         { Launch l_(K_BWD_PIXEL, st);
           k_render_bwd_pixel<<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,

@@ -349,7 +349,7 @@ class RenderChainFn(torch.autograd.Function):
         gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
         ws_views = min(B, lib.g2s_chunk_views_bwd(S))
         ws_sub = torch.empty(ws_views, 7, S, S, device=dev, dtype=torch.float32)   # g_sub | projected verts | vertex grads
-        ws_tex = torch.empty(ws_views, 3, S, S, device=dev, dtype=torch.float32)
+        ws_tex = torch.empty(ws_views, S, S, 4, device=dev, dtype=torch.float32)
         ws_nrm = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
         g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)
         g_albedo = torch.empty(N, 3, S, S, device=dev, dtype=torch.float32)

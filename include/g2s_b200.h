@@ -130,7 +130,7 @@ int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float 
 
 /* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
  * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,7,S,S] (as above),
- * grad_tex_ws [ws_views,3,S,S] (chunked like the forward), grad_normal_ws [n_images,S,S,8] (packed texels: normal xyz,
+ * grad_tex_ws [ws_views,S,S,4] (per-view texture gradient, packed rgb-; 16-byte aligned; chunked like the forward), grad_normal_ws [n_images,S,S,8] (packed texels: normal xyz,
  * albedo rgb, 2 pad; kept for the backward).
  * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
  * grad_t [n_views,3], grad_light [n_views,5]. */
