@@ -81,6 +81,17 @@ struct Launch {
 
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? G2S_OK : G2S_ERR_LAUNCH; }
 
+// one internal non-blocking stream per device for the two-lane chunk pipeline of g2s_render_fused_fwd
+inline cudaStream_t aux_stream() {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+    return streams[dev];
+}
+
 
 // Warp sums of 2^LOG per-lane values by RECURSIVE HALVING: at every step a lane hands one half of its values to its
 // partner and keeps the other, so 2^LOG values cost 2^LOG - 1 + (5 - LOG) shuffles instead of 5 * 2^LOG butterflies
@@ -1192,11 +1203,11 @@ inline dim3 pix_grid2(int S, int views, int bx = PBX, int by = PBY) { return dim
 // views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
 // scratch 16 S^2 B/view) stays resident in the 126 MB L2 between the kernel that writes it and the one that reads it
 inline int chunk_views_for(int S, int cap) {
-    // 32 MB of z-buffer per chunk, but never fewer than 64 views: below that the launches are too short and the
-    // tail of the rasteriser (a few heavy wall tiles) costs more than the L2 misses of a larger z-buffer (measured
-    // at 128^2 and 256^2, profiles/)
-    long v = (32L << 20) / (32L * S * S);
-    if (v < 64) v = 64;
+    // 24 MB of z-buffer per chunk (two chunks are in flight in the two-lane forward), but never fewer than 48 views: below
+    // that the launches are too short and the tail of the rasteriser (a few heavy wall tiles) costs more than the L2
+    // misses of a larger z-buffer (measured at 128^2 and 256^2, profiles/r01_notes.md)
+    long v = (24L << 20) / (32L * S * S);
+    if (v < 48) v = 48;
     if (v > cap) v = cap;
     return (int)v;
 }
@@ -1390,15 +1401,41 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
         k_pack_albedo<<<pix_grid((long)S * S, ni), PIX_THREADS, 0, st>>>(albedo + (long)i0 * 3 * S * S, S * S,
                                                                          normal_ws + (long)i0 * S * S * TEXEL);
     }
-    const int chunk = ws_views < 32768 ? ws_views : 32768;
-    for (long v0 = 0; v0 < n_views; v0 += chunk) {
+    // Chunked so that the z-buffer a k_splat launch writes is still in L2 when k_resolve reads it.  When the workspace
+    // holds two recommended chunks the chunks alternate between its halves on two streams (the caller's and an internal
+    // one, forked and joined with events): the next chunk's k_splat fills the SMs that the tail of the current one leaves
+    // idle (a 64-view launch lost ~8 % to its tail, profiles/r01_notes.md).  Not while per-kernel timing is on.
+    const int rec = g2s_chunk_views(S);
+    const bool two = ws_views >= 2 * rec && n_views > rec && !g_prof_on && !getenv("G2S_NO_PIPELINE");
+    const int one = ws_views >= 2 * rec ? rec : ws_views;     // single lane: one recommended chunk at a time
+    const int chunk = two ? (ws_views / 2 < 32768 ? ws_views / 2 : 32768) : (one < 32768 ? one : 32768);
+    cudaStream_t lanes[2] = {st, st};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (two) {
+        lanes[1] = aux_stream();
+        if (!lanes[1] || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+            return G2S_ERR_LAUNCH;
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(lanes[1], ev_fork, 0);
+    }
+    int lane = 0;
+    for (long v0 = 0; v0 < n_views; v0 += chunk, lane ^= (two ? 1 : 0)) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
-        { Launch l_(K_SPLAT, st);
-          k_splat<false><<<dim3(nv, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
-                                                                           (unsigned long long*)zbuf, tiles, (int)v0); }
+        cudaStream_t ls = lanes[lane];
+        unsigned long long* zb = (unsigned long long*)zbuf + (two && lane ? (size_t)chunk * 4 * S * S : 0);
+        { Launch l_(K_SPLAT, ls);
+          k_splat<false><<<dim3(nv, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), ls>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
+                                                                           zb, tiles, (int)v0); }
         FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0, mask_in, mask_out};
-        { Launch l_(K_RESOLVE_FUSED, st);
-          k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, recon_depth, face_idx, fa); }
+        { Launch l_(K_RESOLVE_FUSED, ls);
+          k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, ls>>>(c, zb, recon_depth, face_idx, fa); }
+    }
+    if (two) {
+        cudaEventRecord(ev_join, lanes[1]);
+        cudaStreamWaitEvent(st, ev_join, 0);
+        cudaEventDestroy(ev_fork);     // released by the runtime once they have completed
+        cudaEventDestroy(ev_join);
     }
     return launch_status();
 }

@@ -315,7 +315,7 @@ class RenderChainFn(torch.autograd.Function):
         L = _f32c(light)
         cam = renderer._camera(depth_pass=True)
         dev = d.device
-        ws_views = min(B, lib.g2s_chunk_views(S))
+        ws_views = min(B, 2 * lib.g2s_chunk_views(S))      # two chunks: the forward alternates between the halves
         zbuf = renderer._zbuf.get(ws_views, S, cam.far_z, dev)
         normal = torch.empty(N, S, S, 8, device=dev, dtype=torch.float32)    # packed texels: normal xyz, albedo rgb, pad
         recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
