@@ -764,7 +764,7 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         for (int m = 0; m < 3; m++) {
             nd[m][0] = __ldg(&pv[vidx[m] * 3]); nd[m][1] = __ldg(&pv[vidx[m] * 3 + 1]); nd[m][2] = __ldg(&pv[vidx[m] * 3 + 2]);
         }
-        float rec[15];
+        float rec[16];
         face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
         float A[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -786,11 +786,10 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         for (int m = 0; m < 3; m++) {
             qd[m] = div_core(rec[3 * m], z[m], rec[12 + m]);
             qd[3 + m] = div_core(rec[3 * m + 1], z[m], rec[12 + m]);
-            bad = max(bad, range_key(z[m]));
             bad = max(bad, rec[3 * m] == 0.0f ? 0u : range_key(rec[3 * m]));
             bad = max(bad, rec[3 * m + 1] == 0.0f ? 0u : range_key(rec[3 * m + 1]));
         }
-        if (bad >= RANGE_SPAN) {
+        if (bad >= RANGE_SPAN || rec[15] != 0.0f) {
 #pragma unroll
             for (int m = 0; m < 3; m++) { qd[m] = __fdiv_rn(rec[3 * m], z[m]); qd[3 + m] = __fdiv_rn(rec[3 * m + 1], z[m]); }
         }

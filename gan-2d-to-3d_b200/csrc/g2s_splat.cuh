@@ -147,6 +147,8 @@ __device__ __forceinline__ void face_record(const Tri& f, int is, float* rec) {
     }
     rec[9] = f.z0; rec[10] = f.z1; rec[11] = f.z2;
     rec[12] = rcp_seed(f.z0); rec[13] = rcp_seed(f.z1); rec[14] = rcp_seed(f.z2);
+    // the operand-range verdict on the three z's is taken once per face, not once per hit
+    rec[15] = max(max(range_key(f.z0), range_key(f.z1)), range_key(f.z2)) >= RANGE_SPAN ? 1.0f : 0.0f;
 }
 
 // Per-hit evaluation from a face record: [nr] kernel 2 after the inside test (clamped, renormalised weights and
@@ -164,7 +166,12 @@ __device__ __forceinline__ bool record_weights_depth(const float* rec, int xi, i
     const float w_sum = add(add(add(0.0f, wc[0]), wc[1]), wc[2]);
     const float ys = rcp_seed(w_sum);
     float t[3];
-    unsigned bad = range_key(w_sum);
+    // Operand ranges of the seven residual-corrected divisions, checked with the structure of the values instead of one
+    // generic test per operand (those tests were a third of the per-hit instructions):
+    //   wc[k] in [0,1]: only 0 < wc < 2^-38 is out -- as unsigned integers, bits(wc) - 1 wraps 0 to the top;
+    //   w_sum in [max wc, 3]: in range as soon as one wc is, 0 when all are (-> IEEE path, 0/0);
+    //   w[k] = wc[k] / w_sum in {0} U [2^-40, 1] follows;  z[k]: the per-face verdict rec[15];  s: checked below.
+    unsigned lo = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         float q = __fmul_rn(wc[k], ys);
@@ -178,12 +185,9 @@ __device__ __forceinline__ bool record_weights_depth(const float* rec, int xi, i
         q = __fmaf_rn(r, yz, q);
         r = __fmaf_rn(-z, q, w[k]);
         t[k] = __fmaf_rn(r, yz, q);
-        bad = max(bad, range_key(z));
-        bad = max(bad, wc[k] == 0.0f ? 0u : range_key(wc[k]));
-        bad = max(bad, w[k] == 0.0f ? 0u : range_key(w[k]));
+        lo = min(lo, __float_as_uint(wc[k]) - 1u);
     }
     const float s = add(add(t[0], t[1]), t[2]);
-    bad = max(bad, range_key(s));
     float zp;
     {
         const float y = rcp_seed(s);
@@ -193,7 +197,8 @@ __device__ __forceinline__ bool record_weights_depth(const float* rec, int xi, i
         r = __fmaf_rn(-s, q, 1.0f);
         zp = __fmaf_rn(r, y, q);
     }
-    if (bad >= RANGE_SPAN) {   // some operand outside [2^-40, 2^40): IEEE path
+    const bool fast = lo >= 0x2C800000u - 1u && w_sum > 0.0f && rec[15] == 0.0f && range_key(s) < RANGE_SPAN;
+    if (!fast) {   // some operand outside its range: IEEE path
         Tri f;
         f.z0 = rec[9]; f.z1 = rec[10]; f.z2 = rec[11];
         float fi[9];
@@ -277,7 +282,7 @@ struct FwdOps {
 // triangle front-facing, which only happens for degenerate triangles).
 template <class Ops>
 __device__ __noinline__ void hit_inline(const Ops& ops, const Tri& f, int code, int face, int xi, int yi, int is) {
-    float rec[15];
+    float rec[16];
     face_record(f, is, rec);
     ops.hit_direct(rec, code, face, xi, yi);
 }
