@@ -1197,6 +1197,56 @@ __global__ void k_selftest_division(unsigned long long per_thread, unsigned seed
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// compares the rasteriser's fast per-face / per-hit arithmetic (face_record + record_weights_depth: shared reciprocals,
+// structural operand-range guards) with the plain IEEE formulation (tri_face_inv + tri_weights_depth) bit for bit on
+// pseudo-random triangles whose coordinates and depths span ordinary AND extreme magnitudes (so that the guards and
+// their IEEE fall-backs are exercised): mismatching (accept, w[3], zp) results are counted
+__global__ void k_selftest_raster(unsigned long long per_thread, unsigned seed, int is, unsigned long long* mismatches) {
+    unsigned long long x = (unsigned long long)seed * 0x9E3779B97F4A7C15ull +
+                           ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1) * 0xD6E8FEB86659FD93ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (unsigned)(x >> 20); };
+    auto unit = [&]() { return (float)(rnd() & 0xffffffu) * (1.0f / 16777216.0f); };   // [0,1)
+    unsigned long long bad = 0;
+    for (unsigned long long it = 0; it < per_thread; it++) {
+        // a small triangle somewhere on (or a little off) the screen, in NDC; every 8th one degenerate / extreme
+        const unsigned kind = rnd() & 7u;
+        const float cx = unit() * 2.2f - 1.1f, cy = unit() * 2.2f - 1.1f;
+        const float ext = kind == 1 ? 1e-6f : (kind == 2 ? 0.5f : 6.0f / (float)is);
+        float vx[3], vy[3], vz[3];
+        for (int k = 0; k < 3; k++) {
+            vx[k] = cx + (unit() - 0.5f) * ext;
+            vy[k] = cy + (unit() - 0.5f) * ext;
+            vz[k] = 0.8f + 0.4f * unit();
+        }
+        if (kind == 3) { vx[2] = vx[1]; vy[2] = vy[1]; }                       // zero area
+        if (kind == 4) vz[rnd() % 3] = __uint_as_float((rnd() % 254u + 1u) << 23);   // any power of two as a depth
+        if (kind == 5) { const float sc = __uint_as_float((127u - 60u + rnd() % 120u) << 23); for (int k = 0; k < 3; k++) vz[k] *= sc; }
+        if (kind == 6) vz[rnd() % 3] *= -1.0f;
+        const float a0[3] = {vx[0], vy[0], vz[0]}, a1[3] = {vx[1], vy[1], vz[1]}, a2[3] = {vx[2], vy[2], vz[2]};
+        const Tri f = make_tri(a0, a1, a2);
+        float rec[16], fi[9];
+        face_record(f, is, rec);
+        tri_face_inv(f, is, fi);
+        for (int k = 0; k < 9; k++) bad += __float_as_uint(rec[k]) != __float_as_uint(fi[k]);
+        // sub-pixels around the triangle (inside and outside: the clamps and the all-zero case)
+        const int px = (int)floorf(ndc_to_pix(cx, is)), py = (int)floorf(ndc_to_pix(cy, is));
+        for (int s2 = 0; s2 < 4; s2++) {
+            const int xi = px + (int)(rnd() % 7u) - 3, yi = py + (int)(rnd() % 7u) - 3;
+            float w0[3] = {0.f, 0.f, 0.f}, w1[3] = {0.f, 0.f, 0.f}, z0 = 0.f, z1 = 0.f;
+            const float nr = kind == 5 ? 0.0f : 0.1f, fr = kind == 5 ? 3.0e38f : 100.0f;
+            const bool ok0 = record_weights_depth(rec, xi, yi, nr, fr, w0, &z0);
+            const bool ok1 = tri_weights_depth(f, fi, xi, yi, nr, fr, w1, &z1);
+            bool same = ok0 == ok1;
+            if (ok0 && ok1) {
+                same = __float_as_uint(z0) == __float_as_uint(z1);
+                for (int k = 0; k < 3; k++) same = same && __float_as_uint(w0[k]) == __float_as_uint(w1[k]);
+            }
+            bad += same ? 0 : 1;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 inline dim3 pix_grid2(int S, int views, int bx = PBX, int by = PBY) { return dim3((S + bx - 1) / bx, (S + by - 1) / by, views); }
 
 // views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
@@ -1569,6 +1619,16 @@ int g2s_selftest_division(unsigned long long n_pairs, unsigned seed, unsigned lo
     const int blocks = 148 * 8, threads = 256;
     const unsigned long long per = (n_pairs + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
     k_selftest_division<<<blocks, threads, 0, (cudaStream_t)stream>>>(per, seed, mismatches_dev);
+    return launch_status();
+}
+
+int g2s_selftest_raster(unsigned long long n_triangles, unsigned seed, int image_size, unsigned long long* mismatches_dev,
+                        void* stream) {
+    if (!mismatches_dev) return G2S_ERR_NULL;
+    if (bad_size(image_size)) return G2S_ERR_SHAPE;
+    const int blocks = 148 * 4, threads = 128;
+    const unsigned long long per = (n_triangles + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
+    k_selftest_raster<<<blocks, threads, 0, (cudaStream_t)stream>>>(per, seed, 2 * image_size, mismatches_dev);
     return launch_status();
 }
 

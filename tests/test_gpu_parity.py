@@ -447,6 +447,19 @@ def test_shared_reciprocal_division_is_ieee_exact():
     assert int(bad.item()) == 0
 
 
+def test_raster_fast_path_equals_ieee_path():
+    """the per-face / per-hit fast arithmetic (shared reciprocals, structural operand-range guards) must equal the plain
+    IEEE formulation bit for bit, including on degenerate and extreme-magnitude triangles that take the fall-backs"""
+    import ctypes
+    from g2s_b200 import _lib
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed, S in ((1, 128), (2, 256), (3, 33)):
+        _lib.check(lib.g2s_selftest_raster(1 << 26, seed, S, ctypes.c_void_p(bad.data_ptr()), None), "selftest_raster")
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
 def test_cuda_graph_step_matches_eager():
     """forward + backward captured once into a CUDA graph (small, launch-bound batches) == eager"""
     import g2s_b200
