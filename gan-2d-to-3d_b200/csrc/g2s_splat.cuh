@@ -516,6 +516,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     const int qy = tid / TILE, qx = tid % TILE;
     const bool quad_ok = ty0 + qy < S - 1 && tx0 + qx < S - 1;
     float* recs = sm.recs;
+    int tile_queues = 1;
     // ---- quads whose two triangles fit one SB x SB box: scanned by the owning thread with uniform control flow
     {
         TriClass A = classify(sm.sv, qy, qx, 0, is, quad_ok), B = classify(sm.sv, qy, qx, 1, is, quad_ok);
@@ -529,6 +530,12 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         const int uw = u.x1 - u.x0 + 1, uh = u.y1 - u.y0 + 1;
         const bool any_act = A.act || B.act;
         const bool small = any_act && uw <= SB && uh <= SB;
+#if G2S_WARP_LOCAL
+        // Does the tile queue anything at all?  Asked HERE, where the eight warps are still in lockstep (the barrier is
+        // nearly free), not after the warp-local phases, where they have drifted apart: tiles of small quads only (the
+        // interior) then finish warp by warp without another barrier.
+        tile_queues = __syncthreads_or(any_act && !small);
+#endif
         if (any_act && !small) {
             // everything else becomes ROW TASKS: (face, row, 8-column segment), one lane each in the next phase
             if (A.act) push_row_tasks(sm, ops, recs, A, codeA, faceA, is);
@@ -663,10 +670,10 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     // ---- rounds: scan as many queued row tasks as are guaranteed to fit the hit queue (8 hits per task at most),
     // build the table entries of the faces that scored for the first time, drain.  One round for ordinary tiles;
     // tiles full of long wall faces take several.
-    __syncthreads();
 #if G2S_WARP_LOCAL
-    if (sm.n_wq + sm.n_mq == 0) return;   // interior tiles: nothing but small quads
+    if (!tile_queues) return;   // interior tiles: nothing but small quads, no barrier
 #endif
+    __syncthreads();
     expand_queued_faces(sm, ops, recs, Q, S, ty0, tx0);
     const uint32_t* tq = sm.tq;
     int t0 = 0, nf_done = 0;
