@@ -784,12 +784,13 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         unsigned bad = 0;
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-            qd[m] = div_core(rec[3 * m], z[m], rec[12 + m]);
-            qd[3 + m] = div_core(rec[3 * m + 1], z[m], rec[12 + m]);
+            const float yz = G2S_FT_SEEDS ? rec[12 + m] : rcp_seed(z[m]);
+            qd[m] = div_core(rec[3 * m], z[m], yz);
+            qd[3 + m] = div_core(rec[3 * m + 1], z[m], yz);
             bad = max(bad, rec[3 * m] == 0.0f ? 0u : range_key(rec[3 * m]));
             bad = max(bad, rec[3 * m + 1] == 0.0f ? 0u : range_key(rec[3 * m + 1]));
         }
-        if (bad >= RANGE_SPAN || rec[15] != 0.0f) {
+        if (bad >= RANGE_SPAN || rec[FT_FLAG] != 0.0f) {
 #pragma unroll
             for (int m = 0; m < 3; m++) { qd[m] = __fdiv_rn(rec[3 * m], z[m]); qd[3 + m] = __fdiv_rn(rec[3 * m + 1], z[m]); }
         }
@@ -1631,6 +1632,12 @@ int g2s_selftest_raster(unsigned long long n_triangles, unsigned seed, int image
     k_selftest_raster<<<blocks, threads, 0, (cudaStream_t)stream>>>(per, seed, 2 * image_size, mismatches_dev);
     return launch_status();
 }
+
+#ifdef G2S_COUNT_SLOW
+int g2s_debug_slow_counters(unsigned long long* out2) {
+    return cudaMemcpyFromSymbol(out2, g2s::g_slow_counters, 16) == cudaSuccess ? G2S_OK : G2S_ERR_LAUNCH;
+}
+#endif
 
 long g2s_launch_count(void) { return g_launches.load(); }
 

@@ -22,13 +22,28 @@
 
 namespace g2s {
 
+#ifdef G2S_COUNT_SLOW     // experiment builds only: how often the queue-overflow slow paths run
+__device__ unsigned long long g_slow_counters[2];
+#endif
+
 #ifndef G2S_WARP_LOCAL
 #define G2S_WARP_LOCAL 1
 #endif
-constexpr int HQ_CAP = 16 * SPLAT_THREADS;                 // hit-queue entries per drain
+#ifndef G2S_HQ_PER_THREAD
+#define G2S_HQ_PER_THREAD 16
+#endif
+#ifndef G2S_TQ_CAP
+#define G2S_TQ_CAP 8192     // 256^2 wall tiles queue up to ~4300 row tasks; overflow falls to a slow inline scan
+#endif
+#ifndef G2S_FT_SEEDS
+#define G2S_FT_SEEDS 0      // 1: the face table also holds the reciprocal seeds of the three z's; 0: recomputed per hit
+                            // (same speed, 8 KB less shared memory: spent on the task queue)
+#endif
+constexpr int HQ_CAP = G2S_HQ_PER_THREAD * SPLAT_THREADS;  // hit-queue entries per drain
 constexpr int NSLOT = 2 * TILE * TILE_H;       // (quad, triangle) slots of the face table
-constexpr int TQ_CAP = 4096;                  // queued row tasks per tile
-constexpr int FT_STRIDE = 17;                // fi[9], z[3], rcp_seed(z)[3], pad; ODD so that lanes on consecutive table
+constexpr int TQ_CAP = G2S_TQ_CAP;            // queued row tasks per tile
+constexpr int FT_FLAG = G2S_FT_SEEDS ? 15 : 12;   // index of the per-face z-range verdict
+constexpr int FT_STRIDE = G2S_FT_SEEDS ? 17 : 13;                // fi[9], z[3], rcp_seed(z)[3], pad; ODD so that lanes on consecutive table
                                              // entries hit distinct shared-memory banks (stride 16 was a 16/32-way conflict)
 // table entry of a (quad, triangle) code: triangle-major, so that the threads of a warp (consecutive quads) own
 // consecutive entries
@@ -146,9 +161,11 @@ __device__ __forceinline__ void face_record(const Tri& f, int is, float* rec) {
         for (int k = 0; k < 9; k++) rec[k] = fi[k];
     }
     rec[9] = f.z0; rec[10] = f.z1; rec[11] = f.z2;
+#if G2S_FT_SEEDS
     rec[12] = rcp_seed(f.z0); rec[13] = rcp_seed(f.z1); rec[14] = rcp_seed(f.z2);
+#endif
     // the operand-range verdict on the three z's is taken once per face, not once per hit
-    rec[15] = max(max(range_key(f.z0), range_key(f.z1)), range_key(f.z2)) >= RANGE_SPAN ? 1.0f : 0.0f;
+    rec[FT_FLAG] = max(max(range_key(f.z0), range_key(f.z1)), range_key(f.z2)) >= RANGE_SPAN ? 1.0f : 0.0f;
 }
 
 // Per-hit evaluation from a face record: [nr] kernel 2 after the inside test (clamped, renormalised weights and
@@ -170,7 +187,7 @@ __device__ __forceinline__ bool record_weights_depth(const float* rec, int xi, i
     // generic test per operand (those tests were a third of the per-hit instructions):
     //   wc[k] in [0,1]: only 0 < wc < 2^-38 is out -- as unsigned integers, bits(wc) - 1 wraps 0 to the top;
     //   w_sum in [max wc, 3]: in range as soon as one wc is, 0 when all are (-> IEEE path, 0/0);
-    //   w[k] = wc[k] / w_sum in {0} U [2^-40, 1] follows;  z[k]: the per-face verdict rec[15];  s: checked below.
+    //   w[k] = wc[k] / w_sum in {0} U [2^-40, 1] follows;  z[k]: the per-face verdict rec[FT_FLAG];  s: checked below.
     unsigned lo = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -179,7 +196,7 @@ __device__ __forceinline__ bool record_weights_depth(const float* rec, int xi, i
         q = __fmaf_rn(r, ys, q);
         r = __fmaf_rn(-w_sum, q, wc[k]);
         w[k] = __fmaf_rn(r, ys, q);
-        const float z = rec[9 + k], yz = rec[12 + k];
+        const float z = rec[9 + k], yz = G2S_FT_SEEDS ? rec[12 + k] : rcp_seed(z);
         q = __fmul_rn(w[k], yz);
         r = __fmaf_rn(-z, q, w[k]);
         q = __fmaf_rn(r, yz, q);
@@ -197,7 +214,7 @@ __device__ __forceinline__ bool record_weights_depth(const float* rec, int xi, i
         r = __fmaf_rn(-s, q, 1.0f);
         zp = __fmaf_rn(r, y, q);
     }
-    const bool fast = lo >= 0x2C800000u - 1u && w_sum > 0.0f && rec[15] == 0.0f && range_key(s) < RANGE_SPAN;
+    const bool fast = lo >= 0x2C800000u - 1u && w_sum > 0.0f && rec[FT_FLAG] == 0.0f && range_key(s) < RANGE_SPAN;
     if (!fast) {   // some operand outside its range: IEEE path
         Tri f;
         f.z0 = rec[9]; f.z1 = rec[10]; f.z2 = rec[11];
@@ -282,6 +299,9 @@ struct FwdOps {
 // triangle front-facing, which only happens for degenerate triangles).
 template <class Ops>
 __device__ __noinline__ void hit_inline(const Ops& ops, const Tri& f, int code, int face, int xi, int yi, int is) {
+#ifdef G2S_COUNT_SLOW
+    atomicAdd(&g_slow_counters[0], 1ull);
+#endif
     float rec[16];
     face_record(f, is, rec);
     ops.hit_direct(rec, code, face, xi, yi);
@@ -424,6 +444,9 @@ __device__ __forceinline__ void push_row_masks(TileSmem& sm, const Ops& ops, uns
 template <class Ops>
 __device__ __noinline__ void scan_row_inline(const Ops& ops, const Tri f, int code, int face, int yi, int xa, int xb,
                                              int is) {
+#ifdef G2S_COUNT_SLOW
+    atomicAdd(&g_slow_counters[1], 1ull);
+#endif
     typename Ops::Scan sc;
     sc.init(ops, f, face);
     sc.row(ops, yi);
@@ -596,34 +619,39 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
             uint32_t* wq_pix = sm.hq_pix + (tid >> 5) * WQ_CAP;
             uint16_t* wq_code = sm.hq_code + (tid >> 5) * WQ_CAP;
             int total;
-            int base = warp_excl_scan(__popc(maskA) + __popc(maskB), &total);
+            warp_excl_scan(__popc(maskA) + __popc(maskB), &total);
             if (total) {
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    unsigned m = k ? maskB : maskA;
-                    const int code = k ? codeB : codeA;
-                    while (m) {
-                        const int bit = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int xi = u.x0 + (bit & (SB - 1)), yi = u.y0 + bit / SB;
-                        if (base < WQ_CAP) {
-                            wq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)xi;
-                            wq_code[base] = (uint16_t)code;
-                        } else {
-                            hit_inline(ops, k ? B.f : A.f, code, k ? faceB : faceA, xi, yi, is);
-                        }
-                        base++;
-                    }
-                }
                 if (maskA) face_record(A.f, is, &sm.ftab[ft_index(tid * 2) * FT_STRIDE]);
                 if (maskB) face_record(B.f, is, &sm.ftab[ft_index(tid * 2 + 1) * FT_STRIDE]);
-                __syncwarp();
-                const int nh = min(total, WQ_CAP);
-                for (int i = lane; i < nh; i += 32) {
-                    const int code = wq_code[i];
-                    const uint32_t pix = wq_pix[i];
-                    ops.hit(&sm.ftab[ft_index(code) * FT_STRIDE], code, code_face(code, Q, S, ty0, tx0), (int)(pix & 0xffffu),
-                            (int)(pix >> 16));
+                // one pass when the warp's hits fit its slice; otherwise the first triangles, then the second ones (a
+                // triangle has at most SB*SB hits, so either half always fits: no overflow path here)
+                static_assert(WQ_CAP >= 32 * SB * SB, "a warp's slice must hold one triangle per lane");
+                const int npass = total <= WQ_CAP ? 1 : 2;
+#pragma unroll 1
+                for (int pass = 0; pass < npass; pass++) {
+                    const unsigned mA = (npass == 2 && pass == 1) ? 0u : maskA, mB = (npass == 2 && pass == 0) ? 0u : maskB;
+                    int nh;
+                    int base = warp_excl_scan(__popc(mA) + __popc(mB), &nh);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        unsigned m = k ? mB : mA;
+                        const int code = k ? codeB : codeA;
+                        while (m) {
+                            const int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            wq_pix[base] = ((uint32_t)(u.y0 + bit / SB) << 16) | (uint32_t)(u.x0 + (bit & (SB - 1)));
+                            wq_code[base] = (uint16_t)code;
+                            base++;
+                        }
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < nh; i += 32) {
+                        const int code = wq_code[i];
+                        const uint32_t pix = wq_pix[i];
+                        ops.hit(&sm.ftab[ft_index(code) * FT_STRIDE], code, code_face(code, Q, S, ty0, tx0),
+                                (int)(pix & 0xffffu), (int)(pix >> 16));
+                    }
+                    __syncwarp();
                 }
             }
         }
