@@ -1253,11 +1253,10 @@ inline dim3 pix_grid2(int S, int views, int bx = PBX, int by = PBY) { return dim
 // views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
 // scratch 16 S^2 B/view) stays resident in the 126 MB L2 between the kernel that writes it and the one that reads it
 inline int chunk_views_for(int S, int cap) {
-    // 24 MB of z-buffer per chunk (two chunks are in flight in the two-lane forward), but never fewer than 48 views: below
-    // that the launches are too short and the tail of the rasteriser (a few heavy wall tiles) costs more than the L2
-    // misses of a larger z-buffer (measured at 128^2 and 256^2, profiles/r01_notes.md)
+    // 24 MB of z-buffer per chunk: two chunks are in flight in the two-lane forward and both must stay in the 126 MB L2
+    // next to the streaming outputs (swept at 128^2 and 256^2, profiles/r01_notes.md); at least 8 views per launch
     long v = (24L << 20) / (32L * S * S);
-    if (v < 48) v = 48;
+    if (v < 8) v = 8;
     if (v > cap) v = cap;
     return (int)v;
 }
