@@ -93,6 +93,7 @@ class ShadingFn(torch.autograd.Function):
                    "g2s_shading_fwd")
         ctx.save_for_backward(n, L, a)
         ctx.meta = (ns, as_, B, HW, normal.shape, albedo.shape)
+        ctx.set_materialize_grads(False)     # an unused output arrives as None, not as a zero-filled tensor
         return diffuse, texture
 
     @staticmethod
@@ -100,6 +101,8 @@ class ShadingFn(torch.autograd.Function):
         lib = _lib.load()
         n, L, a = ctx.saved_tensors
         ns, as_, B, HW, nshape, ashape = ctx.meta
+        if g_diffuse is None and g_texture is None:
+            return None, None, None
         gd = _f32c(g_diffuse) if g_diffuse is not None else None
         gt = _f32c(g_texture) if g_texture is not None else None
         g_n = torch.zeros(nshape, device=L.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None

@@ -106,10 +106,13 @@ class WarpCanonDepthFn(torch.autograd.Function):
         ctx.renderer = renderer
         ctx.shapes = (depth.shape, R.shape, t.shape)
         ctx.mark_non_differentiable(fidx)
+        ctx.set_materialize_grads(False)     # no zero-filled int32 [B,2S,2S] "gradient" for the face-index map
         return recon, fidx
 
     @staticmethod
     def backward(ctx, g_recon, _g_fidx):
+        if g_recon is None:
+            return None, None, None, None
         lib = _lib.load()
         dstore, Rc, tc, fidx, recon = ctx.saved_tensors
         (B, S, _), Rshape, tshape = ctx.shapes
@@ -331,6 +334,9 @@ class RenderChainFn(torch.autograd.Function):
         ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape)
         ctx.mark_non_differentiable(fidx)
+        # unused outputs reach backward as None instead of zero-filled tensors (autograd would otherwise fill a
+        # [B,S,S] float and a [B,2S,2S] int32 tensor per step just to say "no gradient")
+        ctx.set_materialize_grads(False)
         if want_mask:
             ctx.mark_non_differentiable(mask_out)
             return recon_im, recon_depth, fidx, mask_out
@@ -345,6 +351,8 @@ class RenderChainFn(torch.autograd.Function):
         B = N * vpi
         dev = d.device
         cam = renderer._camera(depth_pass=True)
+        if g_im is None and g_depth_out is None:
+            return (None,) * 10
         gi = _f32c(g_im) if g_im is not None else torch.zeros(B, 3, S, S, device=dev)
         gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
         ws_views = min(B, lib.g2s_chunk_views_bwd(S))
