@@ -303,11 +303,13 @@ def run_ours(args):
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same launch shape only)
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tj = json.load(f)["kernels"].get(dom["name"])
-        if tj and S == 128 and dom["launches"] and B * args.steps // dom["launches"] == tj["views_per_launch"]:
-            traffic = tj["dram_bytes_per_launch"]
+        if tj and S == 128 and dom["launches"]:
+            # per launch like `achieved`: the capture's bytes per launch scaled to this run's views per launch
+            traffic = tj["dram_bytes_per_launch"] * (B * args.steps / dom["launches"]) / tj["views_per_launch"]
             ncu_ctx = {k: tj[k] for k in ("sm_throughput_pct", "issue_active_pct", "occupancy_pct",
-                                         "dram_throughput_pct", "registers") if k in tj}
-            ncu_ctx["source"] = "profiles/r01_ncu_full.md (committed ncu --set full capture, not measured by this run)"
+                                         "dram_throughput_pct", "registers", "dram_bytes_per_launch_warm_l2") if k in tj}
+            ncu_ctx["source"] = ("profiles/r01_ncu_full.md (committed ncu --set full capture at %d views per launch, cold "
+                                 "cache; not measured by this run)" % tj["views_per_launch"])
     except Exception:
         traffic = None
     step_achieved = value / world * per_render / 1e9
