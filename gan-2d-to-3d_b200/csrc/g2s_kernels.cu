@@ -1192,6 +1192,11 @@ __global__ void k_selftest_division(unsigned long long per_thread, unsigned seed
         const float b = __uint_as_float(((hi >> 31) << 31) | (eb << 23) | mb);
         const float q0 = __fdiv_rn(a, b), q1 = dvd_y(a, b, rcp_seed(b));
         bad += __float_as_uint(q0) != __float_as_uint(q1);
+        // the unguarded core with a small numerator (face_record relies on it down to 2^-50): a * 2^-16 in [2^-60, 2^28]
+        if (range_key(b) < RANGE_SPAN) {
+            const float as = a * 1.52587890625e-05f;
+            bad += __float_as_uint(__fdiv_rn(as, b)) != __float_as_uint(div_core(as, b, rcp_seed(b)));
+        }
         const float z0 = __fdiv_rn(0.0f, b), z1 = dvd_y(0.0f, b, rcp_seed(b));
         bad += (z0 != z1);
     }

@@ -148,13 +148,14 @@ __device__ __forceinline__ void face_record(const Tri& f, int is, float* rec) {
     a[6] = sub(p01, p11); a[7] = sub(p10, p00); a[8] = sub(mul(p00, p11), mul(p10, p01));
     const float den = add(add(mul(p20, sub(p01, p11)), mul(p00, sub(p11, p21))), mul(p10, sub(p21, p01)));
     const float y = rcp_seed(den);
-    unsigned bad = range_key(den);
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
-        rec[k] = div_core(a[k], den, y);
-        bad = max(bad, a[k] == 0.0f ? 0u : range_key(a[k]));
-    }
-    if (bad >= RANGE_SPAN) {
+    for (int k = 0; k < 9; k++) rec[k] = div_core(a[k], den, y);
+    // Operand ranges from the structure of the values instead of one test per numerator: every p is a multiple of 2^-25
+    // (ndc_to_pix ends in `0.5 * (X - 1)` with X a multiple of 2^-24), so a non-zero numerator -- a difference of p's or of
+    // products of p's -- is at least 2^-50 in magnitude; with max|p| < 2^19 it is below 2^39.  div_core is exact for such
+    // numerators over a denominator in [2^-40, 2^40) (g2s_selftest_division covers numerators down to 2^-60).
+    const float pmax = fmaxf(fmaxf(fmaxf(fabsf(p00), fabsf(p01)), fmaxf(fabsf(p10), fabsf(p11))), fmaxf(fabsf(p20), fabsf(p21)));
+    if (!(pmax < 524288.0f) || range_key(den) >= RANGE_SPAN) {
         float fi[9];
         tri_face_inv(f, is, fi);
 #pragma unroll
