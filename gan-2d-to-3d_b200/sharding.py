@@ -50,13 +50,13 @@ def reduce_image_grads(grads, n_images, group=None):
 
 
 def render_chain_sharded(render_fn, depth, albedo, view, light, cotangent, views_per_image, rank, world_size,
-                         group=None):
+                         group=None, want_loss=True):
     """Data-parallel fwd+bwd of the fused render: each rank renders its slice of the views with `render_fn`
     (= Renderer.render_chain; injected so the host logic can be tested on CPU with the oracle) and the per-image
     gradients are summed across ranks only for images whose views span ranks.
 
     Returns dict(recon_im, recon_depth [local views], grad_depth, grad_albedo [n_images, ...] (reduced), grad_view,
-    grad_light [local views], loss (global sum), shard)."""
+    grad_light [local views], loss (global sum of <recon_im, cotangent>; skipped with want_loss=False), shard)."""
     n_images = depth.shape[0]
     sh = shard_views(n_images, views_per_image, rank, world_size)
     v0, v1, i0, i1 = sh["view_start"], sh["view_stop"], sh["image_start"], sh["image_stop"]
@@ -81,17 +81,19 @@ def render_chain_sharded(render_fn, depth, albedo, view, light, cotangent, views
             recon_im, recon_depth = torch.cat(ims, 0), torch.cat(rds, 0)
         else:
             recon_im, recon_depth = render_fn(d, a, vw, lt, views_per_image)[:2]
-        local = (recon_im * cotangent[v0:v1]).sum()
-        local.backward()
+        cot = cotangent[v0:v1]
+        torch.autograd.backward([recon_im], [cot])        # the cotangent goes straight to the backward
         g_depth[i0:i1] = d.grad
         g_albedo[i0:i1] = a.grad
-        loss = local.detach().float()
+        if want_loss:
+            loss = (recon_im.detach() * cot).sum().float()
         out.update(recon_im=recon_im.detach(), recon_depth=recon_depth.detach(), grad_view=vw.grad, grad_light=lt.grad)
     if world_size > 1 and dist.is_initialized():
         any_split = torch.tensor([1.0 if sh["split_images"] else 0.0], device=depth.device)
         dist.all_reduce(any_split, op=dist.ReduceOp.MAX, group=group)
         if float(any_split.item()) > 0:
             reduce_image_grads([g_depth, g_albedo], n_images, group)
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        if want_loss:
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     out.update(grad_depth=g_depth, grad_albedo=g_albedo, loss=loss)
     return out
