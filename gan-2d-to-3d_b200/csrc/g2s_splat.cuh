@@ -29,6 +29,9 @@ __device__ unsigned long long g_slow_counters[2];
 #ifndef G2S_WARP_LOCAL
 #define G2S_WARP_LOCAL 1
 #endif
+#ifndef G2S_EAGER_FT
+#define G2S_EAGER_FT G2S_WARP_LOCAL   // table entries of all queued faces up front (needs the warp-local small-quad path)
+#endif
 #ifndef G2S_HQ_PER_THREAD
 #define G2S_HQ_PER_THREAD 16
 #endif
@@ -703,9 +706,24 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     if (!tile_queues) return;   // interior tiles: nothing but small quads, no barrier
 #endif
     __syncthreads();
+#if G2S_EAGER_FT
+    // Table entries of ALL queued faces now, one thread per face (from the top thread down: the expansion below keeps the
+    // low warps busy), instead of lazily for the faces that scored in a round: that phase kept one or two warps busy while
+    // six waited at its barrier, every round.
+    {
+        const int nw_ = sm.n_wq, nq_ = nw_ + sm.n_mq;
+        for (int e = SPLAT_THREADS - 1 - tid; e < nq_; e += SPLAT_THREADS) {
+            const int code = e < nw_ ? sm.wq[e] : sm.mq[e - nw_];
+            face_record(code_tri(sm.sv, code), is, &sm.ftab[ft_index(code) * FT_STRIDE]);
+        }
+    }
+#endif
     expand_queued_faces(sm, ops, recs, Q, S, ty0, tx0);
     const uint32_t* tq = sm.tq;
-    int t0 = 0, nf_done = 0;
+    int t0 = 0;
+#if !G2S_EAGER_FT
+    int nf_done = 0;
+#endif
     while (true) {
         __syncthreads();
         const int nt = min(sm.n_tq, TQ_CAP);
@@ -732,6 +750,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
                 mask |= (in ? 1u : 0u) << rx;
             }
             push_row_masks(sm, ops, mask, x0, yi, code, face, is);
+#if !G2S_EAGER_FT
             // the first task of a face to score a hit requests the face's table entry
             bool owner = false;
             if (mask) owner = ((atomicOr(&sm.owned[(code & 511) >> 5], 1u << (code & 31)) >> (code & 31)) & 1u) == 0u;
@@ -742,8 +761,10 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
                 fbase = __shfl_sync(0xffffffffu, fbase, 0);
                 if (owner) sm.fq[fbase + __popc(owners & ((1u << lane) - 1u))] = (uint16_t)code;
             }
+#endif
         }
         __syncthreads();
+#if !G2S_EAGER_FT
         // face table: one thread per face that owns a hit for the first time
         const int nf = sm.n_fq;
         for (int i = nf_done + tid; i < nf; i += SPLAT_THREADS) {
@@ -752,6 +773,7 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         }
         nf_done = nf;
         __syncthreads();
+#endif
         // drain the hit queue: one thread per hit
         const int nh = min(sm.n_hq, HQ_CAP);
         for (int i = tid; i < nh; i += SPLAT_THREADS) {
