@@ -728,8 +728,7 @@ k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, in
     pixel_ray(cam, vx, vy, ray);
     warp_point(cam, sRt, sRt + 9, ray, depth[(long)(b / vpi) * dstride + v], q);
     project_ndc(cam, q, ndc);
-    float* o = proj + ((long)bl * S * S + v) * 3;
-    o[0] = ndc[0]; o[1] = ndc[1]; o[2] = ndc[2];
+    reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
 }
 
 __global__ void __launch_bounds__(RBX * RBY)
@@ -744,8 +743,8 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
     const int2 r0 = *reinterpret_cast<const int2*>(fm + (long)(2 * i) * is + 2 * j);
     const int2 r1 = *reinterpret_cast<const int2*>(fm + (long)(2 * i + 1) * is + 2 * j);
     const int f0 = r0.x, f1 = r0.y, f2 = r1.x, f3 = r1.y;
-    const float* pv = proj + (long)bl * S * S * 3;
-    float* vg = vgrad + (long)bl * S * S * 3;
+    const float4* pv = reinterpret_cast<const float4*>(proj) + (long)bl * S * S;   // projected vertices, packed uvz-
+    float4* vg = reinterpret_cast<float4*>(vgrad) + (long)bl * S * S;              // vertex gradients, packed uvz-
     const float hs = 0.5f * (float)is;
     // Distinct faces of the 2x2 block, one per trip of ONE loop body (not four unrolled copies: the unrolled form ran
     // at 17 active lanes per instruction and stalled on instruction fetch, profiles/r01_notes.md): `rem` = sub-pixels
@@ -762,7 +761,8 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         float nd[3][3];
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-            nd[m][0] = __ldg(&pv[vidx[m] * 3]); nd[m][1] = __ldg(&pv[vidx[m] * 3 + 1]); nd[m][2] = __ldg(&pv[vidx[m] * 3 + 2]);
+            const float4 q = __ldg(&pv[vidx[m]]);
+            nd[m][0] = q.x; nd[m][1] = q.y; nd[m][2] = q.z;
         }
         float rec[16];
         face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
@@ -799,10 +799,8 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
 #pragma unroll
         for (int m = 0; m < 3; m++) {
             if (A[m] == 0.f) continue;
-            float* o = &vg[vidx[m] * 3];
-            atomicAdd(&o[0], -t0 * A[m] * hs);
-            atomicAdd(&o[1], -t1 * A[m] * hs);
-            atomicAdd(&o[2], __fdiv_rn(A[m], z[m] * z[m]));
+            // one 16-byte vector reduction per vertex instead of three scalar ones
+            atomicAdd(&vg[vidx[m]], make_float4(-t0 * A[m] * hs, -t1 * A[m] * hs, __fdiv_rn(A[m], z[m] * z[m]), 0.f));
         }
     }
 }
@@ -822,8 +820,8 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
     if (v < S * S) {
-        const float* gp = vgrad + ((long)bl * S * S + v) * 3;
-        const float gu = gp[0], gv = gp[1], gz = gp[2];
+        const float4 gp = __ldcs(reinterpret_cast<const float4*>(vgrad) + (long)bl * S * S + v);
+        const float gu = gp.x, gv = gp.y, gz = gp.z;
         if (gu != 0.f || gv != 0.f || gz != 0.f) {
             const int vy = v / S, vx = v - vy * S;
             float ray[3], q[3];
@@ -1270,15 +1268,19 @@ inline dim3 pix_grid(long npix, int batch) { return dim3((unsigned)((npix + PIX_
 
 inline bool bad_size(int S) { return S < 2 || S > 2048; }
 
+// the masked-quarter-gradient plane of a raster workspace laid out for nv views (see launch_raster_bwd)
+inline float* raster_ws_gsub(float* raster_ws, int nv, int S) { return raster_ws + (size_t)nv * 8 * S * S; }
+
 inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
                               const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth, long gdstride,
                               float* grad_R, float* grad_t, cudaStream_t st) {
     const int S = c.S;
     const size_t img = (size_t)S * S;
-    float* g_sub = raster_ws;
-    float* proj = raster_ws + (size_t)nv * img;
-    float* vgrad = proj + (size_t)nv * 3 * img;
-    cudaMemsetAsync(vgrad, 0, sizeof(float) * nv * 3 * img, st);
+    // raster_ws [nv, 9, S, S]: projected vertices (uvz-, 16-byte texels) | vertex gradients (uvz-) | masked quarter gradient
+    float* proj = raster_ws;
+    float* vgrad = proj + (size_t)nv * 4 * img;
+    float* g_sub = raster_ws_gsub(raster_ws, nv, S);
+    cudaMemsetAsync(vgrad, 0, sizeof(float) * nv * 4 * img, st);
     { Launch l_(K_PROJECT, st);
       k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj); }
     { Launch l_(K_RASTER_BWD, st);
@@ -1348,7 +1350,7 @@ int g2s_warp_depth_bwd(const g2s_camera* cam, const float* depth, long depth_vie
     cudaStream_t st = (cudaStream_t)stream;
     const long n = (long)n_views * S * S;
     { Launch l_(K_CLAMP_GRAD, st); k_clamp_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(recon_depth, grad_recon_depth, c.clamp_lo, c.clamp_hi, n,
-                                                              grad_sub_ws); }
+                                                              raster_ws_gsub(grad_sub_ws, n_views, S)); }
     launch_raster_bwd(c, depth, depth_view_stride, 1, R, t, face_idx, grad_sub_ws, n_views, 0, grad_depth,
                       grad_depth_view_stride, grad_R, grad_t, st);
     return launch_status();
@@ -1420,7 +1422,7 @@ int g2s_chunk_views_bwd(int image_size) {
         const long v = atol(e) * 128L * 128L / ((long)image_size * image_size);
         if (v >= 1) return (int)v;
     }
-    const long per_view = 11L * image_size * image_size * 4;   // 7 S^2 (raster scratch) + 4 S^2 (packed texture gradient)
+    const long per_view = 13L * image_size * image_size * 4;   // 9 S^2 (raster scratch) + 4 S^2 (packed texture gradient)
     long v = (1L << 30) / per_view;
     return (int)(v < 1 ? 1 : v);
 }
@@ -1524,7 +1526,7 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
         FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
         { Launch l_(K_BWD_PIXEL, st);
           k_render_bwd_pixel<<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
-                                                                         grad_sub_ws, grad_tex_ws, grad_R, grad_t); }
+                                                                         raster_ws_gsub(grad_sub_ws, nv, S), grad_tex_ws, grad_R, grad_t); }
         const int img_lo = (int)(v0 / views_per_image), img_hi = (int)((v0 + nv - 1) / views_per_image);
         { Launch l_(K_BWD_TEX, st);
           k_render_bwd_tex<<<pix_grid((long)S * S, img_hi - img_lo + 1), PIX_THREADS, 0, st>>>(S, fa, nv, grad_tex_ws, grad_albedo,

@@ -118,7 +118,7 @@ class WarpCanonDepthFn(torch.autograd.Function):
         (B, S, _), Rshape, tshape = ctx.shapes
         cam = ctx.renderer._camera(depth_pass=True)
         g = _f32c(g_recon)
-        ws = torch.empty(B, 7, S, S, device=g.device, dtype=torch.float32)   # g_sub | projected verts | vertex grads
+        ws = torch.empty(B, 9, S, S, device=g.device, dtype=torch.float32)   # projected verts | vertex grads (uvz-) | g_sub
         g_depth = torch.zeros(B, S, S, device=g.device, dtype=torch.float32)
         need_view = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         gR = torch.zeros(B, 3, 3, device=g.device, dtype=torch.float32) if need_view else None
@@ -356,7 +356,7 @@ class RenderChainFn(torch.autograd.Function):
         gi = _f32c(g_im) if g_im is not None else torch.zeros(B, 3, S, S, device=dev)
         gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
         ws_views = min(B, lib.g2s_chunk_views_bwd(S))
-        ws_sub = torch.empty(ws_views, 7, S, S, device=dev, dtype=torch.float32)   # g_sub | projected verts | vertex grads
+        ws_sub = torch.empty(ws_views, 9, S, S, device=dev, dtype=torch.float32)   # projected verts | vertex grads (uvz-) | g_sub
         ws_tex = torch.empty(ws_views, S, S, 4, device=dev, dtype=torch.float32)
         ws_nrm = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
         g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)

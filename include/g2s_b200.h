@@ -71,8 +71,8 @@ int g2s_warp_depth_fwd(const g2s_camera *cam, const float *depth, long depth_vie
  * through flip / 2x2 average / clamp on one side and gather / projection / rotation on the other.
  * grad_depth is ACCUMULATED (caller zero-fills) with `grad_depth_view_stride` floats between views
  * (0 = sum over views into one [S,S] map); grad_R [n_views,3,3] and grad_t [n_views,3] are
- * ACCUMULATED too (NULL to skip both).  Workspace grad_sub_ws: n_views * 7 * S * S floats (masked quarter
- * gradient | projected vertices | vertex gradients). */
+ * ACCUMULATED too (NULL to skip both).  Workspace grad_sub_ws: n_views * 9 * S * S floats, 16-byte
+ * aligned (projected vertices uvz- | vertex gradients uvz- | masked quarter gradient). */
 int g2s_warp_depth_bwd(const g2s_camera *cam, const float *depth, long depth_view_stride, const float *R,
                        const float *t, int n_views, const int32_t *face_idx, const float *recon_depth,
                        const float *grad_recon_depth, float *grad_sub_ws, float *grad_depth,
@@ -133,7 +133,7 @@ int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float 
                          void *stream);
 
 /* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
- * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,7,S,S] (as above),
+ * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,9,S,S] (as above),
  * grad_tex_ws [ws_views,S,S,4] (per-view texture gradient, packed rgb-; 16-byte aligned; chunked like the forward), grad_normal_ws [n_images,S,S,8] (packed texels: normal xyz,
  * albedo rgb, 2 pad; kept for the backward).
  * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
