@@ -82,14 +82,16 @@ struct Launch {
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? G2S_OK : G2S_ERR_LAUNCH; }
 
 // one internal non-blocking stream per device for the two-lane chunk pipeline of g2s_render_fused_fwd
-inline cudaStream_t aux_stream() {
+constexpr int MAX_LANES = 4;
+inline cudaStream_t aux_stream(int k) {
     static std::mutex mu;
-    static cudaStream_t streams[64] = {nullptr};
+    static cudaStream_t streams[64][MAX_LANES] = {};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (k < 0 || k >= MAX_LANES || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
-    return streams[dev];
+    if (!streams[dev][k] && cudaStreamCreateWithFlags(&streams[dev][k], cudaStreamNonBlocking) != cudaSuccess)
+        streams[dev][k] = nullptr;
+    return streams[dev][k];
 }
 
 
@@ -1462,24 +1464,28 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
     // one, forked and joined with events): the next chunk's k_splat fills the SMs that the tail of the current one leaves
     // idle (a 64-view launch lost ~8 % to its tail, profiles/r01_notes.md).  Not while per-kernel timing is on.
     const int rec = g2s_chunk_views(S);
-    const bool two = ws_views >= 2 * rec && n_views > rec && !g_prof_on && !getenv("G2S_NO_PIPELINE");
-    const int one = ws_views >= 2 * rec ? rec : ws_views;     // single lane: one recommended chunk at a time
-    const int chunk = two ? (ws_views / 2 < 32768 ? ws_views / 2 : 32768) : (one < 32768 ? one : 32768);
-    cudaStream_t lanes[2] = {st, st};
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    if (two) {
-        lanes[1] = aux_stream();
-        if (!lanes[1] || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
-            return G2S_ERR_LAUNCH;
+    int nl = (int)(ws_views / rec);                    // lanes the workspace has room for
+    if (nl > MAX_LANES) nl = MAX_LANES;
+    if (const char* e = getenv("G2S_FWD_LANES")) { const int v = atoi(e); if (v >= 1 && v < nl) nl = v; }
+    if (nl < 1 || n_views <= rec || g_prof_on || getenv("G2S_NO_PIPELINE")) nl = 1;
+    const int per = nl > 1 ? rec : (ws_views >= rec ? rec : ws_views);   // views per chunk
+    const int chunk = per < 32768 ? per : 32768;
+    cudaStream_t lanes[MAX_LANES] = {st, st, st, st};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    if (nl > 1) {
+        if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return G2S_ERR_LAUNCH;
         cudaEventRecord(ev_fork, st);
-        cudaStreamWaitEvent(lanes[1], ev_fork, 0);
+        for (int k = 1; k < nl; k++) {
+            lanes[k] = aux_stream(k);
+            if (!lanes[k] || cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming) != cudaSuccess) return G2S_ERR_LAUNCH;
+            cudaStreamWaitEvent(lanes[k], ev_fork, 0);
+        }
     }
     int lane = 0;
-    for (long v0 = 0; v0 < n_views; v0 += chunk, lane ^= (two ? 1 : 0)) {
+    for (long v0 = 0; v0 < n_views; v0 += chunk, lane = (lane + 1) % nl) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         cudaStream_t ls = lanes[lane];
-        unsigned long long* zb = (unsigned long long*)zbuf + (two && lane ? (size_t)chunk * 4 * S * S : 0);
+        unsigned long long* zb = (unsigned long long*)zbuf + (size_t)lane * chunk * 4 * S * S;
         { Launch l_(K_SPLAT, ls);
           k_splat<false><<<dim3(nv, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), ls>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
                                                                            zb, tiles, (int)v0); }
@@ -1487,11 +1493,13 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
         { Launch l_(K_RESOLVE_FUSED, ls);
           k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, ls>>>(c, zb, recon_depth, face_idx, fa); }
     }
-    if (two) {
-        cudaEventRecord(ev_join, lanes[1]);
-        cudaStreamWaitEvent(st, ev_join, 0);
-        cudaEventDestroy(ev_fork);     // released by the runtime once they have completed
-        cudaEventDestroy(ev_join);
+    if (nl > 1) {
+        for (int k = 1; k < nl; k++) {
+            cudaEventRecord(ev_join[k], lanes[k]);
+            cudaStreamWaitEvent(st, ev_join[k], 0);
+            cudaEventDestroy(ev_join[k]);      // released by the runtime once it has completed
+        }
+        cudaEventDestroy(ev_fork);
     }
     return launch_status();
 }

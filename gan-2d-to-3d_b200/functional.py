@@ -6,10 +6,14 @@ stream.  torch is used for device memory, streams and autograd bookkeeping only.
 PyTorch fallback: non-CUDA tensors raise.
 """
 import ctypes
+import os
 
 import torch
 
 from . import _lib
+
+
+FWD_LANES = int(os.environ.get("G2S_FWD_LANES", "2"))
 
 
 def _stream():
@@ -318,7 +322,8 @@ class RenderChainFn(torch.autograd.Function):
         L = _f32c(light)
         cam = renderer._camera(depth_pass=True)
         dev = d.device
-        ws_views = min(B, 2 * lib.g2s_chunk_views(S))      # two chunks: the forward alternates between the halves
+        # z-buffer for FWD_LANES chunks: the forward rotates its chunks over that many lanes (streams)
+        ws_views = min(B, FWD_LANES * lib.g2s_chunk_views(S))
         zbuf = renderer._zbuf.get(ws_views, S, cam.far_z, dev)
         normal = torch.empty(N, S, S, 8, device=dev, dtype=torch.float32)    # packed texels: normal xyz, albedo rgb, pad
         recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)

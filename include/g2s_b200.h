@@ -114,11 +114,12 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * light [n_views,5] = (ambient a, diffuse b, direction dx,dy,dz) as get_lighting_directions returns.
  * The views are processed in chunks so that the per-chunk scratch stays L2-resident between the kernel that writes it
  * and the kernel that reads it; g2s_chunk_views(S) returns the recommended chunk (24 MB of z-buffer).  `ws_views` = views
- * the z-buffer workspace holds: with at least two recommended chunks (and more views than one chunk) the chunks
- * alternate between the two halves of the workspace on two streams -- `stream` and one internal non-blocking stream per
- * device, forked from and joined back into `stream` with events (capturable in a CUDA graph) -- so that one chunk's
- * rasteriser fills the SMs the tail of the previous one leaves idle; otherwise one chunk of min(ws_views, recommended)
- * views at a time on `stream` alone (also while per-kernel timing is on, or with G2S_NO_PIPELINE set).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,8] (packed texels: normal xyz,
+ * the z-buffer workspace holds: with room for L >= 2 recommended chunks (and more views than one chunk) the chunks rotate
+ * over L lanes (L <= 4; the Python host asks for 2, the measured optimum) -- one part of the workspace and one stream each:
+ * `stream` and internal non-blocking streams (one set per device), forked from and joined back into `stream` with events
+ * (capturable in a CUDA graph) -- so that one chunk's rasteriser fills the SMs the tail of the previous one leaves idle;
+ * otherwise one chunk of min(ws_views, recommended) views at a time on `stream` alone (also while per-kernel timing is on,
+ * or with G2S_NO_PIPELINE set).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,8] (packed texels: normal xyz,
  * albedo rgb, 2 pad; kept for the backward).
  * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S] (may be NULL).
  * Optional (sample_pseudo_imgs, model.py:291-328 -> render_given_view(..., mask, grid_sample=True), renderer.py:257-264):
