@@ -460,13 +460,15 @@ def test_raster_fast_path_equals_ieee_path():
     assert int(bad.item()) == 0
 
 
-def test_cuda_graph_step_matches_eager():
-    """forward + backward captured once into a CUDA graph (small, launch-bound batches) == eager"""
+@pytest.mark.parametrize("S,P,N", [(32, 4, 1), (128, 16, 8)])
+def test_cuda_graph_step_matches_eager(S, P, N):
+    """forward + backward captured once into a CUDA graph (small, launch-bound batches) == eager; the second case has
+    more views than one forward chunk, so the capture includes the two-lane fork / join (events, internal stream)"""
     import g2s_b200
-    S, P = 32, 4
-    case = _case(S, P, 81, 60.0)
+    from g2s_b200 import synthetic
+    case = synthetic.make_case(S, P, seed=81, n_images=N)
     ren = _cuda_renderer(S)
-    g = g2s_b200.graphs.GraphedRenderStep(ren, 1, P)
+    g = g2s_b200.graphs.GraphedRenderStep(ren, N, P)
     dev = {k: v.cuda() for k, v in case.items()}
     for _ in range(2):     # replay twice: the z-buffer must come back clean each time
         im, rd, fidx, grads = g.step(dev["depth"], dev["albedo"], dev["view"], dev["light"], dev["cotangent"])
