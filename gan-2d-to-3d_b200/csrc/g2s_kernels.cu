@@ -183,8 +183,7 @@ k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, c
         if (tid < 9) sm.sRt[tid] = R[b * 9 + tid];
         else if (tid < 12) sm.sRt[tid] = t[b * 3 + tid - 9];
     }
-    if (tid == 0) sm.n_hq = sm.n_fq = sm.n_tq = sm.n_wq = sm.n_mq = 0;
-    if (tid < NSLOT / 32) sm.owned[tid] = 0u;
+    if (tid == 0) sm.n_hq = sm.n_tq = sm.n_wq = sm.n_mq = 0;
     __syncthreads();
     tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
                              FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, sm.sRt, ty0, tx0, sm.sv);

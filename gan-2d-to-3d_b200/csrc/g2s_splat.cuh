@@ -5,18 +5,19 @@
 //
 // One CTA per TILE x TILE block of quads of one view:
 //   1. project the tile's (TILE+1)^2 vertices once into shared memory (u, v, z);
-//   2. candidate scan -- only the cheap, exact inside test (three edge functions, loop invariants hoisted):
-//        * quads whose two triangles fit one SB x SB sub-pixel box are scanned by their owning thread with UNIFORM
-//          control flow (loop bounds = warp maxima, per-lane predicates) into two 16-bit hit masks;
-//        * triangles with a box up to MB x MB go to a queue scanned by 8-lane groups (one lane per row);
-//        * larger boxes (the 1-px depth-step walls stretch to >100 sub-pixels under yaw) are scanned by whole
-//          warps, row by row over a conservative per-row extent.
-//      Hits are appended to a HIT QUEUE in shared memory (one atomic per warp step);
-//   3. the faces that own at least one hit get their 3x3 inverse computed ONCE, by consecutive threads, into a
-//      shared-memory face table;
-//   4. the hit queue is drained by consecutive threads: weights, perspective z, 64-bit atomicMin into the z-buffer.
-// Steps 3 and 4 hold the correctly rounded divisions and run fully converged; in the first per-thread form the
-// same code ran at 3-7 active lanes per warp (ncu, profiles/r01_*).
+//   2. SMALL QUADS (both triangles inside one SB x SB sub-pixel box: every interior quad) never leave their warp: the
+//      owning thread scans the box with UNIFORM control flow (loop bounds = warp maxima, per-lane predicates; only the
+//      cheap, exact inside test: three edge functions with the loop invariants hoisted) into two 16-bit hit masks; the hits
+//      go to the warp's private slice of the hit queue (offsets from a warp scan, no atomics); every lane builds the 3x3
+//      inverses of its own two triangles into the shared-memory face table; after a __syncwarp the warp drains its slice,
+//      one lane per hit: weights, perspective z, 64-bit atomicMin into the z-buffer.  No CTA barrier in this path;
+//   3. everything else (the 1-px depth-step walls stretch to >100 sub-pixels under yaw) is queued; after ONE barrier the
+//      table entries of all queued faces are built (one thread per face), whole warps expand the faces into ROW TASKS
+//      (face, row, 8-column segment; wide boxes only the segments that overlap a conservative per-row extent), and the
+//      tasks are scanned one lane per task in rounds sized to the CTA-wide hit queue, each round drained by consecutive
+//      threads.
+// The correctly rounded divisions (face table, drain) run fully converged in both paths; in the first per-thread form
+// the same code ran at 3-7 active lanes per warp (ncu, profiles/r01_notes.md).
 #pragma once
 #include "g2s_raster.cuh"
 
@@ -26,12 +27,6 @@ namespace g2s {
 __device__ unsigned long long g_slow_counters[2];
 #endif
 
-#ifndef G2S_WARP_LOCAL
-#define G2S_WARP_LOCAL 1
-#endif
-#ifndef G2S_EAGER_FT
-#define G2S_EAGER_FT G2S_WARP_LOCAL   // table entries of all queued faces up front (needs the warp-local small-quad path)
-#endif
 #ifndef G2S_HQ_PER_THREAD
 #define G2S_HQ_PER_THREAD 16
 #endif
@@ -59,12 +54,10 @@ struct TileSmem {
     uint32_t tq[TQ_CAP];         // row tasks
     uint32_t hq_pix[HQ_CAP];
     uint16_t hq_code[HQ_CAP];
-    uint16_t fq[NSLOT];
-    unsigned owned[NSLOT / 32];
     uint16_t wq[NSLOT];          // wide faces whose rows a warp expands into tasks
     uint16_t mq[NSLOT];          // other queued faces
     float sRt[12];
-    int n_hq, n_fq, n_tq, n_wq, n_mq;
+    int n_hq, n_tq, n_wq, n_mq;
 };
 
 // code = slot | rev << 9, slot = quad * 2 + tri
@@ -557,12 +550,10 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
         const int uw = u.x1 - u.x0 + 1, uh = u.y1 - u.y0 + 1;
         const bool any_act = A.act || B.act;
         const bool small = any_act && uw <= SB && uh <= SB;
-#if G2S_WARP_LOCAL
         // Does the tile queue anything at all?  Asked HERE, where the eight warps are still in lockstep (the barrier is
         // nearly free), not after the warp-local phases, where they have drifted apart: tiles of small quads only (the
         // interior) then finish warp by warp without another barrier.
         tile_queues = __syncthreads_or(any_act && !small);
-#endif
         if (any_act && !small) {
             // everything else becomes ROW TASKS: (face, row, 8-column segment), one lane each in the next phase
             if (A.act) push_row_tasks(sm, ops, recs, A, codeA, faceA, is);
@@ -612,7 +603,6 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
             maskA &= A.act ? vm : 0u;
             maskB &= B.act ? vm : 0u;
         }
-#if G2S_WARP_LOCAL
         // Small quads never leave their warp: the hits go to the warp's PRIVATE slice of the hit queue (offsets from a
         // warp scan, no shared-memory atomics), every lane builds the table entries of its own two triangles from the
         // registers it already holds, and the warp drains its slice after a __syncwarp -- no CTA barrier between scan,
@@ -659,41 +649,6 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
                 }
             }
         }
-#else
-        // queue the hits: one atomic per warp
-        int total;
-        const int off = warp_excl_scan(__popc(maskA) + __popc(maskB), &total);
-        if (total) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sm.n_hq, total);
-            base = __shfl_sync(0xffffffffu, base, 0) + off;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                unsigned m = k ? maskB : maskA;
-                const int code = k ? codeB : codeA;
-                while (m) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int xi = u.x0 + (bit & (SB - 1)), yi = u.y0 + bit / SB;
-                    if (base < HQ_CAP) {
-                        sm.hq_pix[base] = ((uint32_t)yi << 16) | (uint32_t)xi;
-                        sm.hq_code[base] = (uint16_t)code;
-                    } else {
-                        hit_inline(ops, k ? B.f : A.f, code, k ? faceB : faceA, xi, yi, is);
-                    }
-                    base++;
-                }
-            }
-            const int nown = (maskA ? 1 : 0) + (maskB ? 1 : 0);
-            int ftotal;
-            const int foff = warp_excl_scan(nown, &ftotal);
-            int fbase = 0;
-            if (lane == 0) fbase = atomicAdd(&sm.n_fq, ftotal);
-            fbase = __shfl_sync(0xffffffffu, fbase, 0) + foff;
-            if (maskA) sm.fq[fbase++] = (uint16_t)codeA;
-            if (maskB) sm.fq[fbase] = (uint16_t)codeB;
-        }
-#endif
         // degenerate triangles whose two windings both pass the back-face test (rounding): the reversed copy
         // bypasses the queues and the face table, whose slot the first winding owns
         if (A.dup) scan_degenerate(ops, reversed(A.f), A.bb, (tid * 2) | (1 << 9), Q, S, ty0, tx0);
@@ -702,11 +657,8 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
     // ---- rounds: scan as many queued row tasks as are guaranteed to fit the hit queue (8 hits per task at most),
     // build the table entries of the faces that scored for the first time, drain.  One round for ordinary tiles;
     // tiles full of long wall faces take several.
-#if G2S_WARP_LOCAL
     if (!tile_queues) return;   // interior tiles: nothing but small quads, no barrier
-#endif
     __syncthreads();
-#if G2S_EAGER_FT
     // Table entries of ALL queued faces now, one thread per face (from the top thread down: the expansion below keeps the
     // low warps busy), instead of lazily for the faces that scored in a round: that phase kept one or two warps busy while
     // six waited at its barrier, every round.
@@ -717,13 +669,9 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
             face_record(code_tri(sm.sv, code), is, &sm.ftab[ft_index(code) * FT_STRIDE]);
         }
     }
-#endif
     expand_queued_faces(sm, ops, recs, Q, S, ty0, tx0);
     const uint32_t* tq = sm.tq;
     int t0 = 0;
-#if !G2S_EAGER_FT
-    int nf_done = 0;
-#endif
     while (true) {
         __syncthreads();
         const int nt = min(sm.n_tq, TQ_CAP);
@@ -750,30 +698,8 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
                 mask |= (in ? 1u : 0u) << rx;
             }
             push_row_masks(sm, ops, mask, x0, yi, code, face, is);
-#if !G2S_EAGER_FT
-            // the first task of a face to score a hit requests the face's table entry
-            bool owner = false;
-            if (mask) owner = ((atomicOr(&sm.owned[(code & 511) >> 5], 1u << (code & 31)) >> (code & 31)) & 1u) == 0u;
-            const unsigned owners = __ballot_sync(0xffffffffu, owner);
-            if (owners) {
-                int fbase = 0;
-                if (lane == 0) fbase = atomicAdd(&sm.n_fq, __popc(owners));
-                fbase = __shfl_sync(0xffffffffu, fbase, 0);
-                if (owner) sm.fq[fbase + __popc(owners & ((1u << lane) - 1u))] = (uint16_t)code;
-            }
-#endif
         }
         __syncthreads();
-#if !G2S_EAGER_FT
-        // face table: one thread per face that owns a hit for the first time
-        const int nf = sm.n_fq;
-        for (int i = nf_done + tid; i < nf; i += SPLAT_THREADS) {
-            const int code = sm.fq[i];
-            face_record(code_tri(sm.sv, code), is, &sm.ftab[ft_index(code) * FT_STRIDE]);
-        }
-        nf_done = nf;
-        __syncthreads();
-#endif
         // drain the hit queue: one thread per hit
         const int nh = min(sm.n_hq, HQ_CAP);
         for (int i = tid; i < nh; i += SPLAT_THREADS) {
