@@ -179,14 +179,10 @@ k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, c
 #ifdef G2S_EXP_SKIP_INTERIOR
     if (!(tile_x == 0 || tile_x == tiles_x - 1)) return;
 #endif
-    if (!FROM_VERTS) {
-        if (tid < 9) sm.sRt[tid] = R[b * 9 + tid];
-        else if (tid < 12) sm.sRt[tid] = t[b * 3 + tid - 9];
-    }
     if (tid == 0) sm.n_hq = sm.n_tq = sm.n_wq = sm.n_mq = 0;
-    __syncthreads();
     tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
-                             FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, sm.sRt, ty0, tx0, sm.sv);
+                             FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, FROM_VERTS ? nullptr : R + b * 9,
+                             FROM_VERTS ? nullptr : t + b * 3, ty0, tx0, sm.sv);
     __syncthreads();
     FwdOps ops;
     ops.zb = zbuf + (long)bl * is * is;

@@ -56,7 +56,6 @@ struct TileSmem {
     uint16_t hq_code[HQ_CAP];
     uint16_t wq[NSLOT];          // wide faces whose rows a warp expands into tasks
     uint16_t mq[NSLOT];          // other queued faces
-    float sRt[12];
     int n_hq, n_tq, n_wq, n_mq;
 };
 
@@ -77,23 +76,53 @@ __device__ __forceinline__ Tri reversed(const Tri& f) {
     return r;
 }
 
+// Projects the tile's TV x TVH vertices into shared memory.  A thread owns vertex `tid` and, for the first few threads,
+// `tid + SPLAT_THREADS`; the per-vertex inputs (depth, or the 3-D point) of BOTH are requested first and the view's R, t
+// come as warp-uniform loads, so the tile starts with one memory round trip instead of two and without a barrier.
 template <bool FROM_VERTS>
 __device__ __forceinline__ void tile_project(const Cam& cam, const float* __restrict__ depth_b,
-                                             const float* __restrict__ verts_b, const float* sRt, int ty0,
-                                             int tx0, float* sv) {
+                                             const float* __restrict__ verts_b, const float* __restrict__ R_b,
+                                             const float* __restrict__ t_b, int ty0, int tx0, float* sv) {
     const int S = cam.S;
-    for (int i = threadIdx.x; i < TV * TVH; i += SPLAT_THREADS) {
+    constexpr int ROUNDS = (TV * TVH + SPLAT_THREADS - 1) / SPLAT_THREADS;
+    float in[ROUNDS][3];
+    bool live[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int i = threadIdx.x + r * SPLAT_THREADS;
         const int vy = ty0 + i / TV, vx = tx0 + i % TV;
-        float ndc[3] = {0.f, 0.f, 0.f};
-        if (vy < S && vx < S) {
-            float q[3];
+        live[r] = i < TV * TVH && vy < S && vx < S;
+        in[r][0] = in[r][1] = in[r][2] = 0.f;
+        if (live[r]) {
             if (FROM_VERTS) {
                 const float* p = &verts_b[((long)vy * S + vx) * 3];
-                q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+                in[r][0] = __ldg(p); in[r][1] = __ldg(p + 1); in[r][2] = __ldg(p + 2);
+            } else {
+                in[r][0] = __ldg(&depth_b[vy * S + vx]);
+            }
+        }
+    }
+    float Rt[12];
+    if (!FROM_VERTS) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rt[k] = __ldg(&R_b[k]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) Rt[9 + k] = __ldg(&t_b[k]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int i = threadIdx.x + r * SPLAT_THREADS;
+        if (r > 0 && !__any_sync(0xffffffffu, i < TV * TVH)) break;
+        if (i >= TV * TVH) continue;
+        float ndc[3] = {0.f, 0.f, 0.f};
+        if (live[r]) {
+            float q[3];
+            if (FROM_VERTS) {
+                q[0] = in[r][0]; q[1] = in[r][1]; q[2] = in[r][2];
             } else {
                 float ray[3];
-                pixel_ray(cam, vx, vy, ray);
-                warp_point(cam, sRt, sRt + 9, ray, depth_b[vy * S + vx], q);
+                pixel_ray(cam, tx0 + i % TV, ty0 + i / TV, ray);
+                warp_point(cam, Rt, Rt + 9, ray, in[r][0], q);
             }
             project_ndc(cam, q, ndc);
         }
