@@ -351,6 +351,41 @@ def run_ours(args):
         except Exception as exc:   # the headline numbers do not depend on this extra
             single = {"error": str(exc)[:200]}
 
+    # the other BASELINE.json configs that fit one GPU, measured in the same run (reported, not the headline):
+    #   configs[2] car: render_yaw sweep of 64 yaw angles at 128^2, forward only, both branches (renderer.py:141-198)
+    #   configs[3] face: ONE 256^2 image x 1024 pseudo-views, fwd+bwd (N > 1: tests/nccl_sharded_check.py shards its views)
+    other = None
+    if world == 1 and not args.no_single_image:
+        try:
+            with torch.no_grad():
+                car = synthetic.make_case(128, 1, seed=7, n_images=1)
+                ren128 = ren if S == 128 else g2s_b200.Renderer(dict(CFGS), 128, MIN_DEPTH, MAX_DEPTH, device=dev)
+                im_c, d_c = car["albedo"].to(dev), car["depth"].to(dev)
+                for gs in (False, True):
+                    ren128.render_yaw(im_c, d_c, maxr=90, nsample=64, grid_sample=gs)
+                reps = 50
+                ms_mesh = timed(lambda: ren128.render_yaw(im_c, d_c, maxr=90, nsample=64), reps) / reps
+                ms_gs = timed(lambda: ren128.render_yaw(im_c, d_c, maxr=90, nsample=64, grid_sample=True), reps) / reps
+            face = {k: v.to(dev) for k, v in synthetic.make_case(256, 1024, seed=11, n_images=1).items()}
+            ren256 = g2s_b200.Renderer(dict(CFGS), 256, MIN_DEPTH, MAX_DEPTH, device=dev)
+
+            def face_step():
+                d_, a_ = face["depth"].requires_grad_(True), face["albedo"].requires_grad_(True)
+                v_, l_ = face["view"].requires_grad_(True), face["light"].requires_grad_(True)
+                im_ = ren256.render_chain(d_, a_, v_, l_, views_per_image=1024)[0]
+                torch.autograd.grad([im_], [d_, a_, v_, l_], grad_outputs=[face["cotangent"]])
+
+            for _ in range(3):
+                face_step()
+            ms_face = timed(face_step, 5) / 5
+            other = {"car_render_yaw_64_at_128": {"mesh_texture_branch": {"ms_per_sweep": ms_mesh, "value": 64 / (ms_mesh * 1e-3)},
+                                                  "grid_sample_branch": {"ms_per_sweep": ms_gs, "value": 64 / (ms_gs * 1e-3)},
+                                                  "unit": "yaw renders/s (forward only)"},
+                     "face_1024_views_at_256": {"ms_per_step": ms_face, "value": 1024 / (ms_face * 1e-3), "unit": UNIT}}
+            del face, ren256
+        except Exception as exc:   # the headline numbers do not depend on these extras
+            other = {"error": str(exc)[:200]}
+
     threads = os.cpu_count() or 1
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -366,7 +401,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "single_image": single}
+            "single_image": single, "other_configs": other}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
