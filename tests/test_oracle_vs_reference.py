@@ -69,3 +69,29 @@ def test_oracle_vs_golden(name):
     with torch.no_grad():
         yaw = orc.render_yaw(torch.tensor(g["albedo"]), torch.tensor(g["depth"]), maxr=40, nsample=3)
     assert rel_err(yaw, g["render_yaw"]) < 1e-6
+
+
+@needs_ref
+def test_host_helpers_bit_identical_to_reference_utils():
+    """the package's host-side helpers (gan-2d-to-3d_b200/utils.py: same names, written independently) return the
+    reference's bits"""
+    import g2s_b200 as g
+    ru = _ref_utils()
+    gen = torch.Generator().manual_seed(3)
+    v = torch.randn(5, 6, generator=gen)
+    for w in (3, 5, 6):
+        (R, t), (R_ref, t_ref) = g.get_transform_matrices(v[:, :w]), ru.get_transform_matrices(v[:, :w])
+        assert torch.equal(R, R_ref) and torch.equal(t, t_ref)
+    with pytest.raises(Exception):
+        g.get_transform_matrices(v[:, :4])
+    assert torch.equal(g.get_face_idx(2, 7, 9), ru.get_face_idx(2, 7, 9))
+    for normalize in (True, False):
+        assert torch.equal(g.get_grid(2, 5, 6, normalize), ru.get_grid(2, 5, 6, normalize))
+    im = torch.rand(2, 3, 6, 7, generator=gen)
+    for tx in (1, 2):
+        assert torch.equal(g.get_textures_from_im(im, tx), ru.get_textures_from_im(im, tx))
+    torch.manual_seed(1)
+    x = g.rand_posneg_range(10, 1, 2)
+    torch.manual_seed(1)
+    assert torch.equal(x, ru.rand_posneg_range(10, 1, 2))
+    assert torch.equal(g.mm_normalize(im, -1, 1), ru.mm_normalize(im, -1, 1))
