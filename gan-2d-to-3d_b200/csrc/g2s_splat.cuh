@@ -647,12 +647,20 @@ __device__ __forceinline__ void tile_rasterise(TileSmem& sm, const Ops& ops, con
                 if (maskA) face_record(A.f, is, &sm.ftab[ft_index(tid * 2) * FT_STRIDE]);
                 if (maskB) face_record(B.f, is, &sm.ftab[ft_index(tid * 2 + 1) * FT_STRIDE]);
                 // one pass when the warp's hits fit its slice; otherwise the first triangles, then the second ones (a
-                // triangle has at most SB*SB hits, so either half always fits: no overflow path here)
-                static_assert(WQ_CAP >= 32 * SB * SB, "a warp's slice must hold one triangle per lane");
-                const int npass = total <= WQ_CAP ? 1 : 2;
+                // triangle has at most SB*SB hits), each in two halves of its box if the slice is smaller still: some
+                // split always fits, so there is no overflow path here
+                static_assert(WQ_CAP >= 32 * SB * SB / 2, "a warp's slice must hold half a triangle box per lane");
+                constexpr bool HALVES = WQ_CAP < 32 * SB * SB;
+                constexpr unsigned LOW = (1u << (SB * SB / 2)) - 1u;
+                const int npass = total <= WQ_CAP ? 1 : (HALVES ? 4 : 2);
 #pragma unroll 1
                 for (int pass = 0; pass < npass; pass++) {
-                    const unsigned mA = (npass == 2 && pass == 1) ? 0u : maskA, mB = (npass == 2 && pass == 0) ? 0u : maskB;
+                    unsigned mA = maskA, mB = maskB;
+                    if (npass > 1) {
+                        const int tri = HALVES ? pass >> 1 : pass;
+                        if (tri == 0) mB = 0u; else mA = 0u;
+                        if (HALVES) { const unsigned keep = (pass & 1) ? ~LOW : LOW; mA &= keep; mB &= keep; }
+                    }
                     int nh;
                     int base = warp_excl_scan(__popc(mA) + __popc(mB), &nh);
 #pragma unroll
