@@ -1048,10 +1048,12 @@ __device__ __constant__ float kCube[8][3] = {{0.5f, 0.5f, 0.5f}, {0.f, 0.f, 1.f}
                                              {1.f, 0.f, 0.f}, {0.5f, -0.5f, 0.5f}, {0.5f, 0.5f, -0.5f}, {0.f, 0.f, 0.f}};
 
 // colour of one covered sub-pixel: [nr] forward_texture_sampling with the 2^3 cube of utils.py:98-109
+// `coef` (optional): the colour is LINEAR in the three vertex colours, out[c] = sum_j coef[j] * im[c][cidx[j]]; [nr]
+// backward_textures chained through get_textures_from_im (utils.py:98-109) is the transpose of that map.
 template <int C>
 __device__ __forceinline__ void rgb_subpixel(const Cam& cam, const float* __restrict__ verts_b,
                                              const float* __restrict__ im_b, int face, int xi, int yi, float zp_key,
-                                             float eps, float out[C]) {
+                                             float eps, float out[C], float* coef = nullptr, int* cidx = nullptr) {
     const int S = cam.S, is = 2 * S, Q = (S - 1) * (S - 1);
     int vidx[3];
     face_vertices(face, S, vidx);
@@ -1108,6 +1110,79 @@ __device__ __forceinline__ void rgb_subpixel(const Cam& cam, const float* __rest
             acc += wt * tex;
         }
         out[c] = acc;
+    }
+    if (coef) {
+        coef[0] = coef[1] = coef[2] = 0.f;
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) {
+            float wt = 1.f;
+            int ti[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float fr = tif[k] - (float)(int)tif[k];
+                if (((pn >> k) & 1) == 0) { wt *= 1.f - fr; ti[k] = (int)tif[k]; }
+                else { wt *= fr; ti[k] = (int)tif[k] + 1; }
+            }
+            const int ci = rev ? ti[2] * 4 + ti[1] * 2 + ti[0] : ti[0] * 4 + ti[1] * 2 + ti[2];
+#pragma unroll
+            for (int j = 0; j < 3; j++) coef[j] += wt * kCube[ci][j];
+        }
+        cidx[0] = cp[0]; cidx[1] = cp[1]; cidx[2] = cp[2];
+    }
+}
+
+// Backward of k_resolve_rgb with respect to the per-vertex colours `im`: [nr] backward_textures + the autograd of
+// get_textures_from_im / fill_back / the 2x2 mean / clamp(-1,1).  One thread per output pixel; grad_im is ACCUMULATED with
+// atomics (im may be shared by all views).  The vertex (geometry) gradient of an rgb render -- [nr] backward_pixel_map,
+// an approximate edge gradient -- is not built (the reference never differentiates render_rgb, SURVEY.md 8a').
+template <int C>
+__global__ void __launch_bounds__(PIX_THREADS)
+k_resolve_rgb_bwd(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ verts3d,
+                  const float* __restrict__ im, long imstride, const Bg bg, float eps, int clampv,
+                  const float* __restrict__ grad_rgb, float* __restrict__ grad_im, long gstride) {
+    const int S = cam.S, is = 2 * S, b = blockIdx.y;
+    const int pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= S * S) return;
+    const int i = pix / S, j = pix - i * S;
+    const int* fm = face_idx + (long)b * is * is;
+    const int2 r0 = *reinterpret_cast<const int2*>(fm + (long)(2 * i) * is + 2 * j);
+    const int2 r1 = *reinterpret_cast<const int2*>(fm + (long)(2 * i + 1) * is + 2 * j);
+    const int faces[4] = {r0.x, r0.y, r1.x, r1.y};
+    const float* verts_b = verts3d + (long)b * S * S * 3;
+    const float* im_b = im + (long)b * imstride;
+    float sum[C], coef[4][3];
+    int cidx[4][3];
+#pragma unroll
+    for (int c = 0; c < C; c++) sum[c] = 0.f;
+#pragma unroll 1
+    for (int sp = 0; sp < 4; sp++) {
+        float col[C];
+        coef[sp][0] = coef[sp][1] = coef[sp][2] = 0.f;
+        cidx[sp][0] = cidx[sp][1] = cidx[sp][2] = 0;
+        if (faces[sp] < 0) {
+#pragma unroll
+            for (int c = 0; c < C; c++) col[c] = bg.c[c];
+        } else {
+            const int r = 2 * i + (sp >> 1), xi = 2 * j + (sp & 1);
+            rgb_subpixel<C>(cam, verts_b, im_b, faces[sp], xi, is - 1 - r, 0.f, eps, col, coef[sp], cidx[sp]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) sum[c] += col[c];
+    }
+    float* g_b = grad_im + (long)b * gstride;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const float v = sum[c] * 0.25f;
+        float g = grad_rgb[((long)b * C + c) * S * S + pix] * 0.25f;
+        if (clampv && !(v >= -1.f && v <= 1.f)) g = 0.f;
+        if (g == 0.f) continue;
+#pragma unroll
+        for (int sp = 0; sp < 4; sp++) {
+            if (faces[sp] < 0) continue;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (coef[sp][k] != 0.f) atomicAdd(&g_b[(long)c * S * S + cidx[sp][k]], g * coef[sp][k]);
+        }
     }
 }
 
@@ -1620,6 +1695,29 @@ int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const flo
         case 2: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<2><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
         case 3: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<3><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
         default: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<4><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
+    }
+    return launch_status();
+}
+
+int g2s_render_rgb_bwd(const g2s_camera* cam, const float* vertices3d, const float* im, long im_view_stride, int n_views,
+                       int C, int tex_cube_size, const float* bg, int clamp, const int32_t* face_idx, const float* grad_rgb,
+                       float* grad_im, long grad_im_view_stride, void* stream) {
+    if (!cam || !vertices3d || !im || !bg || !face_idx || !grad_rgb || !grad_im) return G2S_ERR_NULL;
+    if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size) || C < 1 || C > 4) return G2S_ERR_SHAPE;
+    if (tex_cube_size != 2) return G2S_ERR_UNSUPPORTED;
+    const Cam c = make_cam(cam);
+    const int S = c.S;
+    cudaStream_t st = (cudaStream_t)stream;
+    Bg b4 = {{0.f, 0.f, 0.f, 0.f}};
+    for (int i = 0; i < C; i++) b4.c[i] = bg[i];
+    const float eps = 1e-3f;  // nr.Renderer.rasterizer_eps
+    const dim3 g = pix_grid((long)S * S, n_views);
+    Launch l_(K_RESOLVE_RGB, st);
+    switch (C) {
+        case 1: k_resolve_rgb_bwd<1><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+        case 2: k_resolve_rgb_bwd<2><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+        case 3: k_resolve_rgb_bwd<3><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+        default: k_resolve_rgb_bwd<4><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
     }
     return launch_status();
 }

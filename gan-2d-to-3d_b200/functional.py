@@ -376,3 +376,63 @@ class RenderChainFn(torch.autograd.Function):
         gR = gR.sum_to_size(Rshape)
         gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
         return g_depth, g_albedo, gR, gt, gL, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------
+class RenderRgbFn(torch.autograd.Function):
+    """nr.Renderer.render_rgb(vertices, get_face_idx, get_textures_from_im(im, 2)) (+ clamp) as renderer.py:194-196,
+    230, 248, 272, 275 call it.  Differentiable with respect to `im` (the per-vertex colours: neural_renderer's
+    backward_textures through get_textures_from_im); the geometry gets no gradient (nr's approximate backward_pixel_map is
+    not built: the reference never differentiates render_rgb, SURVEY.md 8a')."""
+
+    @staticmethod
+    def forward(ctx, vertices3d, im, renderer, clamp):
+        _require_cuda(vertices3d, im)
+        lib = _lib.load()
+        B = vertices3d.shape[0]
+        Bi, C, H, W = im.shape
+        S = renderer.image_size
+        if H != S or W != S or Bi not in (1, B):
+            raise RuntimeError("render_rgb: image must be [B or 1,C,%d,%d]" % (S, S))
+        if C > 4:
+            raise RuntimeError("render_rgb: at most 4 channels")
+        if Bi == 1 and B > 1:                       # one image for all views (a sweep of one input)
+            istore, istride = _f32c(im[0]), 0
+        else:
+            istore, istride = _batched_image(im)
+        verts = _f32c(vertices3d)
+        cam = renderer._camera(rgb_pass=True)
+        zbuf = renderer._zbuf.get(B, S, cam.far_z, im.device)
+        out = torch.empty(B, C, S, S, device=im.device, dtype=torch.float32)
+        fidx = torch.empty(B, 2 * S, 2 * S, device=im.device, dtype=torch.int32)
+        bg = (ctypes.c_float * 4)(*([renderer.background_color[i % 3] for i in range(4)]))
+        _lib.check(lib.g2s_render_rgb_fwd(ctypes.byref(cam), _p(verts), _p(istore), istride, B, C, renderer.tex_cube_size,
+                                          bg, int(clamp), _p(zbuf), _p(out), _p(fidx), _stream()), "g2s_render_rgb_fwd")
+        ctx.save_for_backward(verts, istore, fidx)
+        ctx.meta = (renderer, int(clamp), istride, im.shape)
+        ctx.mark_non_differentiable(fidx)
+        ctx.set_materialize_grads(False)
+        return out, fidx
+
+    @staticmethod
+    def backward(ctx, g_out, _g_fidx):
+        if g_out is None or not ctx.needs_input_grad[1]:
+            return None, None, None, None
+        lib = _lib.load()
+        verts, istore, fidx = ctx.saved_tensors
+        renderer, clamp, istride, imshape = ctx.meta
+        C, S = imshape[1], imshape[2]
+        g = _f32c(g_out)
+        B = g.shape[0]
+        cam = renderer._camera(rgb_pass=True)
+        g_im = torch.zeros(istore.shape, device=g.device, dtype=torch.float32)    # [C,S,S] when shared, else [B,C,S,S]
+        bg = (ctypes.c_float * 4)(*([renderer.background_color[i % 3] for i in range(4)]))
+        _lib.check(lib.g2s_render_rgb_bwd(ctypes.byref(cam), _p(verts), _p(istore), istride, B, C, renderer.tex_cube_size,
+                                          bg, clamp, _p(fidx), _p(g), _p(g_im), istride, _stream()), "g2s_render_rgb_bwd")
+        if istride == 0:
+            if imshape[0] != 1:
+                # an `expand`ed [B,C,S,S] view of one image: autograd will sum B identical slices back onto it
+                g_im = (g_im / imshape[0]).unsqueeze(0).expand(imshape)
+            else:
+                g_im = g_im.unsqueeze(0)
+        return None, g_im, None, None

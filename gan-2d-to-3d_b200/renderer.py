@@ -192,23 +192,8 @@ class Renderer:
 
     def _render_rgb(self, vertices3d, im, clamp=True, return_face_idx=False):
         """nr.Renderer.render_rgb(vertices, get_face_idx, get_textures_from_im(im, tex_cube_size)) +
-        clamp(-1,1) (renderer.py:194-196).  Forward only (the reference never differentiates it)."""
-        lib = _lib.load()
-        B, C, H, W = im.shape
-        S = self.image_size
-        if H != S or W != S:
-            raise RuntimeError("render_rgb: image must be [B,C,%d,%d]" % (S, S))
-        if C > 4:
-            raise RuntimeError("render_rgb: at most 4 channels")
-        istore, istride = Fn._batched_image(im.detach())
-        cam = self._camera(rgb_pass=True)
-        zbuf = self._zbuf.get(B, S, cam.far_z, im.device)
-        out = torch.empty(B, C, S, S, device=im.device, dtype=torch.float32)
-        fidx = torch.empty(B, 2 * S, 2 * S, device=im.device, dtype=torch.int32) if return_face_idx else None
-        bg = (ctypes.c_float * 4)(*([self.background_color[i % 3] for i in range(4)]))
-        _lib.check(lib.g2s_render_rgb_fwd(ctypes.byref(cam), Fn._p(vertices3d), Fn._p(istore), istride, B, C,
-                                          self.tex_cube_size, bg, int(clamp), Fn._p(zbuf), Fn._p(out), Fn._p(fidx),
-                                          Fn._stream()), "g2s_render_rgb_fwd")
+        clamp(-1,1) (renderer.py:194-196).  Differentiable with respect to `im` only (Fn.RenderRgbFn)."""
+        out, fidx = Fn.RenderRgbFn.apply(vertices3d, im, self, clamp)
         return (out, fidx) if return_face_idx else out
 
     @staticmethod
@@ -242,7 +227,7 @@ class Renderer:
                 else:
                     va = rep(v_after.expand(b, v_after.shape[1]))
             verts = self._grid3d(depth_bt, crop_mesh, vb, R1, va)
-            warped = self._render_rgb(verts, im_bt)
+            warped = self._render_rgb(verts, im if b == 1 else im_bt)      # one image: shared by all T views
         return warped.reshape(b, T, c, h, w)
 
     def render_yaw(self, im, depth, v_before=None, v_after=None, rotations=None, maxr=90, nsample=9,

@@ -156,6 +156,16 @@ int g2s_render_rgb_fwd(const g2s_camera *cam, const float *vertices3d, const flo
                        int n_views, int C, int tex_cube_size, const float *bg, int clamp, void *zbuf,
                        float *rgb, int32_t *face_idx, void *stream);
 
+/* Backward of g2s_render_rgb_fwd with respect to the per-vertex colours `im`: neural_renderer's backward_textures chained
+ * through get_textures_from_im (utils.py:98-109), the fill_back texture permutation, the 2x2 mean and clamp(-1,1).
+ * face_idx [n_views,2S,2S] as written by the forward; grad_rgb [n_views,C,S,S]; grad_im is ACCUMULATED (caller zero-fills)
+ * with grad_im_view_stride floats between views (0 = one image shared by all views).  The geometry gradient of an rgb
+ * render (nr backward_pixel_map, an approximate edge gradient) is not provided: the reference never differentiates
+ * render_rgb (SURVEY.md 8a'). */
+int g2s_render_rgb_bwd(const g2s_camera *cam, const float *vertices3d, const float *im, long im_view_stride, int n_views,
+                       int C, int tex_cube_size, const float *bg, int clamp, const int32_t *face_idx,
+                       const float *grad_rgb, float *grad_im, long grad_im_view_stride, void *stream);
+
 /* ---- set_transform_matrices: utils.py:33-73 (view [B, 3|5|6] -> R = Rz Ry Rx [B,3,3], t [B,3]; other widths return
  * G2S_ERR_UNSUPPORTED as utils.py:70-71 raises) and get_lighting_directions: model.py:347-353 (raw light [B,4] ->
  * light5 [B,5] = ambient a, diffuse b, unit direction).  Backward: grad_R / grad_t may be NULL (zeros). */

@@ -98,17 +98,37 @@ def mm3(v, M):
     return Mm3.apply(v.reshape(shp[0], -1, 3), M).reshape(shp)
 
 
+class _MmK3(torch.autograd.Function):
+    """A[na,R,3] @ B[nb,3,C] (na, nb equal or 1) with the pinned fma chain; the backward uses plain matmuls (gradients are
+    compared to tolerance, not bit-for-bit)."""
+
+    @staticmethod
+    def forward(ctx, A, Bm):
+        R, C = A.shape[-2], Bm.shape[-1]
+        na, nb = A.shape[0], Bm.shape[0]
+        n = max(na, nb)
+        out = torch.empty(n, R, C)
+        lib().fma_mm_k3(_fp(A), _fp(Bm), _fp(out), n, R, C, 1 if na > 1 else 0, 1 if nb > 1 else 0)
+        ctx.save_for_backward(A, Bm)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        A, Bm = ctx.saved_tensors
+        gA = g.matmul(Bm.transpose(1, 2))
+        gB = A.transpose(1, 2).matmul(g)
+        if A.shape[0] == 1 and gA.shape[0] != 1:
+            gA = gA.sum(0, keepdim=True)
+        if Bm.shape[0] == 1 and gB.shape[0] != 1:
+            gB = gB.sum(0, keepdim=True)
+        return gA, gB
+
+
 def mm_k3(A, Bm):
-    """A[...,R,3] @ B[...,3,C] (forward only) with the pinned fma chain; batch dims equal or 1."""
-    A = A.detach().contiguous().float()
-    Bm = Bm.detach().contiguous().float()
-    R, C = A.shape[-2], Bm.shape[-1]
-    na = A.numel() // (R * 3)
-    nb = Bm.numel() // (3 * C)
-    n = max(na, nb)
-    out = torch.empty(n, R, C)
-    lib().fma_mm_k3(_fp(A), _fp(Bm), _fp(out), n, R, C, 1 if na > 1 else 0, 1 if nb > 1 else 0)
-    return out
+    """A[...,R,3] @ B[...,3,C] with the pinned fma chain; batch dims equal or 1."""
+    A3 = A.contiguous().float().reshape(-1, A.shape[-2], 3)
+    B3 = Bm.contiguous().float().reshape(-1, 3, Bm.shape[-1])
+    return _MmK3.apply(A3, B3)
 
 
 # Rasteriser mode for the whole oracle: "brute" = the faithful O(is^2 * nf) loop of the reference,

@@ -93,7 +93,7 @@ def vcolor_to_texture_cube(vcolors):
     b, c, n, f = vcolors.shape
     coeffs = torch.tensor(_CUBE, dtype=torch.float32)
     v = vcolors.permute(0, 2, 3, 1).reshape(b * n, 3, c)  # (b n) 3 c
-    return nr_port.mm_k3(coeffs.unsqueeze(0), v).reshape(b, n, 2, 2, 2, c)  # forward only
+    return nr_port.mm_k3(coeffs.unsqueeze(0), v).reshape(b, n, 2, 2, 2, c)
 
 
 def get_textures_from_im(im, tx_size=1):

@@ -364,6 +364,44 @@ def test_sweeps_and_given_view_vs_oracle(S, seed):
             assert close_except_few(m.cpu(), m_o, tol=1e-4)
 
 
+@pytest.mark.parametrize("S,seed", [(32, 61), (64, 62)])
+def test_render_rgb_texture_gradient_vs_oracle(S, seed):
+    """mesh-texture branch (render_yaw / render_given_view with grid_sample=False): gradient with respect to the image =
+    [nr] backward_textures through get_textures_from_im, the fill_back permutation, the 2x2 mean and the clamp.  The
+    geometry gets no gradient on either side (the oracle raises for it, the product returns None)."""
+    case = _case(S, 2, seed, 60.0)
+    orc, ren = oracle_renderer(S), _cuda_renderer(S)
+    depth = case["depth"]
+    gen = torch.Generator().manual_seed(seed)
+    im = case["albedo"] * 1.3                                       # some pixels beyond [-1,1]: the clamp masks their gradient
+    kw = dict(maxr=50, nsample=3)
+    im_o = im.clone().requires_grad_(True)
+    y_o = orc.render_yaw(im_o, depth, **kw)
+    cot = torch.randn(y_o.shape, generator=gen)
+    (y_o * cot).sum().backward()
+    im_c = im.cuda().requires_grad_(True)
+    y = ren.render_yaw(im_c, depth.cuda(), **kw)
+    (y * cot.cuda()).sum().backward()
+    assert close_except_few(y.detach().cpu(), y_o.detach(), tol=1e-4)
+    assert close_except_few(im_c.grad.cpu(), im_o.grad, tol=1e-4, frac=5e-3)
+    # render_given_view, two views of an `expand`ed image (stride-0 batch) and a materialised copy give the same gradient
+    P = 2
+    d2 = depth.expand(P, S, S)
+    cot2 = torch.randn(P, 3, S, S, generator=gen)
+    im_o2 = im.clone().requires_grad_(True)
+    a_o = orc.render_given_view(im_o2.expand(P, 3, S, S), d2, case["view"], grid_sample=False)
+    (a_o * cot2).sum().backward()
+    grads = []
+    for materialise in (False, True):
+        im_c2 = im.cuda().requires_grad_(True)
+        src = im_c2.expand(P, 3, S, S)
+        a = ren.render_given_view(src.contiguous() if materialise else src, d2.cuda(), case["view"].cuda(), grid_sample=False)
+        (a * cot2.cuda()).sum().backward()
+        grads.append(im_c2.grad.cpu())
+    assert rel_err(grads[0], grads[1]) < TOL
+    assert close_except_few(grads[0], im_o2.grad, tol=1e-4, frac=5e-3)
+
+
 # ---- size-independent properties at BASELINE.json's full sizes ----------------------------------------------------
 @pytest.mark.parametrize("S", [128, 256])
 def test_identity_flat_depth_known_answer_full_size(S):
