@@ -173,12 +173,6 @@ k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, c
         else { const int r = k - 2 * tiles_yy; tile_y = r / (tiles_x - 2); tile_x = 1 + r % (tiles_x - 2); }
     }
     const int ty0 = tile_y * TILE_H, tx0 = tile_x * TILE;
-#ifdef G2S_EXP_SKIP_BORDER   // timing experiment only (wrong results): which tiles the time goes to
-    if (tile_x == 0 || tile_x == tiles_x - 1) return;
-#endif
-#ifdef G2S_EXP_SKIP_INTERIOR
-    if (!(tile_x == 0 || tile_x == tiles_x - 1)) return;
-#endif
     if (tid == 0) sm.n_hq = sm.n_tq = sm.n_wq = sm.n_mq = 0;
     tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
                              FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, FROM_VERTS ? nullptr : R + b * 9,
