@@ -928,7 +928,14 @@ k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict_
     const float n0 = nimg[p * TEXEL], n1 = nimg[p * TEXEL + 1], n2 = nimg[p * TEXEL + 2];
     const float al[3] = {aimg[p], aimg[S * S + p], aimg[2 * S * S + p]};
     float ga[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f};
-    const int b0 = max(img * fa.vpi, fa.view0), b1 = min((img + 1) * fa.vpi, fa.view0 + nviews);
+    // the image's views inside this chunk, split over gridDim.z groups of threads (an image with many views -- the face
+    // config has 1024 -- would otherwise be a serial loop on too few threads)
+    int b0 = max(img * fa.vpi, fa.view0), b1 = min((img + 1) * fa.vpi, fa.view0 + nviews);
+    if (gridDim.z > 1) {
+        const int per = (b1 - b0 + (int)gridDim.z - 1) / (int)gridDim.z;
+        b0 += (int)blockIdx.z * per;
+        b1 = min(b1, b0 + per);
+    }
     for (int b = b0; b < b1; b++) {
         const float la = __ldg(&fa.light[b * 5]), lb = __ldg(&fa.light[b * 5 + 1]), dx = __ldg(&fa.light[b * 5 + 2]),
                     dy = __ldg(&fa.light[b * 5 + 3]), dz = __ldg(&fa.light[b * 5 + 4]);
@@ -954,11 +961,17 @@ k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict_
         const float ls = warp_reduce_halving<3>(lg, lane);
         if ((lane & 3) == 0 && li < 5 && ls != 0.f) atomicAdd(&grad_light[b * 5 + li], ls);
     }
-    if (live) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) grad_albedo[((long)img * 3 + c) * S * S + p] += ga[c];
+    if (live && b1 > b0) {
         float* o = grad_normal + ((long)img * S * S + p) * 3;
-        o[0] += gn[0]; o[1] += gn[1]; o[2] += gn[2];
+        if (gridDim.z > 1) {       // several groups share the (image, pixel)
+#pragma unroll
+            for (int c = 0; c < 3; c++) atomicAdd(&grad_albedo[((long)img * 3 + c) * S * S + p], ga[c]);
+            atomicAdd(&o[0], gn[0]); atomicAdd(&o[1], gn[1]); atomicAdd(&o[2], gn[2]);
+        } else {                   // one thread owns the (image, pixel): plain accumulation over the chunks
+#pragma unroll
+            for (int c = 0; c < 3; c++) grad_albedo[((long)img * 3 + c) * S * S + p] += ga[c];
+            o[0] += gn[0]; o[1] += gn[1]; o[2] += gn[2];
+        }
     }
 }
 
@@ -1600,8 +1613,17 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
           k_render_bwd_pixel<<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
                                                                          raster_ws_gsub(grad_sub_ws, nv, S), grad_tex_ws, grad_R, grad_t); }
         const int img_lo = (int)(v0 / views_per_image), img_hi = (int)((v0 + nv - 1) / views_per_image);
+        dim3 tex_grid = pix_grid((long)S * S, img_hi - img_lo + 1);
+        {   // enough CTAs to fill the GPU: split an image's views over up to 16 groups when there are few (image, pixel) blocks
+            const long ctas = (long)tex_grid.x * tex_grid.y;
+            long groups = ctas >= 2048 ? 1 : (2048 + ctas - 1) / ctas;
+            const long vmax = (views_per_image < nv ? views_per_image : nv) / 8;
+            if (groups > vmax) groups = vmax;
+            if (groups > 16) groups = 16;
+            tex_grid.z = (unsigned)(groups < 1 ? 1 : groups);
+        }
         { Launch l_(K_BWD_TEX, st);
-          k_render_bwd_tex<<<pix_grid((long)S * S, img_hi - img_lo + 1), PIX_THREADS, 0, st>>>(S, fa, nv, grad_tex_ws, grad_albedo,
+          k_render_bwd_tex<<<tex_grid, PIX_THREADS, 0, st>>>(S, fa, nv, grad_tex_ws, grad_albedo,
                                                                                              grad_normal_ws, grad_light); }
         launch_raster_bwd(c, depth, (long)S * S, views_per_image, R, t, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,
                           (long)S * S, grad_R, grad_t, st);
