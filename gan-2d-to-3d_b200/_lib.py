@@ -48,6 +48,8 @@ SIGNATURES = {
                                       _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_rgb_fwd": (_c_int, [_CAMP, _vp, _vp, _c_long, _c_int, _c_int, _c_int, ctypes.POINTER(_c_float),
                                     _c_int, _vp, _vp, _vp, _vp]),
+    "g2s_render_depth_fwd": (_c_int, [_CAMP, _vp, _c_int, _vp, _vp, _vp, _vp]),
+    "g2s_render_depth_bwd": (_c_int, [_CAMP, _vp, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_rgb_bwd": (_c_int, [_CAMP, _vp, _vp, _c_long, _c_int, _c_int, _c_int, ctypes.POINTER(_c_float), _c_int,
                                     _vp, _vp, _vp, _c_long, _vp]),
     "g2s_view_fwd": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp]),

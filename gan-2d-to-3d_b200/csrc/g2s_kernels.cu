@@ -722,6 +722,38 @@ k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, in
     reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
 }
 
+// the same for vertices given as 3-D points (the neural_renderer-level entry g2s_render_depth_*): projection only
+__global__ void __launch_bounds__(PIX_THREADS)
+k_project_points(const Cam cam, const float* __restrict__ verts3d, float* __restrict__ proj) {
+    const int S = cam.S, bl = blockIdx.y;
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (v >= S * S) return;
+    const float* p = verts3d + ((long)bl * S * S + v) * 3;
+    const float q[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    float ndc[3];
+    project_ndc(cam, q, ndc);
+    reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
+}
+
+// (u,v,z) NDC gradient -> gradient of the 3-D vertex ([nr] projection backward); WRITES grad_verts [chunk,S*S,3]
+__global__ void __launch_bounds__(PIX_THREADS)
+k_points_bwd(const Cam cam, const float* __restrict__ verts3d, const float* __restrict__ vgrad,
+             float* __restrict__ grad_verts) {
+    const int S = cam.S, bl = blockIdx.y;
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (v >= S * S) return;
+    const float4 gp = __ldcs(reinterpret_cast<const float4*>(vgrad) + (long)bl * S * S + v);
+    const float* p = verts3d + ((long)bl * S * S + v) * 3;
+    const float zz = __ldg(p + 2) + 1e-9f, iz = 1.0f / zz;
+    const float x_ = __ldg(p) * iz, y_ = __ldg(p + 1) * iz;
+    const float gup = gp.x * (2.0f / cam.os), gvp = -gp.y * (2.0f / cam.os);
+    const float gx_ = gup * cam.K[0] + gvp * cam.K[3], gy_ = gup * cam.K[1] + gvp * cam.K[4];
+    float* o = grad_verts + ((long)bl * S * S + v) * 3;
+    o[0] = gx_ * iz;
+    o[1] = gy_ * iz;
+    o[2] = gp.z - (gx_ * x_ + gy_ * y_) * iz;
+}
+
 __global__ void __launch_bounds__(RBX * RBY)
 k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
                 const float* __restrict__ proj, float* __restrict__ vgrad, int view0) {
@@ -1712,6 +1744,46 @@ int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const flo
         case 3: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<3><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
         default: { Launch l_(K_RESOLVE_RGB, st); k_resolve_rgb<4><<<g, PIX_THREADS, 0, st>>>(c, zb, vertices3d, im, im_view_stride, b4, eps, clamp, rgb, face_idx); } break;
     }
+    return launch_status();
+}
+
+int g2s_render_depth_fwd(const g2s_camera* cam, const float* vertices3d, int n_views, void* zbuf, float* depth_out,
+                         int32_t* face_idx, void* stream) {
+    if (!cam || !vertices3d || !zbuf || !depth_out) return G2S_ERR_NULL;
+    if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    Cam c = make_cam(cam);
+    c.clamp_lo = -3.402823466e38f;     // nr.render_depth does not clamp (renderer.py:122-124 does, afterwards)
+    c.clamp_hi = 3.402823466e38f;
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
+    cudaStream_t st = (cudaStream_t)stream;
+    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(n_views, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
+                                                                         (unsigned long long*)zbuf, tiles, 0); }
+    FusedArgs fa = {};
+    { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid2(S, n_views), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, depth_out,
+                                                                             face_idx, fa); }
+    return launch_status();
+}
+
+int g2s_render_depth_bwd(const g2s_camera* cam, const float* vertices3d, int n_views, const int32_t* face_idx,
+                         const float* grad_depth_out, float* raster_ws, float* grad_vertices, void* stream) {
+    if (!cam || !vertices3d || !face_idx || !grad_depth_out || !raster_ws || !grad_vertices) return G2S_ERR_NULL;
+    if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
+    const Cam c = make_cam(cam);
+    const int S = c.S;
+    const size_t img = (size_t)S * S;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* proj = raster_ws;
+    float* vgrad = proj + (size_t)n_views * 4 * img;
+    float* g_sub = raster_ws_gsub(raster_ws, n_views, S);
+    const long n = (long)n_views * S * S;
+    // flip + 2x2 mean backward: every sub-pixel of an output pixel gets a quarter of its cotangent (no clamp here)
+    { Launch l_(K_CLAMP_GRAD, st); k_clamp_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad_depth_out, grad_depth_out, -3.402823466e38f,
+                                                              3.402823466e38f, n, g_sub); }
+    cudaMemsetAsync(vgrad, 0, sizeof(float) * n_views * 4 * img, st);
+    { Launch l_(K_PROJECT, st); k_project_points<<<pix_grid((long)S * S, n_views), PIX_THREADS, 0, st>>>(c, vertices3d, proj); }
+    { Launch l_(K_RASTER_BWD, st);
+      k_raster_bwd_px<<<pix_grid2(S, n_views, RBX, RBY), dim3(RBX, RBY), 0, st>>>(c, face_idx, g_sub, proj, vgrad, 0); }
+    { Launch l_(K_VERTEX_BWD, st); k_points_bwd<<<pix_grid((long)S * S, n_views), PIX_THREADS, 0, st>>>(c, vertices3d, vgrad, grad_vertices); }
     return launch_status();
 }
 

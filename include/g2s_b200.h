@@ -156,6 +156,17 @@ int g2s_render_rgb_fwd(const g2s_camera *cam, const float *vertices3d, const flo
                        int n_views, int C, int tex_cube_size, const float *bg, int clamp, void *zbuf,
                        float *rgb, int32_t *face_idx, void *stream);
 
+/* ---- the neural_renderer-level boundary: nr.Renderer.render_depth(vertices, faces) as renderer.py:120 calls it ----
+ * vertices3d [n_views,S*S,3]: the 3-D vertices of the S x S grid mesh (faces = utils.py:76-80, fill_back) in camera
+ * space.  depth_out [n_views,S,S] = 2x2 mean of the 2S x 2S depth map, background = cam->far_z, NOT clamped (cam->clamp_*
+ * are ignored); face_idx may be NULL.  Backward = neural_renderer's backward_depth_map (approximate x/y gradient) +
+ * flip / mean + vertices_to_faces gather + projection: WRITES grad_vertices [n_views,S*S,3]; raster_ws as
+ * g2s_warp_depth_bwd's grad_sub_ws (n_views * 9 * S * S floats, 16-byte aligned). */
+int g2s_render_depth_fwd(const g2s_camera *cam, const float *vertices3d, int n_views, void *zbuf, float *depth_out,
+                         int32_t *face_idx, void *stream);
+int g2s_render_depth_bwd(const g2s_camera *cam, const float *vertices3d, int n_views, const int32_t *face_idx,
+                         const float *grad_depth_out, float *raster_ws, float *grad_vertices, void *stream);
+
 /* Backward of g2s_render_rgb_fwd with respect to the per-vertex colours `im`: neural_renderer's backward_textures chained
  * through get_textures_from_im (utils.py:98-109), the fill_back texture permutation, the 2x2 mean and clamp(-1,1).
  * face_idx [n_views,2S,2S] as written by the forward; grad_rgb [n_views,C,S,S]; grad_im is ACCUMULATED (caller zero-fills)
