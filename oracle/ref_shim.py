@@ -53,3 +53,28 @@ def make_renderer(image_size=128, min_depth=0.9, max_depth=1.1, cfgs=None):
     """Reference Renderer constructed as GAN2Shape/model.py:68 does (config.yml:25-27 values)."""
     cfgs = cfgs if cfgs is not None else {"rot_center_depth": 1.0, "fov": 10, "tex_cube_size": 2}
     return load().Renderer(cfgs, image_size, min_depth, max_depth)
+
+
+def load_with(nr_module, name):
+    """Loads a SECOND, independent copy of the reference's `GAN2Shape.renderer` package whose `import neural_renderer`
+    resolves to `nr_module` (e.g. g2s_b200.nr_compat: the product's drop-in for that import).  `name` = the module name
+    the copy is registered under."""
+    if not available():
+        raise RuntimeError("reference tree not present at " + REF_DIR)
+    saved = sys.modules.get("neural_renderer")
+    sys.modules["neural_renderer"] = nr_module
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF_DIR, "__init__.py"),
+                                                      submodule_search_locations=[REF_DIR])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules["neural_renderer"] = saved
+        else:
+            sys.modules.pop("neural_renderer", None)
+    return mod

@@ -95,3 +95,20 @@ def test_host_helpers_bit_identical_to_reference_utils():
     torch.manual_seed(1)
     assert torch.equal(x, ru.rand_posneg_range(10, 1, 2))
     assert torch.equal(g.mm_normalize(im, -1, 1), ru.mm_normalize(im, -1, 1))
+
+
+@needs_ref
+def test_reference_renderer_binds_to_nr_compat():
+    """the reference's own, unmodified renderer.py constructs against g2s_b200.nr_compat in place of `neural_renderer`
+    (renderer.py:6, 47-54) and reaches its render calls (renderer.py:120); there is no GPU in the build container, so the
+    call must stop at the product's no-CPU-fallback check, not before"""
+    import g2s_b200
+    pkg = ref_shim.load_with(g2s_b200.nr_compat, "_g2s_reference_renderer_on_nr_compat")
+    ren = pkg.Renderer({"rot_center_depth": 1.0, "fov": 10, "tex_cube_size": 2}, 32, 0.9, 1.1)
+    assert isinstance(ren.renderer, g2s_b200.nr_compat.Renderer)
+    assert ren.renderer.image_size == 32 and ren.renderer.far == 10.0 and ren.renderer.background_color == [1.0, 1.0, 1.0]
+    assert torch.equal(ren.renderer.K, ren.K[0])
+    ren.set_transform_matrices(torch.zeros(1, 6))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ren.warp_canon_depth(torch.ones(1, 32, 32))
