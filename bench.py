@@ -13,10 +13,14 @@ configs[1] (GAN2Shape cat config: 128^2, 16 pseudo-views per image) in its batch
 per-step working set (4.5 GB algorithmic) is far larger than the 126 MB L2 (timing rule: inputs larger than L2).
 
 Keys of the JSON line: see the round prompt; `value` = renders/s with inputs resident in HBM (CUDA events, max over
-ranks); `e2e` = the same through the public API with pinned HOST inputs copied in and the gradients + loss copied out
-every step; `roofline` = live CUDA-event timing of every kernel of the step (g2s_profile_*), algorithmic bytes from
-SURVEY.md 8(d); `cpu_baseline` = the oracle (reference renderer.py on torch-CPU + the C restatement of the external
-rasteriser's brute-force loop) on a bounded sample.
+ranks; the loss is SURVEY.md 8d's fixed device-resident cotangent on recon_im, handed straight to the backward; nothing but
+the step is in the stream); `e2e` = the same through hostio.HostRenderStep with pinned HOST inputs copied in and the four
+gradients copied out every step (two slots, three streams: the copies of neighbouring steps overlap the kernels, all
+inside the timed region); `roofline` = a second pass with a CUDA-event pair around every kernel (g2s_profile_*; single
+forward lane so that kernels do not overlap), algorithmic bytes from SURVEY.md 8(d); `cpu_baseline` = the oracle (reference
+renderer.py on torch-CPU + the C restatement of the external rasteriser's brute-force loop) on a bounded sample;
+`single_image` = the literal configs[1] shape (1 image x 16 views) eager and as a CUDA graph; `other_configs` = the car
+(64-yaw render_yaw sweep) and face (256^2 x 1024 views) configs of BASELINE.json on one GPU.
 """
 import argparse
 import ctypes
