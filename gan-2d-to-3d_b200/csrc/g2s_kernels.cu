@@ -881,7 +881,8 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
 // Writes per-view texture gradients (atomics into grad_tex_ws), the masked quarter gradient of
 // recon_depth (g_sub) and accumulates grad_R / grad_t.  grad_tex / g_sub are indexed by the LOCAL view
 // (chunked launches), everything else by the global view fa.view0 + blockIdx.z.
-__global__ void __launch_bounds__(BPX * BPY)
+// 12 CTAs of 128 threads per SM (40 registers): measured best of 1 / 12 / 16 (54-64 / 40 / 32 registers + spills)
+__global__ void __launch_bounds__(BPX * BPY, 12)
 k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ recon_depth,
                    const float* __restrict__ grad_recon_im, const float* __restrict__ grad_recon_depth,
                    float* __restrict__ g_sub, float* __restrict__ grad_tex, float* __restrict__ grad_R,
