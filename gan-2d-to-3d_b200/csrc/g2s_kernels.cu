@@ -1363,6 +1363,27 @@ __global__ void k_selftest_raster(unsigned long long per_thread, unsigned seed, 
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// face_vertices' device path (reciprocal estimate + one fix-up) against plain integer arithmetic, for EVERY face index of
+// an S x S grid mesh including the fill_back copies
+__global__ void k_selftest_face_vertices(int S, unsigned long long* mismatches) {
+    const long Q = (long)(S - 1) * (S - 1), n = 4 * Q;
+    unsigned long long bad = 0;
+    for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (long)gridDim.x * blockDim.x) {
+        int v[3];
+        face_vertices((int)f, S, v);
+        long g = f;
+        const bool rev = g >= 2 * Q;
+        if (rev) g -= 2 * Q;
+        const bool second = g >= Q;
+        if (second) g -= Q;
+        const long qy = g / (S - 1), qx = g % (S - 1), v00 = qy * S + qx;
+        long a = second ? v00 + 1 : v00, b = v00 + S, c = second ? v00 + S + 1 : v00 + 1;
+        if (rev) { const long t = a; a = c; c = t; }
+        bad += (v[0] != a) + (v[1] != b) + (v[2] != c);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 inline dim3 pix_grid2(int S, int views, int bx = PBX, int by = PBY) { return dim3((S + bx - 1) / bx, (S + by - 1) / by, views); }
 
 // views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
@@ -1816,6 +1837,13 @@ int g2s_selftest_division(unsigned long long n_pairs, unsigned seed, unsigned lo
     const int blocks = 148 * 8, threads = 256;
     const unsigned long long per = (n_pairs + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
     k_selftest_division<<<blocks, threads, 0, (cudaStream_t)stream>>>(per, seed, mismatches_dev);
+    return launch_status();
+}
+
+int g2s_selftest_face_vertices(int image_size, unsigned long long* mismatches_dev, void* stream) {
+    if (!mismatches_dev) return G2S_ERR_NULL;
+    if (bad_size(image_size)) return G2S_ERR_SHAPE;
+    k_selftest_face_vertices<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(image_size, mismatches_dev);
     return launch_status();
 }
 

@@ -251,6 +251,9 @@ long g2s_launch_count(void);
 /* g2s_selftest_division: compares the kernels' shared-reciprocal division with IEEE __fdiv_rn on n_pairs pseudo-random
  * operand pairs and ADDS the number of mismatching results to *mismatches_dev (device, caller zero-fills). */
 int g2s_selftest_division(unsigned long long n_pairs, unsigned seed, unsigned long long *mismatches_dev, void *stream);
+/* g2s_selftest_face_vertices: the kernels' face-index -> vertex-index map (division by S-1 through a reciprocal estimate
+ * and one fix-up) against plain integer arithmetic for every face of an image_size^2 grid mesh; ADDS mismatches. */
+int g2s_selftest_face_vertices(int image_size, unsigned long long *mismatches_dev, void *stream);
 /* g2s_selftest_raster: compares the rasteriser's fast per-face / per-hit arithmetic (shared reciprocals, structural
  * operand-range guards) with the plain IEEE formulation bit for bit on n_triangles pseudo-random triangles (ordinary,
  * degenerate and extreme-magnitude ones, 4 sub-pixels each) and ADDS the number of mismatches to *mismatches_dev. */

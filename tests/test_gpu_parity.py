@@ -485,6 +485,19 @@ def test_shared_reciprocal_division_is_ieee_exact():
     assert int(bad.item()) == 0
 
 
+def test_face_index_division_exact_for_every_face():
+    """face index -> vertex indices on the device (reciprocal estimate + fix-up) == integer arithmetic, every face, sizes up
+    to the largest supported"""
+    import ctypes
+    from g2s_b200 import _lib
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for S in (2, 3, 17, 33, 128, 255, 256, 1000, 2047, 2048):
+        _lib.check(lib.g2s_selftest_face_vertices(S, ctypes.c_void_p(bad.data_ptr()), None), "selftest_face_vertices")
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
 def test_raster_fast_path_equals_ieee_path():
     """the per-face / per-hit fast arithmetic (shared reciprocals, structural operand-range guards) must equal the plain
     IEEE formulation bit for bit, including on degenerate and extreme-magnitude triangles that take the fall-backs"""
