@@ -1,4 +1,4 @@
-"""A/B harness: python scratch/exp.py [name=lib.so ...] -- runs bench.py once per library variant, prints per-kernel ms."""
+"""A/B harness: python profiles/tools/ab_bench.py [name=lib.so ...] -- runs bench.py once per library variant, prints per-kernel ms."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 extra = [a for a in sys.argv[1:] if a.startswith("--")]
