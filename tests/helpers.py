@@ -28,6 +28,29 @@ def rel_err(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
+def el_err(a, b, floor_frac=1e-2):
+    """ELEMENT-WISE relative error with an absolute floor: max_i |a_i - b_i| / (|b_i| + floor_frac * max|b|).
+    `rel_err` normalises every element by max|b|; this one holds small elements to (almost) their own scale.  The floor
+    keeps elements that are zero up to accumulation noise (an fp32 ulp of the largest terms: ~1e-7 max|b|) (float atomics, fp32 sums) from dividing by nothing."""
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    floor = floor_frac * b.abs().max().clamp_min(1e-30)
+    return ((a - b).abs() / (b.abs() + floor)).max().item()
+
+
+_STATS = os.path.join(ROOT, "gpurun_out", "parity_stats.jsonl")
+
+
+def log_stats(test, **kw):
+    """append the measured errors of a parity test to gpurun_out/parity_stats.jsonl (read back after a gpurun call)"""
+    import json
+    try:
+        os.makedirs(os.path.dirname(_STATS), exist_ok=True)
+        with open(_STATS, "a") as f:
+            f.write(json.dumps(dict(test=test, **kw)) + "\n")
+    except OSError:
+        pass
+
+
 # ---- emu harness (product arithmetic headers compiled for the host) -------------------------------------------
 class EmuCam(ctypes.Structure):
     _fields_ = [("K", ctypes.c_float * 9), ("invK", ctypes.c_float * 9), ("rcd", ctypes.c_float),
