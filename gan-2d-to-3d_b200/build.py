@@ -11,7 +11,8 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(CSRC, "g2s_kernels.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "g2s_math.cuh"), os.path.join(CSRC, "g2s_raster.cuh"),
-                  os.path.join(CSRC, "g2s_splat.cuh"), os.path.join(CSRC, "g2s_callers.cuh"),
+                  os.path.join(CSRC, "g2s_splat.cuh"), os.path.join(CSRC, "g2s_tile.cuh"),
+                  os.path.join(CSRC, "g2s_bigface.cuh"), os.path.join(CSRC, "g2s_callers.cuh"),
                   os.path.join(ROOT, "include", "g2s_b200.h")]
 LIB = os.path.join(CSRC, "libg2s_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -40,7 +41,7 @@ def build_variant(out, defines):
     """Kernel A/B experiments: the same sources with extra -D flags into `out` (selected at run time with G2S_LIB=...)."""
     cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-o", out] + SOURCES
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/g2s_b200.h"
-#include "g2s_splat.cuh"
+#include "g2s_bigface.cuh"
 
 using namespace g2s;
 
@@ -42,10 +42,10 @@ Cam make_cam(const g2s_camera* c) {
 
 
 // ---- instrumentation: launch counter + optional CUDA-event timing of every kernel (bench.py / tests) ----
-enum KernelId { K_ZINIT, K_SPLAT, K_RESOLVE, K_RESOLVE_FUSED, K_GRID_FWD, K_GRID_BWD, K_NORMAL_FWD, K_NORMAL_BWD,
+enum KernelId { K_ZINIT, K_SPLAT, K_SPLAT_BIG, K_RESOLVE, K_RESOLVE_FUSED, K_GRID_FWD, K_GRID_BWD, K_NORMAL_FWD, K_NORMAL_BWD,
                 K_SAMPLE_FWD, K_SAMPLE_BWD, K_CLAMP_GRAD, K_RASTER_BWD, K_BWD_PIXEL, K_BWD_TEX, K_GRID3D, K_RESOLVE_RGB,
                 K_PROJECT, K_VERTEX_BWD, K_VIEW, K_LIGHT, K_CLAMPED_DEPTH, K_SHADING, K_PHOTOMETRIC, K_SMOOTH, K_COUNT };
-const char* const kKernelNames[K_COUNT] = {"k_zbuf_init", "k_splat", "k_resolve", "k_resolve_fused", "k_warp_grid_fwd",
+const char* const kKernelNames[K_COUNT] = {"k_zbuf_init", "k_splat_tile", "k_splat_big", "k_resolve", "k_resolve_fused", "k_warp_grid_fwd",
                                            "k_warp_grid_bwd", "k_normal_fwd", "k_normal_bwd", "k_sample_fwd",
                                            "k_sample_bwd", "k_clamp_grad", "k_raster_bwd_px", "k_render_bwd_pixel",
                                            "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb", "k_project_verts",
@@ -149,40 +149,34 @@ __global__ void k_zbuf_init(unsigned long long* zb, long n, unsigned long long k
     for (; i < n; i += stride) zb[i] = key;
 }
 
-// Forward rasterisation of the grid mesh of one view into the packed-key z-buffer (g2s_splat.cuh).
-// grid = (tiles, n_views), block = TILE*TILE threads (one per quad).
-#ifndef G2S_SPLAT_MINBLOCKS
-#define G2S_SPLAT_MINBLOCKS (512 / SPLAT_THREADS)
+// Forward rasterisation of the grid mesh into the packed-key z-buffer, stage 1 (g2s_tile.cuh): one CTA per 16 x 16 block
+// of quads of one view, grid = (views, tiles).  4 CTAs per SM (64 registers), 37 KB of static shared memory.
+#ifndef G2S_TILE_MINBLOCKS
+#define G2S_TILE_MINBLOCKS 4
 #endif
+template <bool FROM_VERTS, bool POW2>
+__global__ void __launch_bounds__(SPLAT_THREADS, G2S_TILE_MINBLOCKS)
+k_splat_tile(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+             const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
+             const WorkList wl, int tiles_x, int view0) {
+    __shared__ TileSmem2 sm;
+    const int bl = blockIdx.x, b = view0 + bl, S = cam.S, is = 2 * S;
+    const int tile_y = blockIdx.y / tiles_x, tile_x = blockIdx.y % tiles_x;
+    splat_tile_body<FROM_VERTS, POW2>(sm, cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
+                                FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, FROM_VERTS ? nullptr : R + (long)b * 9,
+                                FROM_VERTS ? nullptr : t + (long)b * 3, zbuf + (long)bl * is * is, wl, bl, tile_y * TILE_H,
+                                tile_x * TILE);
+}
+
+// stage 2 (g2s_bigface.cuh): persistent CTAs pull the faces stage 1 deferred (long walls, degenerate quads) from the work list
 template <bool FROM_VERTS>
-__global__ void __launch_bounds__(SPLAT_THREADS, G2S_SPLAT_MINBLOCKS)
-k_splat(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
-        const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
-        int tiles_x, int view0) {
+__global__ void __launch_bounds__(BIG_THREADS, 2)
+k_splat_big(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+            const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
+            const WorkList wl, int view0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
-    // grid = (views, tiles): consecutive CTAs are the same tile of consecutive views.  Tile order: the left / right
-    // border columns first -- under yaw they hold the long depth-step wall faces (model.py:341-344) and take several
-    // times longer than interior tiles, so starting them first keeps them out of the launch tail.
-    const int tid = threadIdx.x, bl = blockIdx.x, b = view0 + bl, S = cam.S, is = 2 * S;
-    int tile_x, tile_y;
-    {
-        const int k = blockIdx.y, tiles_yy = gridDim.y / tiles_x;
-        if (tiles_x < 3) { tile_y = k / tiles_x; tile_x = k % tiles_x; }
-        else if (k < 2 * tiles_yy) { tile_y = k >> 1; tile_x = (k & 1) ? tiles_x - 1 : 0; }
-        else { const int r = k - 2 * tiles_yy; tile_y = r / (tiles_x - 2); tile_x = 1 + r % (tiles_x - 2); }
-    }
-    const int ty0 = tile_y * TILE_H, tx0 = tile_x * TILE;
-    if (tid == 0) sm.n_hq = sm.n_tq = sm.n_wq = sm.n_mq = 0;
-    tile_project<FROM_VERTS>(cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
-                             FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, FROM_VERTS ? nullptr : R + b * 9,
-                             FROM_VERTS ? nullptr : t + b * 3, ty0, tx0, sm.sv);
-    __syncthreads();
-    FwdOps ops;
-    ops.zb = zbuf + (long)bl * is * is;
-    ops.near = cam.near; ops.far = cam.far; ops.is = is;
-    ops.pc.init(is);
-    tile_rasterise(sm, ops, cam, ty0, tx0);
+    BigSmem& sm = *reinterpret_cast<BigSmem*>(smem_raw);
+    splat_big_body<FROM_VERTS>(sm, cam, depth, dstride, vpi, R, t, verts3d, zbuf, wl, view0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -807,7 +801,7 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         unsigned bad = 0;
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-            const float yz = G2S_FT_SEEDS ? rec[12 + m] : rcp_seed(z[m]);
+            const float yz = rcp_seed(z[m]);
             qd[m] = div_core(rec[3 * m], z[m], yz);
             qd[3 + m] = div_core(rec[3 * m + 1], z[m], yz);
             bad = max(bad, rec[3 * m] == 0.0f ? 0u : range_key(rec[3 * m]));
@@ -1275,15 +1269,57 @@ k_resolve_rgb(const Cam cam, unsigned long long* __restrict__ zbuf, const float*
     }
 }
 
-// k_splat needs > 48 KB of shared memory: opt in once per device context
-inline void raster_smem_optin() {
-    static std::once_flag once;
-    std::call_once(once, [] {
-        cudaFuncSetAttribute(k_splat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
-        cudaFuncSetAttribute(k_splat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
-    });
+// per-device facts the launchers need: SM count, and the > 48 KB dynamic shared-memory opt-in of k_splat_big (the
+// attribute is per device: a process that uses a second GPU must opt in there as well)
+struct DeviceInfo { bool ready; int sms; };
+inline const DeviceInfo* device_info() {
+    static std::mutex mu;
+    static DeviceInfo info[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    DeviceInfo& d = info[dev];
+    if (!d.ready) {
+        if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sms <= 0) return nullptr;
+        if (cudaFuncSetAttribute(k_splat_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(k_splat_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)) != cudaSuccess)
+            return nullptr;
+        d.ready = true;
+    }
+    return &d;
 }
-inline size_t fwd_smem_bytes() { raster_smem_optin(); return sizeof(TileSmem); }
+
+// Layout of a z-buffer workspace laid out for `cap` views: keys [cap, 2S, 2S] | work list [cap * 4 (S-1)^2] | 8 counter
+// words.  Every word is the EMPTY key at rest (g2s_zbuffer_init; every forward leaves it so), whatever `cap` it is later
+// laid out for.
+inline size_t ws_words(long cap, int S) { return (size_t)cap * (4ul * S * S + 4ul * (S - 1) * (S - 1)) + 8ul; }
+inline WorkList ws_worklist(unsigned long long* ws, long cap, int S, float far_z) {
+    WorkList wl;
+    wl.items = ws + (size_t)cap * 4ul * S * S;
+    wl.ctr = wl.items + (size_t)cap * 4ul * (S - 1) * (S - 1);
+    wl.bias = zkey_empty(far_z);
+    return wl;
+}
+
+// both stages of the forward rasteriser for `nv` views (view0 .. view0 + nv - 1) into workspace `ws` (capacity >= nv views)
+template <bool FROM_VERTS>
+inline int launch_splat(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
+                        const float* verts3d, unsigned long long* ws, long cap, int nv, int view0, cudaStream_t st) {
+    const DeviceInfo* di = device_info();
+    if (!di) return G2S_ERR_LAUNCH;
+    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
+    const WorkList wl = ws_worklist(ws, cap, S, c.far);
+    { Launch l_(K_SPLAT, st);
+      const dim3 grid(nv, tiles * tiles_y);
+      if (((2 * S) & (2 * S - 1)) == 0)     // power-of-two side: sub-pixel centres are exact products
+          k_splat_tile<FROM_VERTS, true><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, tiles, view0);
+      else
+          k_splat_tile<FROM_VERTS, false><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, tiles, view0); }
+    { Launch l_(K_SPLAT_BIG, st);
+      k_splat_big<FROM_VERTS><<<di->sms * 2, BIG_THREADS, sizeof(BigSmem), st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl,
+                                                                                view0); }
+    return G2S_OK;
+}
 
 // compares the shared-reciprocal division (g2s_math.cuh dvd_y) with __fdiv_rn bit for bit on pseudo-random operands
 __global__ void k_selftest_division(unsigned long long per_thread, unsigned seed, unsigned long long* mismatches) {
@@ -1442,14 +1478,15 @@ const char* g2s_error_string(int code) {
 }
 
 size_t g2s_zbuffer_bytes(int n_views, int image_size) {
-    if (n_views <= 0 || image_size <= 0) return 0;
-    return (size_t)n_views * (size_t)(2 * image_size) * (size_t)(2 * image_size) * sizeof(unsigned long long);
+    if (n_views <= 0 || bad_size(image_size)) return 0;
+    // keys + work list + counters, with room for the counter words of MAX_LANES separately laid out parts
+    return (ws_words(n_views, image_size) + 8ul * MAX_LANES) * sizeof(unsigned long long);
 }
 
 int g2s_zbuffer_init(void* zbuf, int n_views, int image_size, float far_z, void* stream) {
     if (!zbuf) return G2S_ERR_NULL;
     if (n_views <= 0 || bad_size(image_size)) return G2S_ERR_SHAPE;
-    const long n = (long)n_views * 4 * image_size * image_size;
+    const long n = (long)(g2s_zbuffer_bytes(n_views, image_size) / sizeof(unsigned long long));
     const int blocks = (int)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
     { Launch l_(K_ZINIT, (cudaStream_t)stream); k_zbuf_init<<<blocks, 256, 0, (cudaStream_t)stream>>>((unsigned long long*)zbuf, n, zkey_empty(far_z)); }
     return launch_status();
@@ -1460,10 +1497,10 @@ int g2s_warp_depth_fwd(const g2s_camera* cam, const float* depth, long depth_vie
     if (!cam || !depth || !R || !t || !zbuf || !recon_depth) return G2S_ERR_NULL;
     if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size)) return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
+    const int S = c.S;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<false><<<dim3(n_views, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, depth, depth_view_stride, 1, R, t,
-                                                                          nullptr, (unsigned long long*)zbuf, tiles, 0); }
+    if (int rc = launch_splat<false>(c, depth, depth_view_stride, 1, R, t, nullptr, (unsigned long long*)zbuf, n_views, n_views, 0, st))
+        return rc;
     FusedArgs fa = {};
     { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid2(S, n_views), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, recon_depth,
                                                                              face_idx, fa); }
@@ -1580,7 +1617,7 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
     if (n_images <= 0 || views_per_image <= 0 || n_views > (1L << 30) || ws_views <= 0 || bad_size(cam->image_size))
         return G2S_ERR_SHAPE;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
+    const int S = c.S;
     cudaStream_t st = (cudaStream_t)stream;
     for (int i0 = 0; i0 < n_images; i0 += 32768) {
         const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;
@@ -1616,10 +1653,9 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
     for (long v0 = 0; v0 < n_views; v0 += chunk, lane = (lane + 1) % nl) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         cudaStream_t ls = lanes[lane];
-        unsigned long long* zb = (unsigned long long*)zbuf + (size_t)lane * chunk * 4 * S * S;
-        { Launch l_(K_SPLAT, ls);
-          k_splat<false><<<dim3(nv, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), ls>>>(c, depth, (long)S * S, views_per_image, R, t, nullptr,
-                                                                           zb, tiles, (int)v0); }
+        unsigned long long* zb = (unsigned long long*)zbuf + (size_t)lane * ws_words(chunk, S);   // this lane's part
+        if (int rc = launch_splat<false>(c, depth, (long)S * S, views_per_image, R, t, nullptr, zb, chunk, nv, (int)v0, ls))
+            return rc;
         FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0, mask_in, mask_out};
         { Launch l_(K_RESOLVE_FUSED, ls);
           k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, ls>>>(c, zb, recon_depth, face_idx, fa); }
@@ -1751,10 +1787,10 @@ int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const flo
     if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size) || C < 1 || C > 4) return G2S_ERR_SHAPE;
     if (tex_cube_size != 2) return G2S_ERR_UNSUPPORTED;
     const Cam c = make_cam(cam);
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
+    const int S = c.S;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(n_views, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
-                                                                         (unsigned long long*)zbuf, tiles, 0); }
+    if (int rc = launch_splat<true>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d, (unsigned long long*)zbuf, n_views, n_views, 0, st))
+        return rc;
     Bg b4 = {{0.f, 0.f, 0.f, 0.f}};
     for (int i = 0; i < C; i++) b4.c[i] = bg[i];
     const float eps = 1e-3f;  // nr.Renderer.rasterizer_eps
@@ -1776,10 +1812,10 @@ int g2s_render_depth_fwd(const g2s_camera* cam, const float* vertices3d, int n_v
     Cam c = make_cam(cam);
     c.clamp_lo = -3.402823466e38f;     // nr.render_depth does not clamp (renderer.py:122-124 does, afterwards)
     c.clamp_hi = 3.402823466e38f;
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
+    const int S = c.S;
     cudaStream_t st = (cudaStream_t)stream;
-    { Launch l_(K_SPLAT, st); k_splat<true><<<dim3(n_views, tiles * tiles_y), SPLAT_THREADS, fwd_smem_bytes(), st>>>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d,
-                                                                         (unsigned long long*)zbuf, tiles, 0); }
+    if (int rc = launch_splat<true>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d, (unsigned long long*)zbuf, n_views, n_views, 0, st))
+        return rc;
     FusedArgs fa = {};
     { Launch l_(K_RESOLVE, st); k_resolve<false><<<pix_grid2(S, n_views), dim3(PBX, PBY), 0, st>>>(c, (unsigned long long*)zbuf, depth_out,
                                                                              face_idx, fa); }

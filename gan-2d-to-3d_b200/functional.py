@@ -74,10 +74,10 @@ class ZBuffer:
 
     def get(self, n_views, S, far, device):
         key = (float(far), device)
-        need = n_views * 4 * S * S
+        lib = _lib.load()
+        need = (lib.g2s_zbuffer_bytes(n_views, S) + 7) // 8     # keys + work list + counters
         cur = self.buf.get(key)
         if cur is None or cur.numel() < need:
-            lib = _lib.load()
             cur = torch.empty(need, dtype=torch.int64, device=device)
             # the buffer is addressed per view, so initialise it as `n_views` views of side S
             _lib.check(lib.g2s_zbuffer_init(_p(cur), n_views, S, far, _stream()), "g2s_zbuffer_init")

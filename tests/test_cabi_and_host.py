@@ -37,7 +37,8 @@ def test_argument_validation_returns_error_codes_without_touching_the_gpu():
     cam = _lib.Camera()
     cam.image_size = 16
     null = ctypes.c_void_p(None)
-    assert lib.g2s_zbuffer_bytes(3, 16) == 3 * 32 * 32 * 8
+    # keys [3, 32, 32] + work list [3 * 4 * 15^2] + counter words (8 + 8 per lane part), 8 bytes each
+    assert lib.g2s_zbuffer_bytes(3, 16) == (3 * (32 * 32 + 4 * 15 * 15) + 8 + 8 * 4) * 8
     assert lib.g2s_zbuffer_bytes(0, 16) == 0
     assert lib.g2s_zbuffer_init(null, 1, 16, 100.0, null) == -1
     assert lib.g2s_warp_depth_fwd(ctypes.byref(cam), null, 0, null, null, 1, null, null, null, null) == -1
