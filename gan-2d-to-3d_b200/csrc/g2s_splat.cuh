@@ -148,6 +148,30 @@ __device__ __forceinline__ int queue_alloc(int* counter) {
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
+// Warp sums of 2^LOG per-lane values by RECURSIVE HALVING: at every step a lane hands one half of its values to its
+// partner and keeps the other, so 2^LOG values cost 2^LOG - 1 + (5 - LOG) shuffles instead of 5 * 2^LOG butterflies
+// (16 instead of 80 for the 12 entries of grad_R | grad_t; the butterflies were 25 % of k_render_bwd_pixel's
+// instructions, profiles/r01_notes.md).  Afterwards every lane holds the warp total of value number halving_index().
+template <int LOG>
+__device__ __forceinline__ int halving_index(int lane) { return (lane >> (5 - LOG)) & ((1 << LOG) - 1); }
+template <int LOG>
+__device__ __forceinline__ float warp_reduce_halving(float (&v)[1 << LOG], int lane) {
+#pragma unroll
+    for (int s = 0; s < LOG; s++) {
+        const int h = (1 << LOG) >> (s + 1), bit = 16 >> s;
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int k = 0; k < h; k++) {
+            const float send = up ? v[k] : v[k + h], keep = up ? v[k + h] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int bit = 16 >> LOG; bit > 0; bit >>= 1) r += __shfl_xor_sync(0xffffffffu, r, bit);
+    return r;
+}
+
 // warp-wide exclusive prefix sum of a small per-lane count + total
 __device__ __forceinline__ int warp_excl_scan(int v, int* total) {
     const int lane = threadIdx.x & 31;

@@ -40,7 +40,7 @@ struct TileSmem2 {
     float vz[NV_PAD];
     float ftab[TWARPS][64 * REC_F];             // warp-local face table, entry = lane * 2 + triangle
     uint32_t fword[TWARPS][64];                 // face index | z-range verdict << 31
-    uint16_t hq[TWARPS][32 * K_ROUND];          // warp-local hit queue: job byte | triangle << 7 | bit << 8
+    uint16_t hq[TWARPS][32 * K_ROUND];          // warp-local hit queue: job lane | bit << 5
     uint8_t jobs[TWARPS][32 * 4];               // warp-local job list: owner lane | box column << 5 | box row << 6
 };
 
@@ -252,8 +252,9 @@ __device__ __forceinline__ void build_face_records(TileSmem2& sm, const TileCtx&
 }
 
 // Rounds: every lane queues at most K_ROUND of the hits of its job (M: bits 0..15 = first triangle, 16..31 = second, bit =
-// row * 4 + column of the job's 4 x 4 box), the warp drains the queue one lane per hit: hit(slot, xi, yi, fi, z, face word).
-// jobword = owner lane | box column << 5 | box row << 6; origin = x0 | y0 << 12 of the OWNER lane's quad box.
+// row * 4 + column of the job's 4 x 4 box) as 16-bit entries `lane | bit << 5`; the warp drains the queue one lane per hit:
+// hit(valid, job lane, triangle, slot, xi, yi, fi, z, face word), called by ALL lanes.
+// jobword = owner lane | box column << 5 | box row << 6 of this lane's job; origin = x0 | y0 << 12 of this lane's OWN quad box.
 template <class Hit>
 __device__ __forceinline__ void drain_rounds(TileSmem2& sm, unsigned M, unsigned jobword, uint32_t origin, const Hit& hit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -269,7 +270,7 @@ __device__ __forceinline__ void drain_rounds(TileSmem2& sm, unsigned M, unsigned
             if (k < c) {
                 const unsigned bit = (unsigned)(__ffs(M) - 1);
                 M &= M - 1u;
-                hq[base++] = (uint16_t)(jobword | (bit << 7));        // bit 4 of `bit` = the triangle
+                hq[base++] = (uint16_t)((unsigned)lane | (bit << 5));
             }
         }
         __syncwarp();
@@ -278,19 +279,20 @@ __device__ __forceinline__ void drain_rounds(TileSmem2& sm, unsigned M, unsigned
             const int i = i0 + lane;
             const bool valid = i < total;
             const unsigned e = valid ? hq[i] : 0u;
-            const unsigned owner = e & 31u;
+            const int jl = (int)(e & 31u);                       // the lane whose job this hit belongs to
+            const unsigned jw = __shfl_sync(0xffffffffu, jobword, jl);
+            const unsigned owner = jw & 31u;
             const uint32_t ow = __shfl_sync(0xffffffffu, origin, (int)owner);
-            if (valid) {
-                const int xi = (int)(ow & 4095u) + (int)(((e >> 5) & 1u) * 4u + ((e >> 7) & 3u));
-                const int yi = (int)((ow >> 12) & 4095u) + (int)(((e >> 6) & 1u) * 4u + ((e >> 9) & 3u));
-                const int slot = (int)(owner * 2u + ((e >> 11) & 1u));
-                const float4* r4 = reinterpret_cast<const float4*>(&sm.ftab[warp][slot * REC_F]);
-                const float4 r0 = r4[0], r1 = r4[1], r2 = r4[2];
-                const uint32_t fw = sm.fword[warp][slot];
-                const float fi[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
-                const float z[3] = {r2.y, r2.z, r2.w};
-                hit(slot, xi, yi, fi, z, fw);
-            }
+            const unsigned bit = e >> 5, tri = bit >> 4;
+            const int xi = (int)(ow & 4095u) + (int)(((jw >> 5) & 1u) * 4u + (bit & 3u));
+            const int yi = (int)((ow >> 12) & 4095u) + (int)(((jw >> 6) & 1u) * 4u + ((bit >> 2) & 3u));
+            const int slot = (int)(owner * 2u + tri);            // invalid lanes read slot 0
+            const float4* r4 = reinterpret_cast<const float4*>(&sm.ftab[warp][slot * REC_F]);
+            const float4 r0 = r4[0], r1 = r4[1], r2 = r4[2];
+            const uint32_t fw = sm.fword[warp][slot];
+            const float fi[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+            const float z[3] = {r2.y, r2.z, r2.w};
+            hit(valid, jl, (int)tri, slot, xi, yi, fi, z, fw);
         }
         __syncwarp();
     }
@@ -299,9 +301,10 @@ __device__ __forceinline__ void drain_rounds(TileSmem2& sm, unsigned M, unsigned
 // forward hit: weights, perspective z, 64-bit atomicMin of the packed key
 struct FwdHit {
     const TileCtx* cx;
-    __device__ __forceinline__ void operator()(int, int xi, int yi, const float fi[9], const float z[3], uint32_t fw) const {
+    __device__ __forceinline__ void operator()(bool valid, int, int, int, int xi, int yi, const float fi[9],
+                                               const float z[3], uint32_t fw) const {
         float w[3], zp;
-        if (weights_depth_core(fi, z, (fw >> 31) != 0u, xi, yi, cx->near, cx->far, w, &zp))
+        if (valid && weights_depth_core(fi, z, (fw >> 31) != 0u, xi, yi, cx->near, cx->far, w, &zp))
             atomicMin(&cx->zb[(long)(cx->is - 1 - yi) * cx->is + xi], zkey_pack(zp, fw & 0x7fffffffu));
     }
 };
