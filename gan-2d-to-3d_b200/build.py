@@ -12,8 +12,7 @@ ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(CSRC, "g2s_kernels.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "g2s_math.cuh"), os.path.join(CSRC, "g2s_raster.cuh"),
                   os.path.join(CSRC, "g2s_splat.cuh"), os.path.join(CSRC, "g2s_tile.cuh"),
-                  os.path.join(CSRC, "g2s_bigface.cuh"), os.path.join(CSRC, "g2s_tile_bwd.cuh"),
-                  os.path.join(CSRC, "g2s_callers.cuh"),
+                  os.path.join(CSRC, "g2s_bigface.cuh"), os.path.join(CSRC, "g2s_callers.cuh"),
                   os.path.join(ROOT, "include", "g2s_b200.h")]
 LIB = os.path.join(CSRC, "libg2s_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -38,14 +38,10 @@ struct BigSmem {
 };
 
 struct BigCtx {
-    unsigned long long* zbuf;      // forward: z-buffer of the launch
+    unsigned long long* zbuf;      // z-buffer of the launch
     float near, far;
     int is;
     PixCenter pc;
-    // backward (g2s_tile_bwd.cuh): face-index map and masked quarter gradient of the launch's views, per-slot sums
-    const int* fmap;
-    const float* gsub;
-    float* aacc;
 };
 
 // [nr] kernel 2 inside test of one triangle with the loop invariants hoisted
@@ -65,11 +61,9 @@ struct RowScanT {
     }
 };
 
-// What a stage-2 kernel does with a (face, sub-pixel) pair.  Forward (BigFwd): candidate test = [nr] kernel 2's exact inside
-// test, hit = weights, perspective z, 64-bit atomicMin.  The backward (g2s_tile_bwd.cuh) plugs in "does the face-index map
-// name this face here" and the gradient accumulation instead.
+// What stage 2 does with a (face, sub-pixel) pair: candidate test = [nr] kernel 2's exact inside test, hit = weights,
+// perspective z, 64-bit atomicMin.
 struct BigFwd {
-    static constexpr bool kBackward = false;
     struct Row {      // inside test of one face on one sub-pixel row
         RowScanT sc;
         const BigCtx* cx;
@@ -258,14 +252,15 @@ __device__ __forceinline__ void project_vertex(const Cam& cam, const float* __re
     project_ndc(cam, q, ndc);
 }
 
-// P = BigFwd, or the backward's policy; `fin` (backward only) turns the per-face sums of a batch into gradients
-template <bool FROM_VERTS, class P, class Finish>
+template <bool FROM_VERTS>
 __device__ __forceinline__ void splat_big_body(BigSmem& sm, const Cam& cam, const float* __restrict__ depth, long dstride,
                                                int vpi, const float* __restrict__ R, const float* __restrict__ t,
-                                               const float* __restrict__ verts3d, BigCtx cx, const WorkList& wl, int view0,
-                                               const Finish& fin) {
+                                               const float* __restrict__ verts3d, unsigned long long* zbuf,
+                                               const WorkList& wl, int view0) {
+    typedef BigFwd P;
     const int tid = threadIdx.x, S = cam.S, is = 2 * S;
-    cx.near = cam.near; cx.far = cam.far; cx.is = is;
+    BigCtx cx;
+    cx.zbuf = zbuf; cx.near = cam.near; cx.far = cam.far; cx.is = is;
     cx.pc.init(is);
     const long long count = (long long)(*(volatile unsigned long long*)&wl.ctr[0] - wl.bias);   // written by stage 1
     // faces per ticket: the list spread over all CTAs of the grid (a full 256-face batch of wall faces keeps one CTA busy
@@ -305,7 +300,6 @@ __device__ __forceinline__ void splat_big_body(BigSmem& sm, const Cam& cam, cons
             BBox bb;
             sm.zoff[tid] = (unsigned long long)bl * (unsigned long long)is * (unsigned long long)is;
             sm.face[tid] = face;
-            if constexpr (P::kBackward) { cx.aacc[tid * 3] = 0.f; cx.aacc[tid * 3 + 1] = 0.f; cx.aacc[tid * 3 + 2] = 0.f; }
             if (tri_bbox(f, is, bb)) {
                 r[6] = __uint_as_float((uint32_t)bb.x0 | ((uint32_t)bb.x1 << 16));
                 r[7] = __uint_as_float((uint32_t)bb.y0 | ((uint32_t)bb.y1 << 16));
@@ -316,10 +310,6 @@ __device__ __forceinline__ void splat_big_body(BigSmem& sm, const Cam& cam, cons
         }
         __syncthreads();
         big_rounds<P>(sm, cx);
-        if constexpr (P::kBackward) {
-            __syncthreads();
-            fin(sm, cx, n, view0);
-        }
     }
     // the last CTA to leave puts the counters back to their rest value
     if (tid == 0) {

@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/g2s_b200.h"
-#include "g2s_tile_bwd.cuh"
+#include "g2s_bigface.cuh"
 
 using namespace g2s;
 
@@ -43,12 +43,13 @@ Cam make_cam(const g2s_camera* c) {
 
 // ---- instrumentation: launch counter + optional CUDA-event timing of every kernel (bench.py / tests) ----
 enum KernelId { K_ZINIT, K_SPLAT, K_SPLAT_BIG, K_RESOLVE, K_RESOLVE_FUSED, K_GRID_FWD, K_GRID_BWD, K_NORMAL_FWD, K_NORMAL_BWD,
-                K_SAMPLE_FWD, K_SAMPLE_BWD, K_CLAMP_GRAD, K_RASTER_BWD, K_RASTER_BWD_BIG, K_BWD_PIXEL, K_BWD_TEX, K_GRID3D, K_RESOLVE_RGB,
-                K_VIEW, K_LIGHT, K_CLAMPED_DEPTH, K_SHADING, K_PHOTOMETRIC, K_SMOOTH, K_COUNT };
+                K_SAMPLE_FWD, K_SAMPLE_BWD, K_CLAMP_GRAD, K_RASTER_BWD, K_BWD_PIXEL, K_BWD_TEX, K_GRID3D, K_RESOLVE_RGB,
+                K_PROJECT, K_VERTEX_BWD, K_VIEW, K_LIGHT, K_CLAMPED_DEPTH, K_SHADING, K_PHOTOMETRIC, K_SMOOTH, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_zbuf_init", "k_splat_tile", "k_splat_big", "k_resolve", "k_resolve_fused", "k_warp_grid_fwd",
                                            "k_warp_grid_bwd", "k_normal_fwd", "k_normal_bwd", "k_sample_fwd",
-                                           "k_sample_bwd", "k_clamp_grad", "k_raster_bwd_tile", "k_raster_bwd_big", "k_render_bwd_pixel",
-                                           "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb", "k_view_fwd/bwd", "k_light_fwd/bwd", "k_clamped_depth",
+                                           "k_sample_bwd", "k_clamp_grad", "k_raster_bwd_px", "k_render_bwd_pixel",
+                                           "k_render_bwd_tex", "k_grid3d", "k_resolve_rgb", "k_project_verts",
+                                           "k_vertex_bwd", "k_view_fwd/bwd", "k_light_fwd/bwd", "k_clamped_depth",
                                            "k_shading_fwd/bwd", "k_photometric", "k_smooth"};
 std::atomic<long> g_launches{0};
 struct ProfRec { int id; cudaEvent_t a, b; };
@@ -151,9 +152,7 @@ k_splat_big(const Cam cam, const float* __restrict__ depth, long dstride, int vp
             const WorkList wl, int view0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BigSmem& sm = *reinterpret_cast<BigSmem*>(smem_raw);
-    BigCtx cx = {};
-    cx.zbuf = zbuf;
-    splat_big_body<FROM_VERTS, BigFwd>(sm, cam, depth, dstride, vpi, R, t, verts3d, cx, wl, view0, 0);
+    splat_big_body<FROM_VERTS>(sm, cam, depth, dstride, vpi, R, t, verts3d, zbuf, wl, view0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -669,48 +668,178 @@ __global__ void k_light_bwd(const float* __restrict__ light, int B, const float*
 // vertex through projection / rotation to grad_depth, grad_R, grad_t.  neural_renderer does 9 float atomics per
 // covered sub-pixel into grad_faces[B,F,3,3] and leaves the gather to autograd (index_put over 6 faces per vertex).
 
-// stage 1 (g2s_tile_bwd.cuh): one CTA per 16 x 16 block of quads of one view, grid = (tiles, views): CTAs that run at the
-// same time are different tiles of one view (with views fastest, the 16 views of an image would all add to the same
-// grad_depth words at once: same-address atomics serialise in L2)
-template <bool FROM_VERTS>
-__global__ void __launch_bounds__(SPLAT_THREADS, 3)
-k_raster_bwd_tile(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
-                  const float* __restrict__ t, const float* __restrict__ verts3d, const int* __restrict__ face_idx,
-                  const float* __restrict__ g_sub, const WorkList wl, int tiles_x, int view0, float* __restrict__ grad_depth,
-                  long gdstride, float* __restrict__ grad_verts, float* __restrict__ grad_R, float* __restrict__ grad_t) {
-    __shared__ TileSmemB sm;
-    const int bl = blockIdx.y, b = view0 + bl, S = cam.S, is = 2 * S;
-    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x % tiles_x;
-    raster_bwd_tile_body<FROM_VERTS>(sm, cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
-                                     FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, FROM_VERTS ? nullptr : R + (long)b * 9,
-                                     FROM_VERTS ? nullptr : t + (long)b * 3, face_idx + (long)b * is * is, g_sub + (long)bl * S * S,
-                                     wl, bl, tile_y * TILE_H, tile_x * TILE,
-                                     FROM_VERTS ? nullptr : grad_depth + (long)(b / vpi) * gdstride,
-                                     FROM_VERTS ? grad_verts + (long)b * S * S * 3 : nullptr,
-                                     (FROM_VERTS || !grad_R) ? nullptr : grad_R + (long)b * 9,
-                                     (FROM_VERTS || !grad_R) ? nullptr : grad_t + (long)b * 3);
+// projected (u, v, z) of every vertex of the chunk's views: proj [chunk, S*S, 3]
+__global__ void __launch_bounds__(PIX_THREADS)
+k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+                const float* __restrict__ t, int view0, float* __restrict__ proj) {
+    __shared__ float sRt[12];
+    const int S = cam.S, bl = blockIdx.y, b = view0 + bl;
+    if (threadIdx.x < 9) sRt[threadIdx.x] = R[b * 9 + threadIdx.x];
+    else if (threadIdx.x < 12) sRt[threadIdx.x] = t[b * 3 + threadIdx.x - 9];
+    __syncthreads();
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (v >= S * S) return;
+    const int vy = v / S, vx = v - vy * S;
+    float ray[3], q[3], ndc[3];
+    pixel_ray(cam, vx, vy, ray);
+    warp_point(cam, sRt, sRt + 9, ray, depth[(long)(b / vpi) * dstride + v], q);
+    project_ndc(cam, q, ndc);
+    reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
 }
 
-// stage 2: the deferred faces, persistent CTAs over the work list (g2s_bigface.cuh machinery with the backward policy)
-struct BigSmemB {
-    BigSmem b;
-    float aacc[BIG_THREADS * 3];
-};
-template <bool FROM_VERTS>
-__global__ void __launch_bounds__(BIG_THREADS, 2)
-k_raster_bwd_big(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
-                 const float* __restrict__ t, const float* __restrict__ verts3d, const int* __restrict__ face_idx,
-                 const float* __restrict__ g_sub, const WorkList wl, int view0, float* __restrict__ grad_depth, long gdstride,
-                 float* __restrict__ grad_verts, float* __restrict__ grad_R, float* __restrict__ grad_t) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BigSmemB& sm = *reinterpret_cast<BigSmemB*>(smem_raw);
-    const int is = 2 * cam.S;
-    BigCtx cx = {};
-    cx.fmap = face_idx + (long)view0 * is * is;
-    cx.gsub = g_sub;
-    cx.aacc = sm.aacc;
-    BigBwdFinish<FROM_VERTS> fin = {cam, depth, dstride, vpi, R, t, verts3d, grad_depth, gdstride, grad_verts, grad_R, grad_t};
-    splat_big_body<FROM_VERTS, BigBwd>(sm.b, cam, depth, dstride, vpi, R, t, verts3d, cx, wl, view0, fin);
+// the same for vertices given as 3-D points (the neural_renderer-level entry g2s_render_depth_*): projection only
+__global__ void __launch_bounds__(PIX_THREADS)
+k_project_points(const Cam cam, const float* __restrict__ verts3d, float* __restrict__ proj) {
+    const int S = cam.S, bl = blockIdx.y;
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (v >= S * S) return;
+    const float* p = verts3d + ((long)bl * S * S + v) * 3;
+    const float q[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    float ndc[3];
+    project_ndc(cam, q, ndc);
+    reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
+}
+
+// (u,v,z) NDC gradient -> gradient of the 3-D vertex ([nr] projection backward); WRITES grad_verts [chunk,S*S,3]
+__global__ void __launch_bounds__(PIX_THREADS)
+k_points_bwd(const Cam cam, const float* __restrict__ verts3d, const float* __restrict__ vgrad,
+             float* __restrict__ grad_verts) {
+    const int S = cam.S, bl = blockIdx.y;
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (v >= S * S) return;
+    const float4 gp = __ldcs(reinterpret_cast<const float4*>(vgrad) + (long)bl * S * S + v);
+    const float* p = verts3d + ((long)bl * S * S + v) * 3;
+    const float zz = __ldg(p + 2) + 1e-9f, iz = 1.0f / zz;
+    const float x_ = __ldg(p) * iz, y_ = __ldg(p + 1) * iz;
+    const float gup = gp.x * (2.0f / cam.os), gvp = -gp.y * (2.0f / cam.os);
+    const float gx_ = gup * cam.K[0] + gvp * cam.K[3], gy_ = gup * cam.K[1] + gvp * cam.K[4];
+    float* o = grad_verts + ((long)bl * S * S + v) * 3;
+    o[0] = gx_ * iz;
+    o[1] = gy_ * iz;
+    o[2] = gp.z - (gx_ * x_ + gy_ * y_) * iz;
+}
+
+constexpr int RBX = 16, RBY = 8;
+__global__ void __launch_bounds__(RBX * RBY)
+k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
+                const float* __restrict__ proj, float* __restrict__ vgrad, int view0) {
+    const int S = cam.S, is = 2 * S, bl = blockIdx.z, b = view0 + bl;
+    const int j = blockIdx.x * RBX + threadIdx.x, i = blockIdx.y * RBY + threadIdx.y;
+    if (j >= S || i >= S) return;
+    const float g = g_sub[(long)bl * S * S + i * S + j];
+    if (g == 0.f) return;
+    const int* fm = face_idx + (long)b * is * is;
+    const int2 r0 = *reinterpret_cast<const int2*>(fm + (long)(2 * i) * is + 2 * j);
+    const int2 r1 = *reinterpret_cast<const int2*>(fm + (long)(2 * i + 1) * is + 2 * j);
+    const int f0 = r0.x, f1 = r0.y, f2 = r1.x, f3 = r1.y;
+    const float4* pv = reinterpret_cast<const float4*>(proj) + (long)bl * S * S;   // projected vertices, packed uvz-
+    float4* vg = reinterpret_cast<float4*>(vgrad) + (long)bl * S * S;              // vertex gradients, packed uvz-
+    const float hs = 0.5f * (float)is;
+    // Distinct faces of the 2x2 block, one per trip of ONE loop body (not four unrolled copies: the unrolled form ran
+    // at 17 active lanes per instruction and stalled on instruction fetch, profiles/r01_notes.md): `rem` = sub-pixels
+    // still to do; a trip takes the face of the lowest one and every other sub-pixel that shares it.
+    unsigned rem = (f0 >= 0 ? 1u : 0u) | (f1 >= 0 ? 2u : 0u) | (f2 >= 0 ? 4u : 0u) | (f3 >= 0 ? 8u : 0u);
+#pragma unroll 1
+    while (rem) {
+        const int k = __ffs(rem) - 1;
+        const int face = k == 0 ? f0 : (k == 1 ? f1 : (k == 2 ? f2 : f3));
+        unsigned mine = ((f0 == face ? 1u : 0u) | (f1 == face ? 2u : 0u) | (f2 == face ? 4u : 0u) | (f3 == face ? 8u : 0u)) & rem;
+        rem &= ~mine;
+        int vidx[3];
+        face_vertices(face, S, vidx);
+        float nd[3][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const float4 q = __ldg(&pv[vidx[m]]);
+            nd[m][0] = q.x; nd[m][1] = q.y; nd[m][2] = q.z;
+        }
+        float rec[16];
+        face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
+        float A[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+        while (mine) {
+            const int k2 = __ffs(mine) - 1;
+            mine &= mine - 1;
+            const int xi = 2 * j + (k2 & 1), yi = is - 1 - (2 * i + (k2 >> 1));
+            float w[3], zp = 0.f;
+            record_weights_depth(rec, xi, yi, cam.near, cam.far, w, &zp);
+            const float s = g * zp * zp;
+            A[0] += s * w[0]; A[1] += s * w[1]; A[2] += s * w[2];
+        }
+        // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
+        const float z[3] = {rec[9], rec[10], rec[11]};
+        // six exact quotients fi[m][l] / z_m from the tabulated reciprocal seeds, one merged range check
+        float qd[6];
+        unsigned bad = 0;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const float yz = rcp_seed(z[m]);
+            qd[m] = div_core(rec[3 * m], z[m], yz);
+            qd[3 + m] = div_core(rec[3 * m + 1], z[m], yz);
+            bad = max(bad, rec[3 * m] == 0.0f ? 0u : range_key(rec[3 * m]));
+            bad = max(bad, rec[3 * m + 1] == 0.0f ? 0u : range_key(rec[3 * m + 1]));
+        }
+        if (bad >= RANGE_SPAN || rec[FT_FLAG] != 0.0f) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) { qd[m] = __fdiv_rn(rec[3 * m], z[m]); qd[3 + m] = __fdiv_rn(rec[3 * m + 1], z[m]); }
+        }
+        const float t0 = -(qd[0] + qd[1] + qd[2]);
+        const float t1 = -(qd[3] + qd[4] + qd[5]);
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            if (A[m] == 0.f) continue;
+            // one 16-byte vector reduction per vertex instead of three scalar ones
+            atomicAdd(&vg[vidx[m]], make_float4(-t0 * A[m] * hs, -t1 * A[m] * hs, __fdiv_rn(A[m], z[m] * z[m]), 0.f));
+        }
+    }
+}
+
+// vertex chain: (u,v,z) NDC gradient -> 3-D point -> depth, R, t.  One thread per vertex.
+__global__ void __launch_bounds__(PIX_THREADS)
+k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
+             const float* __restrict__ t, int view0, const float* __restrict__ vgrad, float* __restrict__ grad_depth,
+             long gdstride, float* __restrict__ grad_R, float* __restrict__ grad_t) {
+    __shared__ float sRt[12];
+    const int S = cam.S, bl = blockIdx.y, b = view0 + bl;
+    if (threadIdx.x < 9) sRt[threadIdx.x] = R[b * 9 + threadIdx.x];
+    else if (threadIdx.x < 12) sRt[threadIdx.x] = t[b * 3 + threadIdx.x - 9];
+    __syncthreads();
+    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0.f;
+    if (v < S * S) {
+        const float4 gp = __ldcs(reinterpret_cast<const float4*>(vgrad) + (long)bl * S * S + v);
+        const float gu = gp.x, gv = gp.y, gz = gp.z;
+        if (gu != 0.f || gv != 0.f || gz != 0.f) {
+            const int vy = v / S, vx = v - vy * S;
+            float ray[3], q[3];
+            pixel_ray(cam, vx, vy, ray);
+            const float d = depth[(long)(b / vpi) * dstride + v];
+            warp_point(cam, sRt, sRt + 9, ray, d, q);
+            const float p3[3] = {ray[0] * d, ray[1] * d, ray[2] * d - cam.rcd};
+            const float zz = q[2] + 1e-9f, iz = 1.0f / zz;
+            const float x_ = q[0] * iz, y_ = q[1] * iz;
+            const float gup = gu * (2.0f / cam.os), gvp = -gv * (2.0f / cam.os);
+            const float gx_ = gup * cam.K[0] + gvp * cam.K[3], gy_ = gup * cam.K[1] + gvp * cam.K[4];
+            const float gq[3] = {gx_ * iz, gy_ * iz, gz - (gx_ * x_ + gy_ * y_) * iz};
+            float gd = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float gvk = gq[0] * sRt[k] + gq[1] * sRt[3 + k] + gq[2] * sRt[6 + k];
+                gd += gvk * ray[k];
+#pragma unroll
+                for (int jj = 0; jj < 3; jj++) acc[3 * jj + k] += gq[jj] * p3[k];
+                acc[9 + k] += gq[k];
+            }
+            float* o = &grad_depth[(long)(b / vpi) * gdstride + v];
+            if (vpi == 1 && gdstride != 0) *o += gd;   // one view per depth map: this thread is the only writer
+            else atomicAdd(o, gd);
+        }
+    }
+    if (grad_R) {
+        block_accumulate_Rt<PIX_THREADS>(acc, grad_R + b * 9, grad_t + b * 3);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1125,9 +1254,7 @@ inline const DeviceInfo* device_info() {
     if (!d.ready) {
         if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sms <= 0) return nullptr;
         if (cudaFuncSetAttribute(k_splat_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)) != cudaSuccess ||
-            cudaFuncSetAttribute(k_splat_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)) != cudaSuccess ||
-            cudaFuncSetAttribute(k_raster_bwd_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmemB)) != cudaSuccess ||
-            cudaFuncSetAttribute(k_raster_bwd_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmemB)) != cudaSuccess)
+            cudaFuncSetAttribute(k_splat_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)) != cudaSuccess)
             return nullptr;
         d.ready = true;
     }
@@ -1285,28 +1412,27 @@ inline bool bad_size(int S) { return S < 2 || S > 2048; }
 // the masked-quarter-gradient plane of a raster workspace laid out for nv views (see launch_raster_bwd)
 inline float* raster_ws_gsub(float* raster_ws, int nv, int S) { return raster_ws + (size_t)nv * 8 * S * S; }
 
-// Backward of the rasteriser for `nv` views.  raster_ws [nv, 9, S, S] floats: work list of deferred faces (8-byte items) +
-// 4 counter words in the first 8 S^2 floats per view | masked quarter gradient g_sub [nv, S, S].
-template <bool FROM_VERTS>
-inline int launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
-                             const float* verts3d, const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth,
-                             long gdstride, float* grad_verts, float* grad_R, float* grad_t, cudaStream_t st) {
-    const DeviceInfo* di = device_info();
-    if (!di) return G2S_ERR_LAUNCH;
-    const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
-    WorkList wl;
-    wl.items = reinterpret_cast<unsigned long long*>(raster_ws);
-    wl.ctr = wl.items + (size_t)nv * 4ul * (S - 1) * (S - 1);
-    wl.bias = 0ull;
-    const float* g_sub = raster_ws_gsub(raster_ws, nv, S);
-    cudaMemsetAsync(wl.ctr, 0, 4 * sizeof(unsigned long long), st);
+// Backward of the rasteriser for `nv` views.  raster_ws [nv, 9, S, S] floats: projected vertices (uvz-, 16-byte texels) |
+// vertex gradients (uvz-) | masked quarter gradient g_sub [nv, S, S].  Mesh from (depth, R, t) or, when verts3d is given, from
+// 3-D points (gradient -> grad_verts [nv, S*S, 3], written).
+inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
+                              const float* verts3d, const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth,
+                              long gdstride, float* grad_verts, float* grad_R, float* grad_t, cudaStream_t st) {
+    const int S = c.S;
+    const size_t img = (size_t)S * S;
+    float* proj = raster_ws;
+    float* vgrad = proj + (size_t)nv * 4 * img;
+    float* g_sub = raster_ws_gsub(raster_ws, nv, S);
+    cudaMemsetAsync(vgrad, 0, sizeof(float) * nv * 4 * img, st);
+    { Launch l_(K_PROJECT, st);
+      if (verts3d) k_project_points<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj);
+      else k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj); }
     { Launch l_(K_RASTER_BWD, st);
-      k_raster_bwd_tile<FROM_VERTS><<<dim3(tiles * tiles_y, nv), SPLAT_THREADS, 0, st>>>(
-          c, depth, dstride, vpi, R, t, verts3d, face_idx, g_sub, wl, tiles, view0, grad_depth, gdstride, grad_verts, grad_R, grad_t); }
-    { Launch l_(K_RASTER_BWD_BIG, st);
-      k_raster_bwd_big<FROM_VERTS><<<di->sms * 2, BIG_THREADS, sizeof(BigSmemB), st>>>(
-          c, depth, dstride, vpi, R, t, verts3d, face_idx, g_sub, wl, view0, grad_depth, gdstride, grad_verts, grad_R, grad_t); }
-    return G2S_OK;
+      k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), dim3(RBX, RBY), 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
+    { Launch l_(K_VERTEX_BWD, st);
+      if (verts3d) k_points_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, vgrad, grad_verts);
+      else k_vertex_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
+                                                                        gdstride, grad_R, grad_t); }
 }
 
 }  // namespace
@@ -1371,9 +1497,8 @@ int g2s_warp_depth_bwd(const g2s_camera* cam, const float* depth, long depth_vie
     const long n = (long)n_views * S * S;
     { Launch l_(K_CLAMP_GRAD, st); k_clamp_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(recon_depth, grad_recon_depth, c.clamp_lo, c.clamp_hi, n,
                                                               raster_ws_gsub(grad_sub_ws, n_views, S)); }
-    if (int rc = launch_raster_bwd<false>(c, depth, depth_view_stride, 1, R, t, nullptr, face_idx, grad_sub_ws, n_views, 0, grad_depth,
-                                          grad_depth_view_stride, nullptr, grad_R, grad_t, st))
-        return rc;
+    launch_raster_bwd(c, depth, depth_view_stride, 1, R, t, nullptr, face_idx, grad_sub_ws, n_views, 0, grad_depth,
+                      grad_depth_view_stride, nullptr, grad_R, grad_t, st);
     return launch_status();
 }
 
@@ -1566,9 +1691,8 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
         { Launch l_(K_BWD_TEX, st);
           k_render_bwd_tex<<<tex_grid, PIX_THREADS, 0, st>>>(S, fa, nv, grad_tex_ws, grad_albedo,
                                                                                              grad_normal_ws, grad_light); }
-        if (int rc = launch_raster_bwd<false>(c, depth, (long)S * S, views_per_image, R, t, nullptr, face_idx, grad_sub_ws, nv, (int)v0,
-                                              grad_depth, (long)S * S, nullptr, grad_R, grad_t, st))
-            return rc;
+        launch_raster_bwd(c, depth, (long)S * S, views_per_image, R, t, nullptr, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,
+                          (long)S * S, nullptr, grad_R, grad_t, st);
     }
     for (int i0 = 0; i0 < n_images; i0 += 32768) {
         const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;
@@ -1686,10 +1810,8 @@ int g2s_render_depth_bwd(const g2s_camera* cam, const float* vertices3d, int n_v
     // flip + 2x2 mean backward: every sub-pixel of an output pixel gets a quarter of its cotangent (no clamp here)
     { Launch l_(K_CLAMP_GRAD, st); k_clamp_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad_depth_out, grad_depth_out, -3.402823466e38f,
                                                               3.402823466e38f, n, g_sub); }
-    cudaMemsetAsync(grad_vertices, 0, sizeof(float) * n * 3, st);      // tiles share their border vertices: accumulated
-    if (int rc = launch_raster_bwd<true>(c, nullptr, 0, 1, nullptr, nullptr, vertices3d, face_idx, raster_ws, n_views, 0, nullptr, 0,
-                                         grad_vertices, nullptr, nullptr, st))
-        return rc;
+    launch_raster_bwd(c, nullptr, 0, 1, nullptr, nullptr, vertices3d, face_idx, raster_ws, n_views, 0, nullptr, 0, grad_vertices,
+                      nullptr, nullptr, st);
     return launch_status();
 }
 
