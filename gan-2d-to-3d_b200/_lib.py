@@ -17,7 +17,7 @@ class Camera(ctypes.Structure):
     """struct g2s_camera (include/g2s_b200.h)."""
     _fields_ = [("K", _c_float * 9), ("inv_K", _c_float * 9), ("rot_center_depth", _c_float),
                 ("near_z", _c_float), ("far_z", _c_float), ("clamp_lo", _c_float), ("clamp_hi", _c_float),
-                ("image_size", ctypes.c_int32)]
+                ("image_size", ctypes.c_int32), ("K_grid", _c_float * 9)]
 
 
 _CAMP = ctypes.POINTER(Camera)
@@ -26,6 +26,9 @@ _CAMP = ctypes.POINTER(Camera)
 SIGNATURES = {
     "g2s_version": (_c_int, []),
     "g2s_error_string": (ctypes.c_char_p, [_c_int]),
+    "g2s_context_create": (_c_int, [ctypes.POINTER(_vp)]),
+    "g2s_context_destroy": (None, [_vp]),
+    "g2s_workspace_bytes": (ctypes.c_size_t, [_c_int, _c_int, _c_int]),
     "g2s_zbuffer_bytes": (ctypes.c_size_t, [_c_int, _c_int]),
     "g2s_zbuffer_init": (_c_int, [_vp, _c_int, _c_int, _c_float, _vp]),
     "g2s_warp_depth_fwd": (_c_int, [_CAMP, _vp, _c_long, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
@@ -42,7 +45,7 @@ SIGNATURES = {
                                 _c_int, _vp, _c_long, _vp, _vp]),
     "g2s_chunk_views": (_c_int, [_c_int]),
     "g2s_chunk_views_bwd": (_c_int, [_c_int]),
-    "g2s_render_fused_fwd": (_c_int, [_CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp,
+    "g2s_render_fused_fwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_fused_bwd": (_c_int, [_CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
                                       _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -51,7 +54,7 @@ SIGNATURES = {
     "g2s_render_depth_fwd": (_c_int, [_CAMP, _vp, _c_int, _vp, _vp, _vp, _vp]),
     "g2s_render_depth_bwd": (_c_int, [_CAMP, _vp, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_rgb_bwd": (_c_int, [_CAMP, _vp, _vp, _c_long, _c_int, _c_int, _c_int, ctypes.POINTER(_c_float), _c_int,
-                                    _vp, _vp, _vp, _c_long, _vp]),
+                                    _vp, _vp, _vp, _c_long, _vp, _vp, _vp, _vp]),
     "g2s_view_fwd": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp]),
     "g2s_view_bwd": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp]),
     "g2s_light_fwd": (_c_int, [_vp, _c_int, _vp, _vp]),
@@ -78,7 +81,13 @@ SIGNATURES = {
                                   ctypes.POINTER(_c_int)]),
     "g2s_grid3d_fwd": (_c_int, [_CAMP, _vp, _c_long, _c_int, _c_int, _c_int, ctypes.POINTER(_c_int), _vp, _vp, _vp,
                                 _vp, _vp, _vp, _vp]),
+    "g2s_grid3d_bwd": (_c_int, [_CAMP, _vp, _c_long, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g2s_grid_3d_to_2d_fwd": (_c_int, [_CAMP, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "g2s_grid_3d_to_2d_bwd": (_c_int, [_CAMP, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
 }
+
+# g2s_workspace_bytes kinds (include/g2s_b200.h)
+WS_ZBUFFER, WS_RASTER_BWD, WS_TEX_BWD, WS_TEXELS, WS_GRAD_NORMAL, WS_RGB_MAP = range(6)
 
 _lib = None
 
@@ -99,6 +108,30 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class Context:
+    """A caller-owned g2s_context (the streams / events of the multi-lane forward) for the CURRENT device."""
+
+    def __init__(self):
+        h = _vp()
+        check(load().g2s_context_create(ctypes.byref(h)), "g2s_context_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.g2s_context_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def ws_floats(kind, n, S):
+    """number of fp32 elements of workspace `kind` for n views / images of side S (g2s_workspace_bytes)"""
+    b = load().g2s_workspace_bytes(kind, n, S)
+    if b == 0:
+        raise RuntimeError("g2s_workspace_bytes: bad arguments (kind %d, n %d, S %d)" % (kind, n, S))
+    return (b + 3) // 4
 
 
 def check(code, what):

@@ -27,6 +27,7 @@ Cam make_cam(const g2s_camera* c) {
     Cam k;
     for (int i = 0; i < 9; i++) {
         k.K[i] = c->K[i];
+        k.Kg[i] = c->K_grid[i];
         k.invK[i] = c->inv_K[i];
     }
     k.rcd = c->rot_center_depth;
@@ -81,19 +82,7 @@ struct Launch {
 
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? G2S_OK : G2S_ERR_LAUNCH; }
 
-// one internal non-blocking stream per device for the two-lane chunk pipeline of g2s_render_fused_fwd
 constexpr int MAX_LANES = 4;
-inline cudaStream_t aux_stream(int k) {
-    static std::mutex mu;
-    static cudaStream_t streams[64][MAX_LANES] = {};
-    int dev = 0;
-    if (k < 0 || k >= MAX_LANES || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!streams[dev][k] && cudaStreamCreateWithFlags(&streams[dev][k], cudaStreamNonBlocking) != cudaSuccess)
-        streams[dev][k] = nullptr;
-    return streams[dev][k];
-}
-
 
 // Sum the per-thread grad_R (9) | grad_t (3) contributions over the block and atomically add the totals to the view's
 // grad_R / grad_t.  All threads must call.
@@ -234,6 +223,13 @@ __device__ __forceinline__ void shade_taps(const float* __restrict__ pack, const
         lo[k] = __ldg(q);
         hi[k] = __ldg(q + 1);
     }
+    // All eight loads are in flight before anything waits on one of them: ONE round trip.  The empty asm "uses" every loaded
+    // value, so the scheduler cannot sink a tap's loads below the shading of the previous tap (it did, after an unrelated
+    // change to the camera struct: long-scoreboard stalls 34 % -> 67 %, k_resolve 1.87 -> 2.51 ms; profiles/r02_notes.md).
+    asm volatile("" : "+f"(lo[0].x), "+f"(lo[0].y), "+f"(lo[0].z), "+f"(lo[0].w), "+f"(hi[0].x), "+f"(hi[0].y),
+                      "+f"(lo[1].x), "+f"(lo[1].y), "+f"(lo[1].z), "+f"(lo[1].w), "+f"(hi[1].x), "+f"(hi[1].y),
+                      "+f"(lo[2].x), "+f"(lo[2].y), "+f"(lo[2].z), "+f"(lo[2].w), "+f"(hi[2].x), "+f"(hi[2].y),
+                      "+f"(lo[3].x), "+f"(lo[3].y), "+f"(lo[3].z), "+f"(lo[3].w), "+f"(hi[3].x), "+f"(hi[3].y));
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const float ndl = lo[k].x * L[2] + lo[k].y * L[3] + lo[k].z * L[4];
@@ -284,9 +280,6 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
     }
     if (!inside) return;
     const int pix = i * S + j;
-    const unsigned long long empty = zkey_empty(cam.far);
-    __stcg(r0, make_ulonglong2(empty, empty));
-    __stcg(r1, make_ulonglong2(empty, empty));
     if (face_idx) {
         int* fo = face_idx + (long)b * is * is;
         __stcs(reinterpret_cast<int2*>(fo + (long)(2 * i) * is + 2 * j), make_int2(zkey_face(k0.x), zkey_face(k0.y)));
@@ -295,6 +288,17 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
     const float sum = add(add(add(zkey_depth(k0.x), zkey_depth(k0.y)), zkey_depth(k1.x)), zkey_depth(k1.y));
     const float rd = fminf(fmaxf(mul(sum, 0.25f), cam.clamp_lo), cam.clamp_hi);
     __stcs(&recon_depth[(long)b * S * S + pix], rd);
+    // The z-buffer reset.  Its data is made to depend on `rd` (through a mask that is zero for every valid launch but that the
+    // compiler cannot see through), so that it cannot be scheduled before the key loads have RETURNED: when ptxas placed the
+    // first of the two stores in front of the 17 view loads, that store -- to the very line a key load was still waiting
+    // on -- held the load / store unit until the load came back, the view loads went out a round trip late, long-scoreboard
+    // stalls rose from 34 % to 67 % of the samples and the kernel from 1.87 to 2.51 ms (profiles/r02_notes.md).
+    {
+        const unsigned zmask = (unsigned)(fa.view0 >> 31);
+        const unsigned long long empty = zkey_empty(cam.far) + (unsigned long long)(__float_as_uint(rd) & zmask);
+        __stcg(r0, make_ulonglong2(empty, empty));
+        __stcg(r1, make_ulonglong2(empty, empty));
+    }
     if (FUSED) {
         const int img = b / fa.vpi;
         float ray[3], q[3], v[3], g[2];
@@ -357,7 +361,7 @@ __device__ __forceinline__ float warp_grid_bwd_pixel(const Cam& cam, const float
     const float iz = 1.0f / q[2];
     const float nx = q[0] * iz, ny = q[1] * iz;
     const float dpx = Gx * 2.0f / (float)(W - 1), dpy = Gy * 2.0f / (float)(H - 1);
-    const float dnx = dpx * cam.K[0] + dpy * cam.K[3], dny = dpx * cam.K[1] + dpy * cam.K[4];
+    const float dnx = dpx * cam.Kg[0] + dpy * cam.Kg[3], dny = dpx * cam.Kg[1] + dpy * cam.Kg[4];
     float dq[3] = {dnx * iz, dny * iz, -(dnx * nx + dny * ny) * iz};
     float dv[3];
     if (inverse) {
@@ -1045,6 +1049,89 @@ k_grid3d(const Cam cam, const float* __restrict__ depth, long dstride, int H, in
     o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
 }
 
+// Backward of depth_to_3d_grid (mode 0) / get_warped_3d_grid (1) / get_inv_warped_3d_grid (2): renderer.py:74-102
+__global__ void __launch_bounds__(PIX_THREADS)
+k_grid3d_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int H, int W, int mode, const float* __restrict__ R,
+             const float* __restrict__ t, const float* __restrict__ grad_out, float* __restrict__ grad_depth,
+             float* __restrict__ grad_R, float* __restrict__ grad_t) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0.f;
+    if (pix < H * W) {
+        const int y = pix / W, x = pix - y * W;
+        float ray[3];
+        pixel_ray(cam, x, y, ray);
+        const float* go = grad_out + ((long)b * H * W + pix) * 3;
+        const float g[3] = {go[0], go[1], go[2]};
+        float gd;
+        if (mode == 0) {
+            gd = g[0] * ray[0] + g[1] * ray[1] + g[2] * ray[2];
+        } else {
+            float Rm[9], tv[3];
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rm[k] = __ldg(&R[b * 9 + k]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) tv[k] = __ldg(&t[b * 3 + k]);
+            const float d = depth[(long)b * dstride + pix];
+            float dv[3];
+            if (mode == 1) {          // q = R v + c0 + t,  v = ray d - c0
+                const float v[3] = {ray[0] * d, ray[1] * d, ray[2] * d - cam.rcd};
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    dv[k] = g[0] * Rm[k] + g[1] * Rm[3 + k] + g[2] * Rm[6 + k];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) acc[3 * j + k] += g[j] * v[k];
+                    acc[9 + k] += g[k];
+                }
+            } else {                  // q = R^T v + c0,  v = ray d - t - c0
+                const float v[3] = {ray[0] * d - tv[0], ray[1] * d - tv[1], ray[2] * d - tv[2] - cam.rcd};
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    dv[k] = g[0] * Rm[3 * k] + g[1] * Rm[3 * k + 1] + g[2] * Rm[3 * k + 2];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) acc[3 * k + j] += v[k] * g[j];
+                    acc[9 + k] -= dv[k];
+                }
+            }
+            gd = dv[0] * ray[0] + dv[1] * ray[1] + dv[2] * ray[2];
+        }
+        grad_depth[(long)b * H * W + pix] = gd;
+    }
+    if (grad_R) {
+        block_accumulate_Rt<PIX_THREADS>(acc, grad_R + b * 9, grad_t + b * 3);
+    }
+}
+
+// grid_3d_to_2d: renderer.py:82-88
+__global__ void __launch_bounds__(PIX_THREADS)
+k_grid_3d_to_2d_fwd(const Cam cam, const float* __restrict__ grid3d, int H, int W, float* __restrict__ grid) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= H * W) return;
+    const float* p = grid3d + ((long)b * H * W + pix) * 3;
+    const float q[3] = {p[0], p[1], p[2]};
+    float g[2];
+    point_to_grid(cam, q, W, H, g);
+    reinterpret_cast<float2*>(grid)[(long)b * H * W + pix] = make_float2(g[0], g[1]);
+}
+
+__global__ void __launch_bounds__(PIX_THREADS)
+k_grid_3d_to_2d_bwd(const Cam cam, const float* __restrict__ grid3d, int H, int W, const float* __restrict__ grad_grid,
+                    float* __restrict__ grad_grid3d) {
+    const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= H * W) return;
+    const float* p = grid3d + ((long)b * H * W + pix) * 3;
+    const float2 G = reinterpret_cast<const float2*>(grad_grid)[(long)b * H * W + pix];
+    const float iz = 1.0f / p[2], nx = p[0] * iz, ny = p[1] * iz;
+    const float dpx = G.x * 2.0f / (float)(W - 1), dpy = G.y * 2.0f / (float)(H - 1);
+    // (px, py) = K_grid (nx, ny, nz) with nz = z / z = 1: no gradient through nz
+    const float dnx = dpx * cam.Kg[0] + dpy * cam.Kg[3], dny = dpx * cam.Kg[1] + dpy * cam.Kg[4];
+    float* o = grad_grid3d + ((long)b * H * W + pix) * 3;
+    o[0] = dnx * iz;
+    o[1] = dny * iz;
+    o[2] = -(dnx * nx + dny * ny) * iz;
+}
+
 struct Bg {
     float c[4];
 };
@@ -1104,16 +1191,16 @@ __device__ __forceinline__ void rgb_subpixel(const Cam& cam, const float* __rest
             int ti[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const float fr = tif[k] - (float)(int)tif[k];
-                if (((pn >> k) & 1) == 0) { wt *= 1.f - fr; ti[k] = (int)tif[k]; }
-                else { wt *= fr; ti[k] = (int)tif[k] + 1; }
+                const float fr = sub(tif[k], (float)(int)tif[k]);
+                if (((pn >> k) & 1) == 0) { wt = mul(wt, sub(1.f, fr)); ti[k] = (int)tif[k]; }
+                else { wt = mul(wt, fr); ti[k] = (int)tif[k] + 1; }
             }
             // fill_back copies see the cube with axes 0 and 2 swapped
             const int ci = rev ? ti[2] * 4 + ti[1] * 2 + ti[0] : ti[0] * 4 + ti[1] * 2 + ti[2];
             float tex = mul(kCube[ci][0], v0);
             tex = fma_(kCube[ci][1], v1, tex);
             tex = fma_(kCube[ci][2], v2, tex);
-            acc += wt * tex;
+            acc = add(acc, mul(wt, tex));        // un-fused, in corner order: the same bits as [nr] forward_texture_sampling
         }
         out[c] = acc;
     }
@@ -1190,6 +1277,157 @@ k_resolve_rgb_bwd(const Cam cam, const int* __restrict__ face_idx, const float* 
                 if (coef[sp][k] != 0.f) atomicAdd(&g_b[(long)c * S * S + cidx[sp][k]], g * coef[sp][k]);
         }
     }
+}
+
+// ---- geometry gradient of an rgb render: [nr] backward_pixel_map ---------------------------------
+// supersampled colour map [n,2S,2S,4] (image orientation; what nr keeps as rgb_map) ...
+__global__ void __launch_bounds__(PIX_THREADS)
+k_rgb_map(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ verts3d, const float* __restrict__ im,
+          long imstride, const Bg bg, float eps, float* __restrict__ rgb_map) {
+    const int S = cam.S, is = 2 * S, b = blockIdx.y;
+    const long sp = (long)blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (sp >= (long)is * is) return;
+    const int r = (int)(sp / is), c = (int)(sp - (long)r * is);
+    const int face = face_idx[(long)b * is * is + sp];
+    float col[3] = {bg.c[0], bg.c[1], bg.c[2]};
+    if (face >= 0) rgb_subpixel<3>(cam, verts3d + (long)b * S * S * 3, im + (long)b * imstride, face, c, is - 1 - r, 0.f, eps, col);
+    reinterpret_cast<float4*>(rgb_map)[(long)b * is * is + sp] = make_float4(col[0], col[1], col[2], 0.f);
+}
+
+// ... and the gradient every sub-pixel of an output pixel receives: a quarter of the pixel's cotangent, zero where the
+// clamp(-1,1) of the 2x2 mean is active
+__global__ void __launch_bounds__(PIX_THREADS)
+k_rgb_gquarter(int S, const float* __restrict__ rgb_map, const float* __restrict__ grad_rgb, int clampv, float* __restrict__ g4) {
+    const int is = 2 * S, b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
+    if (pix >= S * S) return;
+    const int i = pix / S, j = pix - i * S;
+    const float4* m = reinterpret_cast<const float4*>(rgb_map) + (long)b * is * is;
+    const float4 a = m[(long)(2 * i) * is + 2 * j], bq = m[(long)(2 * i) * is + 2 * j + 1], c = m[(long)(2 * i + 1) * is + 2 * j],
+                 d = m[(long)(2 * i + 1) * is + 2 * j + 1];
+    const float v[3] = {(a.x + bq.x + c.x + d.x) * 0.25f, (a.y + bq.y + c.y + d.y) * 0.25f, (a.z + bq.z + c.z + d.z) * 0.25f};
+    float g[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        g[k] = grad_rgb[((long)b * 3 + k) * S * S + pix] * 0.25f;
+        if (clampv && !(v[k] >= -1.f && v[k] <= 1.f)) g[k] = 0.f;
+    }
+    reinterpret_cast<float4*>(g4)[(long)b * S * S + pix] = make_float4(g[0], g[1], g[2], 0.f);
+}
+
+// One thread per face (fill_back copies included): for each edge and each axis walk the integer positions between the edge's
+// end points; "out" pass from the pixel just outside the edge to the image border (only when the pixel just inside belongs
+// to this face), "in" pass from the pixel just inside to the opposite edge over this face's own pixels; a visited pixel whose
+// colour difference to the pixel across the edge correlates positively with its gradient pulls the edge's two vertices by
+// diff_grad / dist.  The face's x / y gradients go to the per-view vertex-gradient scratch (uvz-).
+__global__ void __launch_bounds__(128)
+k_backward_pixel_map(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ proj,
+                     const float* __restrict__ rgb_map, const float* __restrict__ g4, float eps, float* __restrict__ vgrad) {
+    const int S = cam.S, is = 2 * S, b = blockIdx.y, Q = (S - 1) * (S - 1);
+    const int fn = blockIdx.x * 128 + threadIdx.x;
+    if (fn >= 4 * Q) return;
+    int vidx[3];
+    face_vertices(fn, S, vidx);
+    const float4* pv = reinterpret_cast<const float4*>(proj) + (long)b * S * S;
+    float face[9];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const float4 q = __ldg(&pv[vidx[m]]);
+        face[3 * m] = q.x; face[3 * m + 1] = q.y; face[3 * m + 2] = q.z;
+    }
+    if (mul(sub(face[7], face[1]), sub(face[3], face[0])) < mul(sub(face[4], face[1]), sub(face[6], face[0]))) return;
+    const int* fmap = face_idx + (long)b * is * is;
+    const float4* cmap = reinterpret_cast<const float4*>(rgb_map) + (long)b * is * is;
+    const float4* gmap = reinterpret_cast<const float4*>(g4) + (long)b * S * S;
+    // maps are stored in image orientation: nr's row yi (counting upwards) is row is - 1 - yi
+    auto at = [&](int xi, int yi) { return (long)(is - 1 - yi) * is + xi; };
+    auto gat = [&](int xi, int yi) { return (long)((is - 1 - yi) >> 1) * S + (xi >> 1); };
+    float grad_face[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) grad_face[k] = 0.f;
+    // arithmetic as the original evaluates it: un-fused fp32, `* 2. / is` in double
+    const float fis = (float)is;
+    const double dis = (double)is;
+#pragma unroll 1
+    for (int edge_num = 0; edge_num < 3; edge_num++) {
+        const int pi0 = edge_num, pi1 = (edge_num + 1) % 3, pi2 = (edge_num + 2) % 3;
+        const float pp[3][2] = {{ndc_to_pix(face[3 * pi0], is), ndc_to_pix(face[3 * pi0 + 1], is)},
+                                {ndc_to_pix(face[3 * pi1], is), ndc_to_pix(face[3 * pi1 + 1], is)},
+                                {ndc_to_pix(face[3 * pi2], is), ndc_to_pix(face[3 * pi2 + 1], is)}};
+#pragma unroll 1
+        for (int axis = 0; axis < 2; axis++) {
+            float p[3][2];
+#pragma unroll
+            for (int num = 0; num < 3; num++) { p[num][0] = pp[num][axis]; p[num][1] = pp[num][1 - axis]; }
+            const int direction = axis == 0 ? (p[0][0] < p[1][0] ? -1 : 1) : (p[0][0] < p[1][0] ? 1 : -1);
+            const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
+            const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), fis - 1.f);
+#pragma unroll 1
+            for (int d0 = d0_from; d0 <= d0_to; d0++) {
+                const float fd0 = (float)d0;
+                const float d1_cross = add(mul(dvd(sub(p[1][1], p[0][1]), sub(p[1][0], p[0][0])), sub(fd0, p[0][0])), p[0][1]);
+                if (!(fabsf(d1_cross) < 1.0e9f)) continue;          // zero-extent edge on an integer position: 0/0
+                const int d1_in = 0 < direction ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
+                const int d1_out = d1_in + direction;
+                if (d1_in < 0 || is <= d1_in || d1_out < 0 || is <= d1_out) continue;
+                const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
+                const int xout = axis == 0 ? d0 : d1_out, yout = axis == 0 ? d1_out : d0;
+                const float4 rgb_in = cmap[at(xin, yin)], rgb_out = cmap[at(xout, yout)];
+                auto pull = [&](float diff_grad, int d1) {
+                    const float along = sub((float)d1, d1_cross), span = sub(p[1][0], p[0][0]);
+                    if (p[1][0] != fd0) {
+                        float dist = (float)((double)mul(dvd(span, sub(p[1][0], fd0)), along) * 2. / dis);
+                        dist = 0.f < dist ? add(dist, eps) : sub(dist, eps);
+                        grad_face[pi0 * 3 + (1 - axis)] = sub(grad_face[pi0 * 3 + (1 - axis)], dvd(diff_grad, dist));
+                    }
+                    if (p[0][0] != fd0) {
+                        float dist = (float)((double)mul(dvd(span, sub(fd0, p[0][0])), along) * 2. / dis);
+                        dist = 0.f < dist ? add(dist, eps) : sub(dist, eps);
+                        grad_face[pi1 * 3 + (1 - axis)] = sub(grad_face[pi1 * 3 + (1 - axis)], dvd(diff_grad, dist));
+                    }
+                };
+                // out
+                if (fmap[at(xin, yin)] == fn) {
+                    const int d1_limit = 0 < direction ? is - 1 : 0;
+                    const int d1_from = max(min(d1_out, d1_limit), 0), d1_to = min(max(d1_out, d1_limit), is - 1);
+#pragma unroll 1
+                    for (int d1 = d1_from; d1 <= d1_to; d1++) {
+                        const int x = axis == 0 ? d0 : d1, y = axis == 0 ? d1 : d0;
+                        const float4 cc = cmap[at(x, y)], gg = gmap[gat(x, y)];
+                        const float diff_grad = add(add(add(0.f, mul(sub(cc.x, rgb_in.x), gg.x)), mul(sub(cc.y, rgb_in.y), gg.y)),
+                                                    mul(sub(cc.z, rgb_in.z), gg.z));
+                        if (diff_grad <= 0.f) continue;
+                        pull(diff_grad, d1);
+                    }
+                }
+                // in
+                {
+                    float d0_cross2;
+                    if (mul(sub(fd0, p[0][0]), sub(fd0, p[2][0])) < 0.f)
+                        d0_cross2 = add(mul(dvd(sub(p[2][1], p[0][1]), sub(p[2][0], p[0][0])), sub(fd0, p[0][0])), p[0][1]);
+                    else
+                        d0_cross2 = add(mul(dvd(sub(p[1][1], p[2][1]), sub(p[1][0], p[2][0])), sub(fd0, p[2][0])), p[2][1]);
+                    if (!(fabsf(d0_cross2) < 1.0e9f)) continue;
+                    const int d1_limit = 0 < direction ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
+                    const int d1_from = max(min(d1_in, d1_limit), 0), d1_to = min(max(d1_in, d1_limit), is - 1);
+#pragma unroll 1
+                    for (int d1 = d1_from; d1 <= d1_to; d1++) {
+                        const int x = axis == 0 ? d0 : d1, y = axis == 0 ? d1 : d0;
+                        if (fmap[at(x, y)] != fn) continue;
+                        const float4 cc = cmap[at(x, y)], gg = gmap[gat(x, y)];
+                        const float diff_grad = add(add(add(0.f, mul(sub(cc.x, rgb_out.x), gg.x)), mul(sub(cc.y, rgb_out.y), gg.y)),
+                                                    mul(sub(cc.z, rgb_out.z), gg.z));
+                        if (diff_grad <= 0.f) continue;
+                        pull(diff_grad, d1);
+                    }
+                }
+            }
+        }
+    }
+    float4* vg = reinterpret_cast<float4*>(vgrad) + (long)b * S * S;
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+        if (grad_face[3 * m] != 0.f || grad_face[3 * m + 1] != 0.f)
+            atomicAdd(&vg[vidx[m]], make_float4(grad_face[3 * m], grad_face[3 * m + 1], 0.f, 0.f));
 }
 
 template <int C>
@@ -1437,8 +1675,60 @@ inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, in
 
 }  // namespace
 
+// caller-owned context (include/g2s_b200.h): the streams / events of the multi-lane forward and the tuning read from the
+// environment at creation
+struct g2s_context {
+    int device;
+    int lanes;                       // forward lanes the host asked for through the environment (0 = library default)
+    bool no_pipeline;
+    cudaStream_t aux[MAX_LANES];     // aux[0] unused: lane 0 is the caller's stream
+    cudaEvent_t ev_fork, ev_join[MAX_LANES];
+};
+
 // =================================================================================================
 extern "C" {
+
+int g2s_context_create(g2s_context** out) {
+    if (!out) return G2S_ERR_NULL;
+    *out = nullptr;
+    g2s_context* c = new (std::nothrow) g2s_context();
+    if (!c) return G2S_ERR_LAUNCH;
+    if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; return G2S_ERR_LAUNCH; }
+    const char* e = getenv("G2S_FWD_LANES");
+    c->lanes = e ? atoi(e) : 0;
+    c->no_pipeline = getenv("G2S_NO_PIPELINE") != nullptr;
+    bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 1; k < MAX_LANES && ok; k++)
+        ok = cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { g2s_context_destroy(c); return G2S_ERR_LAUNCH; }
+    *out = c;
+    return G2S_OK;
+}
+
+void g2s_context_destroy(g2s_context* c) {
+    if (!c) return;
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int k = 1; k < MAX_LANES; k++) {
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+        if (c->aux[k]) cudaStreamDestroy(c->aux[k]);
+    }
+    delete c;
+}
+
+size_t g2s_workspace_bytes(int kind, int n, int image_size) {
+    if (n <= 0 || bad_size(image_size)) return 0;
+    const size_t S2 = (size_t)image_size * image_size, f = sizeof(float);
+    switch (kind) {
+        case G2S_WS_ZBUFFER: return g2s_zbuffer_bytes(n, image_size);
+        case G2S_WS_RASTER_BWD: return (size_t)n * 9 * S2 * f;
+        case G2S_WS_TEX_BWD: return (size_t)n * 4 * S2 * f;
+        case G2S_WS_TEXELS: return (size_t)n * 8 * S2 * f;
+        case G2S_WS_GRAD_NORMAL: return (size_t)n * 3 * S2 * f;
+        case G2S_WS_RGB_MAP: return (size_t)n * 20 * S2 * f;      // colour map [n,2S,2S,4] + quarter gradient [n,S,S,4]
+        default: return 0;
+    }
+}
 
 int g2s_version(void) { return 100; }
 
@@ -1564,8 +1854,9 @@ int g2s_sample_bwd(const float* input, long input_batch_stride, const float* gri
 // win): cap the chunk by scratch memory only (~1 GB)
 int g2s_chunk_views_bwd(int image_size) {
     if (bad_size(image_size)) return 0;
-    if (const char* e = getenv("G2S_CHUNK_VIEWS_BWD_128")) {
-        const long v = atol(e) * 128L * 128L / ((long)image_size * image_size);
+    static const long env128 = [] { const char* e = getenv("G2S_CHUNK_VIEWS_BWD_128"); return e ? atol(e) : 0L; }();
+    if (env128 > 0) {
+        const long v = env128 * 128L * 128L / ((long)image_size * image_size);
         if (v >= 1) return (int)v;
     }
     const long per_view = 13L * image_size * image_size * 4;   // 9 S^2 (raster scratch) + 4 S^2 (packed texture gradient)
@@ -1575,15 +1866,16 @@ int g2s_chunk_views_bwd(int image_size) {
 
 int g2s_chunk_views(int image_size) {
     if (bad_size(image_size)) return 0;
-    // tuning override (views per chunk at 128^2; scaled by (128/S)^2): G2S_CHUNK_VIEWS_128
-    if (const char* e = getenv("G2S_CHUNK_VIEWS_128")) {
-        const long v = atol(e) * 128L * 128L / ((long)image_size * image_size);
+    // tuning override (views per chunk at 128^2; scaled by (128/S)^2): G2S_CHUNK_VIEWS_128, read once
+    static const long env128 = [] { const char* e = getenv("G2S_CHUNK_VIEWS_128"); return e ? atol(e) : 0L; }();
+    if (env128 > 0) {
+        const long v = env128 * 128L * 128L / ((long)image_size * image_size);
         if (v >= 1) return (int)v;
     }
     return chunk_views_for(image_size, 1 << 20);
 }
 
-int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
                          int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
                          const float* mask_in, float* mask_out, void* stream) {
@@ -1610,41 +1902,42 @@ int g2s_render_fused_fwd(const g2s_camera* cam, const float* depth, const float*
     const int rec = g2s_chunk_views(S);
     int nl = (int)(ws_views / rec);                    // lanes the workspace has room for
     if (nl > MAX_LANES) nl = MAX_LANES;
-    if (const char* e = getenv("G2S_FWD_LANES")) { const int v = atoi(e); if (v >= 1 && v < nl) nl = v; }
-    if (nl < 1 || n_views <= rec || g_prof_on || getenv("G2S_NO_PIPELINE")) nl = 1;
+    if (ctx && ctx->lanes >= 1 && ctx->lanes < nl) nl = ctx->lanes;
+    if (!ctx || ctx->no_pipeline || nl < 1 || n_views <= rec || g_prof_on) nl = 1;
+    if (nl > 1) {      // the context's streams belong to one device
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev != ctx->device) nl = 1;
+    }
     const int per = nl > 1 ? rec : (ws_views >= rec ? rec : ws_views);   // views per chunk
     const int chunk = per < 32768 ? per : 32768;
     cudaStream_t lanes[MAX_LANES] = {st, st, st, st};
-    cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     if (nl > 1) {
-        if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return G2S_ERR_LAUNCH;
-        cudaEventRecord(ev_fork, st);
+        cudaEventRecord(ctx->ev_fork, st);
         for (int k = 1; k < nl; k++) {
-            lanes[k] = aux_stream(k);
-            if (!lanes[k] || cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming) != cudaSuccess) return G2S_ERR_LAUNCH;
-            cudaStreamWaitEvent(lanes[k], ev_fork, 0);
+            lanes[k] = ctx->aux[k];
+            cudaStreamWaitEvent(lanes[k], ctx->ev_fork, 0);
         }
     }
-    int lane = 0;
+    int lane = 0, rc_lane = 0;
     for (long v0 = 0; v0 < n_views; v0 += chunk, lane = (lane + 1) % nl) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         cudaStream_t ls = lanes[lane];
         unsigned long long* zb = (unsigned long long*)zbuf + (size_t)lane * ws_words(chunk, S);   // this lane's part
-        if (int rc = launch_splat<false>(c, depth, (long)S * S, views_per_image, R, t, nullptr, zb, chunk, nv, (int)v0, ls))
-            return rc;
+        if (int rc = launch_splat<false>(c, depth, (long)S * S, views_per_image, R, t, nullptr, zb, chunk, nv, (int)v0, ls)) {
+            rc_lane = rc;      // the lanes are still joined back below
+            break;
+        }
         FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0, mask_in, mask_out};
         { Launch l_(K_RESOLVE_FUSED, ls);
           k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, ls>>>(c, zb, recon_depth, face_idx, fa); }
     }
     if (nl > 1) {
         for (int k = 1; k < nl; k++) {
-            cudaEventRecord(ev_join[k], lanes[k]);
-            cudaStreamWaitEvent(st, ev_join[k], 0);
-            cudaEventDestroy(ev_join[k]);      // released by the runtime once it has completed
+            cudaEventRecord(ctx->ev_join[k], lanes[k]);
+            cudaStreamWaitEvent(st, ctx->ev_join[k], 0);
         }
-        cudaEventDestroy(ev_fork);
     }
-    return launch_status();
+    return rc_lane ? rc_lane : launch_status();
 }
 
 int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
@@ -1756,6 +2049,39 @@ int g2s_grid3d_fwd(const g2s_camera* cam, const float* depth, long depth_view_st
     return launch_status();
 }
 
+int g2s_grid3d_bwd(const g2s_camera* cam, const float* depth, long depth_view_stride, int B, int H, int W, int mode,
+                   const float* R, const float* t, const float* grad_out, float* grad_depth, float* grad_R, float* grad_t,
+                   void* stream) {
+    if (!cam || !depth || !grad_out || !grad_depth) return G2S_ERR_NULL;
+    if (mode < 0 || mode > 2) return G2S_ERR_UNSUPPORTED;
+    if (mode != 0 && (!R || !t)) return G2S_ERR_NULL;
+    if ((grad_R == nullptr) != (grad_t == nullptr)) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 2 || W < 2) return G2S_ERR_SHAPE;
+    { Launch l_(K_GRID3D, (cudaStream_t)stream);
+      k_grid3d_bwd<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(
+          make_cam(cam), depth, depth_view_stride, H, W, mode, R, t, grad_out, grad_depth, mode == 0 ? nullptr : grad_R,
+          mode == 0 ? nullptr : grad_t); }
+    return launch_status();
+}
+
+int g2s_grid_3d_to_2d_fwd(const g2s_camera* cam, const float* grid3d, int B, int H, int W, float* grid, void* stream) {
+    if (!cam || !grid3d || !grid) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 2 || W < 2) return G2S_ERR_SHAPE;
+    { Launch l_(K_GRID_FWD, (cudaStream_t)stream);
+      k_grid_3d_to_2d_fwd<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(make_cam(cam), grid3d, H, W, grid); }
+    return launch_status();
+}
+
+int g2s_grid_3d_to_2d_bwd(const g2s_camera* cam, const float* grid3d, int B, int H, int W, const float* grad_grid,
+                          float* grad_grid3d, void* stream) {
+    if (!cam || !grid3d || !grad_grid || !grad_grid3d) return G2S_ERR_NULL;
+    if (B <= 0 || B > 65535 || H < 2 || W < 2) return G2S_ERR_SHAPE;
+    { Launch l_(K_GRID_BWD, (cudaStream_t)stream);
+      k_grid_3d_to_2d_bwd<<<pix_grid((long)H * W, B), PIX_THREADS, 0, (cudaStream_t)stream>>>(make_cam(cam), grid3d, H, W, grad_grid,
+                                                                                            grad_grid3d); }
+    return launch_status();
+}
+
 int g2s_render_rgb_fwd(const g2s_camera* cam, const float* vertices3d, const float* im, long im_view_stride,
                        int n_views, int C, int tex_cube_size, const float* bg, int clamp, void* zbuf, float* rgb,
                        int32_t* face_idx, void* stream) {
@@ -1817,23 +2143,43 @@ int g2s_render_depth_bwd(const g2s_camera* cam, const float* vertices3d, int n_v
 
 int g2s_render_rgb_bwd(const g2s_camera* cam, const float* vertices3d, const float* im, long im_view_stride, int n_views,
                        int C, int tex_cube_size, const float* bg, int clamp, const int32_t* face_idx, const float* grad_rgb,
-                       float* grad_im, long grad_im_view_stride, void* stream) {
-    if (!cam || !vertices3d || !im || !bg || !face_idx || !grad_rgb || !grad_im) return G2S_ERR_NULL;
+                       float* grad_im, long grad_im_view_stride, float* rgb_ws, float* raster_ws, float* grad_vertices,
+                       void* stream) {
+    if (!cam || !vertices3d || !im || !bg || !face_idx || !grad_rgb) return G2S_ERR_NULL;
+    if (!grad_im && !grad_vertices) return G2S_ERR_NULL;
+    if (grad_vertices && (!rgb_ws || !raster_ws)) return G2S_ERR_NULL;
     if (n_views <= 0 || n_views > 65535 || bad_size(cam->image_size) || C < 1 || C > 4) return G2S_ERR_SHAPE;
-    if (tex_cube_size != 2) return G2S_ERR_UNSUPPORTED;
+    if (tex_cube_size != 2 || (grad_vertices && C != 3)) return G2S_ERR_UNSUPPORTED;
     const Cam c = make_cam(cam);
-    const int S = c.S;
+    const int S = c.S, is = 2 * S;
     cudaStream_t st = (cudaStream_t)stream;
     Bg b4 = {{0.f, 0.f, 0.f, 0.f}};
     for (int i = 0; i < C; i++) b4.c[i] = bg[i];
     const float eps = 1e-3f;  // nr.Renderer.rasterizer_eps
     const dim3 g = pix_grid((long)S * S, n_views);
-    Launch l_(K_RESOLVE_RGB, st);
-    switch (C) {
-        case 1: k_resolve_rgb_bwd<1><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
-        case 2: k_resolve_rgb_bwd<2><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
-        case 3: k_resolve_rgb_bwd<3><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
-        default: k_resolve_rgb_bwd<4><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+    if (grad_im) {
+        Launch l_(K_RESOLVE_RGB, st);
+        switch (C) {
+            case 1: k_resolve_rgb_bwd<1><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+            case 2: k_resolve_rgb_bwd<2><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+            case 3: k_resolve_rgb_bwd<3><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+            default: k_resolve_rgb_bwd<4><<<g, PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, clamp, grad_rgb, grad_im, grad_im_view_stride); break;
+        }
+    }
+    if (grad_vertices) {
+        const size_t img = (size_t)S * S;
+        float* rgb_map = rgb_ws;                                  // [n, 2S, 2S, 4]
+        float* g4 = rgb_ws + (size_t)n_views * 16 * img;          // [n, S, S, 4]
+        float* proj = raster_ws;
+        float* vgrad = proj + (size_t)n_views * 4 * img;
+        Launch l_(K_RESOLVE_RGB, st);
+        k_rgb_map<<<pix_grid((long)is * is, n_views), PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, rgb_map);
+        k_rgb_gquarter<<<g, PIX_THREADS, 0, st>>>(S, rgb_map, grad_rgb, clamp, g4);
+        cudaMemsetAsync(vgrad, 0, sizeof(float) * n_views * 4 * img, st);
+        k_project_points<<<g, PIX_THREADS, 0, st>>>(c, vertices3d, proj);
+        const int Q4 = 4 * (S - 1) * (S - 1);
+        k_backward_pixel_map<<<dim3((Q4 + 127) / 128, n_views), 128, 0, st>>>(c, face_idx, proj, rgb_map, g4, eps, vgrad);
+        k_points_bwd<<<g, PIX_THREADS, 0, st>>>(c, vertices3d, vgrad, grad_vertices);
     }
     return launch_status();
 }

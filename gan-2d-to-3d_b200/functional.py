@@ -66,23 +66,44 @@ def _Rt(R, t, B):
 
 
 class ZBuffer:
-    """Packed-key z-buffer workspace owned by a Renderer (one per (far) value, grown on demand).
-    The forward kernels leave it re-initialised, so it is filled only when (re)allocated."""
+    """Packed-key z-buffer workspaces owned by a Renderer: one per (far value, device, CUDA stream), grown on demand.
+    Every word is the EMPTY key at rest (g2s_zbuffer_init) and every forward leaves it so; a buffer is therefore only
+    filled when it is (re)allocated.  Separate streams get separate buffers (two streams rasterising into one buffer would
+    race on its keys), a buffer that is replaced by a larger one is handed to the caching allocator with `record_stream`,
+    and `invalidate()` -- called when a launch reports an error -- drops every buffer so that the next call re-initialises."""
 
     def __init__(self):
         self.buf = {}
 
     def get(self, n_views, S, far, device):
-        key = (float(far), device)
+        stream = torch.cuda.current_stream(device)
+        key = (float(far), device, stream.cuda_stream)
         lib = _lib.load()
-        need = (lib.g2s_zbuffer_bytes(n_views, S) + 7) // 8     # keys + work list + counters
+        need = (lib.g2s_workspace_bytes(_lib.WS_ZBUFFER, n_views, S) + 7) // 8     # keys + work list + counters
         cur = self.buf.get(key)
         if cur is None or cur.numel() < need:
+            if cur is not None:
+                cur.record_stream(stream)
             cur = torch.empty(need, dtype=torch.int64, device=device)
-            # the buffer is addressed per view, so initialise it as `n_views` views of side S
+            # laid out per view by every call, so initialise it as `n_views` views of side S: uniformly EMPTY
             _lib.check(lib.g2s_zbuffer_init(_p(cur), n_views, S, far, _stream()), "g2s_zbuffer_init")
             self.buf[key] = cur
         return cur
+
+    def invalidate(self):
+        self.buf.clear()
+
+
+def _checked(renderer, code, what):
+    """_lib.check that also drops the renderer's z-buffers on failure (a failed forward may leave stale keys behind)"""
+    if code != 0:
+        renderer._zbuf.invalidate()
+    _lib.check(code, what)
+
+
+def _ws(kind, n, S, device):
+    """caller-owned workspace sized by g2s_workspace_bytes"""
+    return torch.empty(_lib.ws_floats(kind, n, S), device=device, dtype=torch.float32)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -103,8 +124,8 @@ class WarpCanonDepthFn(torch.autograd.Function):
         zbuf = renderer._zbuf.get(B, S, cam.far_z, depth.device)
         recon = torch.empty(B, S, S, device=depth.device, dtype=torch.float32)
         fidx = torch.empty(B, 2 * S, 2 * S, device=depth.device, dtype=torch.int32)
-        _lib.check(lib.g2s_warp_depth_fwd(ctypes.byref(cam), _p(dstore), dstride, _p(Rc), _p(tc), B, _p(zbuf),
-                                          _p(recon), _p(fidx), _stream()), "g2s_warp_depth_fwd")
+        _checked(renderer, lib.g2s_warp_depth_fwd(ctypes.byref(cam), _p(dstore), dstride, _p(Rc), _p(tc), B, _p(zbuf),
+                                                  _p(recon), _p(fidx), _stream()), "g2s_warp_depth_fwd")
         ctx.save_for_backward(dstore, Rc, tc, fidx, recon)
         ctx.dstride = dstride
         ctx.renderer = renderer
@@ -122,7 +143,7 @@ class WarpCanonDepthFn(torch.autograd.Function):
         (B, S, _), Rshape, tshape = ctx.shapes
         cam = ctx.renderer._camera(depth_pass=True)
         g = _f32c(g_recon)
-        ws = torch.empty(B, 9, S, S, device=g.device, dtype=torch.float32)   # projected verts | vertex grads (uvz-) | g_sub
+        ws = _ws(_lib.WS_RASTER_BWD, B, S, g.device)             # projected verts | vertex grads (uvz-) | g_sub
         g_depth = torch.zeros(B, S, S, device=g.device, dtype=torch.float32)
         need_view = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         gR = torch.zeros(B, 3, 3, device=g.device, dtype=torch.float32) if need_view else None
@@ -325,17 +346,17 @@ class RenderChainFn(torch.autograd.Function):
         # z-buffer for FWD_LANES chunks: the forward rotates its chunks over that many lanes (streams)
         ws_views = min(B, FWD_LANES * lib.g2s_chunk_views(S))
         zbuf = renderer._zbuf.get(ws_views, S, cam.far_z, dev)
-        normal = torch.empty(N, S, S, 8, device=dev, dtype=torch.float32)    # packed texels: normal xyz, albedo rgb, pad
+        normal = _ws(_lib.WS_TEXELS, N, S, dev)               # packed texels [N,S,S,8]: normal xyz, albedo rgb, pad
         recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
         recon_depth = torch.empty(B, S, S, device=dev, dtype=torch.float32)
         fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)
         mask_in = _f32c(mask.reshape(N, S, S)) if mask is not None else None
         mask_out = torch.empty(B, 1, S, S, device=dev, dtype=torch.float32) if want_mask else None
-        _lib.check(lib.g2s_render_fused_fwd(ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N,
-                                            views_per_image, int(bool(align_corners)), _p(zbuf), ws_views,
-                                            _p(normal), _p(recon_im), _p(recon_depth), _p(fidx), _p(mask_in),
-                                            _p(mask_out), _stream()),
-                   "g2s_render_fused_fwd")
+        _checked(renderer, lib.g2s_render_fused_fwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc),
+                                                    _p(tc), _p(L), N, views_per_image, int(bool(align_corners)), _p(zbuf),
+                                                    ws_views, _p(normal), _p(recon_im), _p(recon_depth), _p(fidx),
+                                                    _p(mask_in), _p(mask_out), _stream()),
+                 "g2s_render_fused_fwd")
         ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape)
         ctx.mark_non_differentiable(fidx)
@@ -361,9 +382,9 @@ class RenderChainFn(torch.autograd.Function):
         gi = _f32c(g_im) if g_im is not None else torch.zeros(B, 3, S, S, device=dev)
         gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
         ws_views = min(B, lib.g2s_chunk_views_bwd(S))
-        ws_sub = torch.empty(ws_views, 9, S, S, device=dev, dtype=torch.float32)   # projected verts | vertex grads (uvz-) | g_sub
-        ws_tex = torch.empty(ws_views, S, S, 4, device=dev, dtype=torch.float32)
-        ws_nrm = torch.empty(N, S, S, 3, device=dev, dtype=torch.float32)
+        ws_sub = _ws(_lib.WS_RASTER_BWD, ws_views, S, dev)     # projected verts | vertex grads (uvz-) | g_sub
+        ws_tex = _ws(_lib.WS_TEX_BWD, ws_views, S, dev)
+        ws_nrm = _ws(_lib.WS_GRAD_NORMAL, N, S, dev)
         g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)
         g_albedo = torch.empty(N, 3, S, S, device=dev, dtype=torch.float32)
         gR = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
@@ -382,8 +403,8 @@ class RenderChainFn(torch.autograd.Function):
 class RenderRgbFn(torch.autograd.Function):
     """nr.Renderer.render_rgb(vertices, get_face_idx, get_textures_from_im(im, 2)) (+ clamp) as renderer.py:194-196,
     230, 248, 272, 275 call it.  Differentiable with respect to `im` (the per-vertex colours: neural_renderer's
-    backward_textures through get_textures_from_im); the geometry gets no gradient (nr's approximate backward_pixel_map is
-    not built: the reference never differentiates render_rgb, SURVEY.md 8a')."""
+    backward_textures through get_textures_from_im) and with respect to the vertices (neural_renderer's approximate
+    backward_pixel_map edge gradient chained through the projection; 3-channel images)."""
 
     @staticmethod
     def forward(ctx, vertices3d, im, renderer, clamp):
@@ -406,8 +427,9 @@ class RenderRgbFn(torch.autograd.Function):
         out = torch.empty(B, C, S, S, device=im.device, dtype=torch.float32)
         fidx = torch.empty(B, 2 * S, 2 * S, device=im.device, dtype=torch.int32)
         bg = (ctypes.c_float * 4)(*([renderer.background_color[i % 3] for i in range(4)]))
-        _lib.check(lib.g2s_render_rgb_fwd(ctypes.byref(cam), _p(verts), _p(istore), istride, B, C, renderer.tex_cube_size,
-                                          bg, int(clamp), _p(zbuf), _p(out), _p(fidx), _stream()), "g2s_render_rgb_fwd")
+        _checked(renderer, lib.g2s_render_rgb_fwd(ctypes.byref(cam), _p(verts), _p(istore), istride, B, C,
+                                                  renderer.tex_cube_size, bg, int(clamp), _p(zbuf), _p(out), _p(fidx),
+                                                  _stream()), "g2s_render_rgb_fwd")
         ctx.save_for_backward(verts, istore, fidx)
         ctx.meta = (renderer, int(clamp), istride, im.shape)
         ctx.mark_non_differentiable(fidx)
@@ -416,7 +438,8 @@ class RenderRgbFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, _g_fidx):
-        if g_out is None or not ctx.needs_input_grad[1]:
+        need_v, need_im = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_out is None or not (need_v or need_im):
             return None, None, None, None
         lib = _lib.load()
         verts, istore, fidx = ctx.saved_tensors
@@ -425,14 +448,89 @@ class RenderRgbFn(torch.autograd.Function):
         g = _f32c(g_out)
         B = g.shape[0]
         cam = renderer._camera(rgb_pass=True)
-        g_im = torch.zeros(istore.shape, device=g.device, dtype=torch.float32)    # [C,S,S] when shared, else [B,C,S,S]
+        if need_v and C != 3:
+            raise RuntimeError("render_rgb: the geometry gradient (backward_pixel_map) needs a 3-channel image")
+        g_im = torch.zeros(istore.shape, device=g.device, dtype=torch.float32) if need_im else None    # [C,S,S] when shared
+        g_v = torch.empty_like(verts) if need_v else None
+        rgb_ws = _ws(_lib.WS_RGB_MAP, B, S, g.device) if need_v else None
+        ras_ws = _ws(_lib.WS_RASTER_BWD, B, S, g.device) if need_v else None
         bg = (ctypes.c_float * 4)(*([renderer.background_color[i % 3] for i in range(4)]))
         _lib.check(lib.g2s_render_rgb_bwd(ctypes.byref(cam), _p(verts), _p(istore), istride, B, C, renderer.tex_cube_size,
-                                          bg, clamp, _p(fidx), _p(g), _p(g_im), istride, _stream()), "g2s_render_rgb_bwd")
-        if istride == 0:
+                                          bg, clamp, _p(fidx), _p(g), _p(g_im), istride, _p(rgb_ws), _p(ras_ws), _p(g_v),
+                                          _stream()), "g2s_render_rgb_bwd")
+        if need_im and istride == 0:
             if imshape[0] != 1:
                 # an `expand`ed [B,C,S,S] view of one image: autograd will sum B identical slices back onto it
                 g_im = (g_im / imshape[0]).unsqueeze(0).expand(imshape)
             else:
                 g_im = g_im.unsqueeze(0)
-        return None, g_im, None, None
+        return g_v, g_im, None, None
+
+
+class Grid3dFn(torch.autograd.Function):
+    """renderer.py:74-80 depth_to_3d_grid (mode 0), :90-95 get_warped_3d_grid (1), :97-102 get_inv_warped_3d_grid (2):
+    depth [B,H,W] (+ R [B,3,3], t [B,1,3]) -> [B,H,W,3]."""
+
+    @staticmethod
+    def forward(ctx, depth, R, t, renderer, mode):
+        _require_cuda(depth, R, t)
+        lib = _lib.load()
+        B, H, W = depth.shape
+        dstore, dstride = _batched_image(depth)
+        Rc = tc = None
+        if mode != 0:
+            Rc, tc = _Rt(R, t, B)
+        cam = renderer._camera()
+        out = torch.empty(B, H, W, 3, device=depth.device, dtype=torch.float32)
+        R0, t0, R2, t2 = (Rc, tc, None, None) if mode == 2 else (None, None, Rc, tc)
+        _lib.check(lib.g2s_grid3d_fwd(ctypes.byref(cam), _p(dstore), dstride, B, H, W, None, _p(R0), _p(t0), None, _p(R2),
+                                      _p(t2), _p(out), _stream()), "g2s_grid3d_fwd")
+        ctx.save_for_backward(dstore, Rc, tc)
+        ctx.meta = (dstride, renderer, mode, depth.shape, None if R is None else R.shape, None if t is None else t.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        dstore, Rc, tc = ctx.saved_tensors
+        dstride, renderer, mode, (B, H, W), Rshape, tshape = ctx.meta
+        cam = renderer._camera()
+        g = _f32c(g_out)
+        g_depth = torch.empty(B, H, W, device=g.device, dtype=torch.float32)
+        need_view = mode != 0 and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        gR = torch.zeros(B, 3, 3, device=g.device, dtype=torch.float32) if need_view else None
+        gt = torch.zeros(B, 3, device=g.device, dtype=torch.float32) if need_view else None
+        _lib.check(lib.g2s_grid3d_bwd(ctypes.byref(cam), _p(dstore), dstride, B, H, W, mode, _p(Rc), _p(tc), _p(g),
+                                      _p(g_depth), _p(gR), _p(gt), _stream()), "g2s_grid3d_bwd")
+        if need_view:
+            gR = gR.sum_to_size(Rshape)
+            gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
+        return g_depth, gR, gt, None, None
+
+
+class Grid3dTo2dFn(torch.autograd.Function):
+    """renderer.py:82-88 grid_3d_to_2d: [B,H,W,3] -> [B,H,W,2] in [-1,1]."""
+
+    @staticmethod
+    def forward(ctx, grid_3d, renderer):
+        _require_cuda(grid_3d)
+        lib = _lib.load()
+        g3 = _f32c(grid_3d)
+        B, H, W, _ = g3.shape
+        cam = renderer._camera()
+        out = torch.empty(B, H, W, 2, device=g3.device, dtype=torch.float32)
+        _lib.check(lib.g2s_grid_3d_to_2d_fwd(ctypes.byref(cam), _p(g3), B, H, W, _p(out), _stream()), "g2s_grid_3d_to_2d_fwd")
+        ctx.save_for_backward(g3)
+        ctx.renderer = renderer
+        return out
+
+    @staticmethod
+    def backward(ctx, g_grid):
+        lib = _lib.load()
+        (g3,) = ctx.saved_tensors
+        B, H, W, _ = g3.shape
+        cam = ctx.renderer._camera()
+        out = torch.empty_like(g3)
+        _lib.check(lib.g2s_grid_3d_to_2d_bwd(ctypes.byref(cam), _p(g3), B, H, W, _p(_f32c(g_grid)), _p(out), _stream()),
+                   "g2s_grid_3d_to_2d_bwd")
+        return out, None

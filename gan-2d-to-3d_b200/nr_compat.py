@@ -12,8 +12,8 @@ extrinsics and moves the vertices itself), ambient light 1 / directional 0, anti
 grid-mesh topology of utils.py:76-80, texture cubes of size 2 built by utils.py:98-109.
 
 render_depth is differentiable with respect to the vertices (neural_renderer's approximate backward_depth_map gradient);
-render_rgb with respect to the textures (backward_textures) -- the geometry gradient of an rgb render is not built (the
-reference never asks for it).  CUDA tensors only; no CPU fallback.
+render_rgb with respect to the vertices (backward_pixel_map) and, through the image the cubes were built from, the textures'
+corner colours (backward_textures).  CUDA tensors only; no CPU fallback.
 """
 import ctypes
 
@@ -46,7 +46,7 @@ class _RenderDepthFn(torch.autograd.Function):
         v, fidx = ctx.saved_tensors
         B, S = v.shape[0], ctx.owner.image_size
         cam = ctx.owner._camera(depth_pass=True)
-        ws = torch.empty(B, 9, S, S, device=v.device, dtype=torch.float32)
+        ws = torch.empty(_lib.ws_floats(_lib.WS_RASTER_BWD, B, S), device=v.device, dtype=torch.float32)
         gv = torch.empty_like(v)
         _lib.check(lib.g2s_render_depth_bwd(ctypes.byref(cam), _p(v), B, _p(fidx), _p(_f32c(g)), _p(ws), _p(gv), _stream()),
                    "g2s_render_depth_bwd")
@@ -77,20 +77,26 @@ class Renderer:
         self.tex_cube_size = 2
         self._zbuf = ZBuffer()
         self._grid_faces = None
+        self._checked = set()      # (data_ptr, shape, device) of `faces` tensors already validated
+        self._cams = {}
 
     # the camera struct of the C ABI; render_depth uses neural_renderer's module defaults near=0.1, far=100 (the
     # constructor's near / far only reach render_rgb), exactly like the reference's Renderer._camera
     def _camera(self, depth_pass=False, rgb_pass=False):
-        cam = _lib.Camera()
-        K = self.K
-        invK = torch.inverse(K)
-        for i in range(9):
-            cam.K[i] = float(K.reshape(-1)[i])
-            cam.inv_K[i] = float(invK.reshape(-1)[i])
-        cam.rot_center_depth = 0.0
-        cam.near_z, cam.far_z = (0.1, 100.0) if depth_pass else (self.near, self.far)
-        cam.clamp_lo, cam.clamp_hi = -3.0e38, 3.0e38
-        cam.image_size = self.image_size
+        cam = self._cams.get(bool(depth_pass))
+        if cam is None:      # built once: the 3x3 inverse and the ctypes fill are host work that every render would repeat
+            cam = _lib.Camera()
+            K = self.K
+            invK = torch.inverse(K)
+            for i in range(9):
+                cam.K[i] = float(K.reshape(-1)[i])
+                cam.K_grid[i] = float(K.reshape(-1)[i])
+                cam.inv_K[i] = float(invK.reshape(-1)[i])
+            cam.rot_center_depth = 0.0
+            cam.near_z, cam.far_z = (0.1, 100.0) if depth_pass else (self.near, self.far)
+            cam.clamp_lo, cam.clamp_hi = -3.0e38, 3.0e38
+            cam.image_size = self.image_size
+            self._cams[bool(depth_pass)] = cam
         return cam
 
     def _check_mesh(self, vertices, faces):
@@ -101,10 +107,15 @@ class Renderer:
         F = 2 * (S - 1) * (S - 1)
         if faces.dim() != 3 or faces.shape[1] != F or faces.shape[2] != 3:
             raise RuntimeError("nr_compat: faces must be get_face_idx(b, S, S): [B,%d,3]" % F)
-        if self._grid_faces is None:
-            self._grid_faces = get_face_idx(1, S, S)[0]
-        if not torch.equal(faces[0].detach().to("cpu", torch.int32), self._grid_faces):
-            raise NotImplementedError("nr_compat: only the grid-mesh topology of utils.py:76-80 is supported")
+        key = (faces.data_ptr(), tuple(faces.shape), str(faces.device), faces._version)
+        if key not in self._checked:     # the device-to-host copy + compare is a blocking sync: once per faces tensor
+            if self._grid_faces is None:
+                self._grid_faces = get_face_idx(1, S, S)[0]
+            if not torch.equal(faces[0].detach().to("cpu", torch.int32), self._grid_faces):
+                raise NotImplementedError("nr_compat: only the grid-mesh topology of utils.py:76-80 is supported")
+            if len(self._checked) > 64:
+                self._checked.clear()
+            self._checked.add(key)
 
     def render_depth(self, vertices, faces):
         """[B,S*S,3], int32 [B,2(S-1)^2,3] -> [B,S,S] (background = 100, not clamped)."""

@@ -44,6 +44,7 @@ class Renderer:
         self._set_K(K.unsqueeze(0), torch.inverse(K).unsqueeze(0), origin=True)
         self.background_color = [1., 1., 1.]  # renderer.py:54
         self._zbuf = Fn.ZBuffer()
+        self._ctx = {}        # g2s_context per device (created on first use)
         self.rot_mat = None
         self.trans_xyz = None
         _lib.load()  # fail loudly at construction when the CUDA library is missing
@@ -69,9 +70,11 @@ class Renderer:
             cam = _lib.Camera()
             Ksrc = self._K_raster_host if (depth_pass or rgb_pass) else self._K_host
             K = Ksrc.reshape(-1).tolist()
+            Kg = self._K_host.reshape(-1).tolist()      # the grid operators always use the current K (renderer.py:82-88)
             iK = self._inv_K_host.reshape(-1).tolist()
             for i in range(9):
                 cam.K[i] = K[i]
+                cam.K_grid[i] = Kg[i]
                 cam.inv_K[i] = iK[i]
             cam.rot_center_depth = self.rot_center_depth
             if rgb_pass:
@@ -84,6 +87,16 @@ class Renderer:
             cam.image_size = self.image_size
             self._cams[key] = cam
         return cam
+
+    def _context(self, device):
+        """the caller-owned g2s_context of `device` (streams / events of the multi-lane forward)"""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        ctx = self._ctx.get(idx)
+        if ctx is None:
+            with torch.cuda.device(idx):
+                ctx = _lib.Context()
+            self._ctx[idx] = ctx
+        return ctx
 
     def downscale_K(self, downscale):
         """renderer.py:56-59 (does not reach the K the rasteriser captured, as in the reference)."""
@@ -110,6 +123,22 @@ class Renderer:
         return pts + trans_xyz
 
     # -- hot-path operators -------------------------------------------------------------------------
+    def depth_to_3d_grid(self, depth):
+        """renderer.py:74-80 -> [B,H,W,3]."""
+        return Fn.Grid3dFn.apply(depth, None, None, self, 0)
+
+    def grid_3d_to_2d(self, grid_3d):
+        """renderer.py:82-88 -> [B,H,W,2] in [-1,1]."""
+        return Fn.Grid3dTo2dFn.apply(grid_3d, self)
+
+    def get_warped_3d_grid(self, depth):
+        """renderer.py:90-95 -> [B,H,W,3]."""
+        return Fn.Grid3dFn.apply(depth, self.rot_mat, self.trans_xyz, self, 1)
+
+    def get_inv_warped_3d_grid(self, depth):
+        """renderer.py:97-102 -> [B,H,W,3]."""
+        return Fn.Grid3dFn.apply(depth, self.rot_mat, self.trans_xyz, self, 2)
+
     def get_warped_2d_grid(self, depth):
         """renderer.py:104-108."""
         return Fn.WarpGridFn.apply(depth, self.rot_mat, self.trans_xyz, self, False)
@@ -192,7 +221,8 @@ class Renderer:
 
     def _render_rgb(self, vertices3d, im, clamp=True, return_face_idx=False):
         """nr.Renderer.render_rgb(vertices, get_face_idx, get_textures_from_im(im, tex_cube_size)) +
-        clamp(-1,1) (renderer.py:194-196).  Differentiable with respect to `im` only (Fn.RenderRgbFn)."""
+        clamp(-1,1) (renderer.py:194-196).  Differentiable with respect to `im` (backward_textures) and to the vertices
+        (neural_renderer's approximate backward_pixel_map gradient): Fn.RenderRgbFn."""
         out, fidx = Fn.RenderRgbFn.apply(vertices3d, im, self, clamp)
         return (out, fidx) if return_face_idx else out
 

@@ -8,7 +8,9 @@
  *     (host memory, copied by value into the launch);
  *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or freed here;
  *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no host sync;
- *   - re-entrant, no global state apart from the instrumentation counters at the end of this header;
+ *   - re-entrant; the only process-wide state is the instrumentation at the end of this header and a per-device cache of
+ *     device attributes (SM count, the shared-memory opt-in of one kernel).  Streams and events the library needs for
+ *     its own pipelining live in a caller-owned g2s_context;
  *   - returns G2S_OK (0) or a negative G2S_ERR_* code; never throws.  The reference's neural_renderer
  *     extension reports the same class of failures through AT_ASSERTM -> RuntimeError
  *     (CHECK_CUDA / CHECK_CONTIGUOUS); the Python host layer turns non-zero codes into RuntimeError.
@@ -48,14 +50,37 @@ typedef struct g2s_camera {
     float clamp_lo;  /* min_depth - margin */
     float clamp_hi;  /* max_depth + margin */
     int32_t image_size;
+    float K_grid[9]; /* the CURRENT K of the grid operators (renderer.py:82-88 uses self.K, which downscale_K rescales), while
+                      * K above is what the rasteriser projects with: neural_renderer captures K at construction
+                      * (renderer.py:47-50) and downscale_K never reaches it.  Equal to K unless downscale_K was called. */
 } g2s_camera;
 
 int g2s_version(void);
 const char *g2s_error_string(int code);
 
-/* ---- z-buffer workspace -------------------------------------------------------------------
- * One packed 64-bit key (zp bits << 32 | face index) per sub-pixel: n_views * (2S)^2 * 8 bytes.
- * It must be initialised once with g2s_zbuffer_init; every forward call leaves it re-initialised. */
+/* ---- caller-owned context -------------------------------------------------------------------
+ * Holds what the library would otherwise keep in globals: the internal non-blocking streams and the fork / join events of
+ * the multi-lane forward (g2s_render_fused_fwd), created for the device that is current at creation time, and the tuning
+ * read once from the environment (G2S_FWD_LANES, G2S_NO_PIPELINE).  One context per device and per thread of use; a NULL
+ * context is accepted everywhere and means "no internal streams" (single lane). */
+typedef struct g2s_context g2s_context;
+int g2s_context_create(g2s_context **out);
+void g2s_context_destroy(g2s_context *ctx);
+
+/* ---- workspace sizes --------------------------------------------------------------------------
+ * Every workspace is caller-owned; g2s_workspace_bytes returns the bytes one needs (0 for bad arguments).
+ *   G2S_WS_ZBUFFER     forward z-buffer for n views: packed 64-bit keys (zp bits << 32 | face index) per sub-pixel, the work
+ *                      list of the rasteriser's second stage and its counters (same as g2s_zbuffer_bytes); must be
+ *                      initialised once with g2s_zbuffer_init, every forward leaves it re-initialised;
+ *   G2S_WS_RASTER_BWD  backward of the rasteriser for n views: [n,9,S,S] floats (projected vertices | vertex gradients |
+ *                      masked quarter gradient); 16-byte aligned;
+ *   G2S_WS_TEX_BWD     per-view texture gradient of the fused backward: [n,S,S,4] floats;
+ *   G2S_WS_TEXELS      packed texel map of the fused render for n IMAGES: [n,S,S,8] floats;
+ *   G2S_WS_GRAD_NORMAL normal-map gradient of the fused backward for n IMAGES: [n,S,S,3] floats;
+ *   G2S_WS_RGB_MAP     rgb backward for n views: supersampled colour map [n,2S,2S,4] + quarter gradient [n,S,S,4] floats. */
+enum { G2S_WS_ZBUFFER = 0, G2S_WS_RASTER_BWD = 1, G2S_WS_TEX_BWD = 2, G2S_WS_TEXELS = 3, G2S_WS_GRAD_NORMAL = 4,
+       G2S_WS_RGB_MAP = 5 };
+size_t g2s_workspace_bytes(int kind, int n, int image_size);
 size_t g2s_zbuffer_bytes(int n_views, int image_size);
 int g2s_zbuffer_init(void *zbuf, int n_views, int image_size, float far_z, void *stream);
 
@@ -116,7 +141,7 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * and the kernel that reads it; g2s_chunk_views(S) returns the recommended chunk (24 MB of z-buffer).  `ws_views` = views
  * the z-buffer workspace holds: with room for L >= 2 recommended chunks (and more views than one chunk) the chunks rotate
  * over L lanes (L <= 4; the Python host asks for 2, the measured optimum) -- one part of the workspace and one stream each:
- * `stream` and internal non-blocking streams (one set per device), forked from and joined back into `stream` with events
+ * `stream` and the non-blocking streams of `ctx` (NULL ctx: one lane), forked from and joined back into `stream` with events
  * (capturable in a CUDA graph) -- so that one chunk's rasteriser fills the SMs the tail of the previous one leaves idle;
  * otherwise one chunk of min(ws_views, recommended) views at a time on `stream` alone (also while per-kernel timing is on,
  * or with G2S_NO_PIPELINE set).  Workspaces: zbuf (g2s_zbuffer_bytes(ws_views, S), initialised), normal_ws [n_images,S,S,8] (packed texels: normal xyz,
@@ -127,7 +152,7 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * mask_out = NULL to skip. */
 int g2s_chunk_views(int image_size);
 int g2s_chunk_views_bwd(int image_size);   /* recommended ws_views of g2s_render_fused_bwd (~1 GB of scratch) */
-int g2s_render_fused_fwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
+int g2s_render_fused_fwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
                          float *recon_depth, int32_t *face_idx, const float *mask_in, float *mask_out,
@@ -170,12 +195,15 @@ int g2s_render_depth_bwd(const g2s_camera *cam, const float *vertices3d, int n_v
 /* Backward of g2s_render_rgb_fwd with respect to the per-vertex colours `im`: neural_renderer's backward_textures chained
  * through get_textures_from_im (utils.py:98-109), the fill_back texture permutation, the 2x2 mean and clamp(-1,1).
  * face_idx [n_views,2S,2S] as written by the forward; grad_rgb [n_views,C,S,S]; grad_im is ACCUMULATED (caller zero-fills)
- * with grad_im_view_stride floats between views (0 = one image shared by all views).  The geometry gradient of an rgb
- * render (nr backward_pixel_map, an approximate edge gradient) is not provided: the reference never differentiates
- * render_rgb (SURVEY.md 8a'). */
+ * with grad_im_view_stride floats between views (0 = one image shared by all views); NULL to skip.
+ * Geometry gradient (NULL grad_vertices to skip): neural_renderer's backward_pixel_map -- the approximate silhouette / colour
+ * edge gradient of Kato et al., one thread per face scanning along each edge and each axis -- chained
+ * through vertices_to_faces and the projection: WRITES grad_vertices [n_views,S*S,3].  It needs rgb_ws
+ * (G2S_WS_RGB_MAP) and raster_ws (G2S_WS_RASTER_BWD); C must be 3. */
 int g2s_render_rgb_bwd(const g2s_camera *cam, const float *vertices3d, const float *im, long im_view_stride, int n_views,
                        int C, int tex_cube_size, const float *bg, int clamp, const int32_t *face_idx,
-                       const float *grad_rgb, float *grad_im, long grad_im_view_stride, void *stream);
+                       const float *grad_rgb, float *grad_im, long grad_im_view_stride, float *rgb_ws, float *raster_ws,
+                       float *grad_vertices, void *stream);
 
 /* ---- set_transform_matrices: utils.py:33-73 (view [B, 3|5|6] -> R = Rz Ry Rx [B,3,3], t [B,3]; other widths return
  * G2S_ERR_UNSUPPORTED as utils.py:70-71 raises) and get_lighting_directions: model.py:347-353 (raw light [B,4] ->
@@ -194,6 +222,17 @@ int g2s_light_bwd(const float *light, int B, const float *grad_light5, float *gr
 int g2s_grid3d_fwd(const g2s_camera *cam, const float *depth, long depth_view_stride, int B, int H, int W,
                    const int *crop, const float *R0, const float *t0, const float *R1, const float *R2,
                    const float *t2, float *out, void *stream);
+/* Backward of the three public forms of the above (no crop): depth_to_3d_grid (mode 0, renderer.py:74-80),
+ * get_warped_3d_grid (mode 1: R, t of the forward warp, renderer.py:90-95) and get_inv_warped_3d_grid (mode 2,
+ * renderer.py:97-102).  grad_out [B,H*W,3]; grad_depth [B,H,W] WRITTEN; grad_R / grad_t ACCUMULATED (NULL to skip both). */
+int g2s_grid3d_bwd(const g2s_camera *cam, const float *depth, long depth_view_stride, int B, int H, int W, int mode,
+                   const float *R, const float *t, const float *grad_out, float *grad_depth, float *grad_R, float *grad_t,
+                   void *stream);
+/* grid_3d_to_2d: renderer.py:82-88.  grid3d [B,H*W,3] -> grid [B,H,W,2] in [-1,1] (with cam->K_grid); backward WRITES
+ * grad_grid3d [B,H*W,3]. */
+int g2s_grid_3d_to_2d_fwd(const g2s_camera *cam, const float *grid3d, int B, int H, int W, float *grid, void *stream);
+int g2s_grid_3d_to_2d_bwd(const g2s_camera *cam, const float *grid3d, int B, int H, int W, const float *grad_grid,
+                          float *grad_grid3d, void *stream);
 
 /* ---- callers either side of the path -------------------------------------------
  * Every reduction below is deterministic: per-block partial sums go to the caller-owned `reduce_ws`

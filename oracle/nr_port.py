@@ -49,6 +49,8 @@ def lib():
         L.nr_forward_texture_sampling.restype = None
         L.nr_backward_textures.argtypes = [i32p, f32p, i32p, f32p, f32p, ci, ci, ci, ci]
         L.nr_backward_textures.restype = None
+        L.nr_backward_pixel_map.argtypes = [f32p, i32p, f32p, f32p, f32p, f32p, f32p, ci, ci, ci, cf, ci, ci]
+        L.nr_backward_pixel_map.restype = None
         cl = ctypes.c_long
         L.fma_mm3_nt.argtypes = [f32p, f32p, f32p, cl, cl, ci]
         L.fma_mm3_nt.restype = None
@@ -165,9 +167,8 @@ def forward_face_index_map(faces, image_size, near, far, mode=None, want_stats=F
 class Rasterize(torch.autograd.Function):
     """[nr] rasterize.RasterizeFunction (forward maps, approximate-gradient backward).
 
-    backward_pixel_map (the silhouette/colour edge gradient) is NOT restated: it only runs when rgb or
-    alpha is requested, and the reference never differentiates render_rgb (SURVEY.md 8a').  Gradients
-    with respect to the vertices of an rgb render are therefore reported as unavailable (error)."""
+    backward_pixel_map (the silhouette / colour edge gradient, only run when rgb or alpha is requested) is restated in
+    oracle/nr_raster.c nr_backward_pixel_map; the reference itself never differentiates render_rgb (SURVEY.md 8a')."""
 
     @staticmethod
     def forward(ctx, faces, textures, image_size, near, far, eps, background_color, return_rgb,
@@ -177,6 +178,7 @@ class Rasterize(torch.autograd.Function):
         maps = forward_face_index_map(faces, s, near, far)
         ctx.maps = maps
         ctx.dims = (B, NF, s)
+        ctx.eps = eps
         ctx.flags = (return_rgb, return_alpha, return_depth)
         ctx.has_tex = textures is not None
         facesc = faces.detach().contiguous().float()
@@ -192,6 +194,7 @@ class Rasterize(torch.autograd.Function):
                                               _fp(maps["weight_map"]), _fp(maps["depth_map"]), _fp(rgb),
                                               _ip(sidx), _fp(swt), _fp(alpha), _fp(bg), B, NF, s, ts, eps)
             ctx.sampling = (sidx, swt, ts)
+            ctx.rgb_map = rgb.clone()
         elif return_alpha:
             alpha = (maps["face_index_map"] >= 0).float()
         ctx.save_for_backward(facesc)
@@ -208,8 +211,13 @@ class Rasterize(torch.autograd.Function):
         maps = ctx.maps
         grad_faces = torch.zeros(B, NF, 3, 3)
         grad_textures = None
-        if return_rgb and ctx.needs_input_grad[0]:
-            raise NotImplementedError("oracle: [nr] backward_pixel_map is not restated (never used by the reference)")
+        if (return_rgb or return_alpha) and ctx.needs_input_grad[0]:
+            g_rgb = grad_rgb.contiguous().float() if (return_rgb and grad_rgb is not None) else torch.zeros(B, s, s, 3)
+            g_alpha = grad_alpha.contiguous().float() if (return_alpha and grad_alpha is not None) else torch.zeros(B, s, s)
+            rgb_map = ctx.rgb_map if return_rgb else torch.zeros(B, s, s, 3)
+            alpha_map = (maps["face_index_map"] >= 0).float()
+            lib().nr_backward_pixel_map(_fp(faces), _ip(maps["face_index_map"]), _fp(rgb_map), _fp(alpha_map), _fp(g_rgb),
+                                        _fp(g_alpha), _fp(grad_faces), B, NF, s, ctx.eps, int(return_rgb), int(return_alpha))
         if return_rgb and ctx.has_tex and ctx.needs_input_grad[1]:
             sidx, swt, ts = ctx.sampling
             grad_textures = torch.zeros(B, NF, ts, ts, ts, 3)

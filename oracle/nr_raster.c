@@ -12,7 +12,9 @@
  * PARITY UNPINNED at this boundary: the reference holds no test, golden image or known-answer vector
  * for the rasteriser.  What pins this file instead: the analytic known-answer tests
  * in tests/test_oracle_known_answers.py (identity view + flat depth, closed-form face-index map,
- * tie rule) and finite-difference checks of d(zp)/d(z).
+ * tie rule), finite-difference checks of d(zp)/d(z), and tests/test_raycast_known_answers.py: an independent
+ * float64 3-D ray caster (tilted planes, occlusion, fill_back, near / far, rgb blend) and the backward_depth_map
+ * formula evaluated in float64.
  *
  * Arithmetic contract: the C expressions below keep the source's literal types (`0.5`, `2.`, `1.`,
  * `0.` are double literals in the CUDA source, everything else is float), source evaluation order, and
@@ -387,6 +389,179 @@ EXPORT void nr_backward_textures(const int32_t *face_index_map, const float *sam
                 }
             }
         }
+    }
+}
+
+
+/*
+ * [nr] backward_pixel_map_cuda_kernel: the approximate silhouette / colour gradient of Kato et al. with respect to the x, y
+ * of the projected vertices.  One "thread" per face: for each edge, for each axis, walk the integer
+ * positions d0 between the edge's end points, find the crossing d1_cross and the pixel just inside / outside; the "out" pass
+ * (only when the inside pixel belongs to this face) walks from the outside pixel to the image border, the "in" pass walks
+ * from the inside pixel to the opposite edge over the pixels that belong to this face; a visited pixel whose colour
+ * difference to the pixel across the edge correlates positively with the incoming gradient pulls the edge's two vertices
+ * by diff_grad / dist.  grad_faces [B,nf,9] is WRITTEN for front faces (x, y components; z stays 0), as the original does.
+ * Maps in nr's native orientation (row yi counts upwards).  Restated from knowledge of the public source: PARITY UNPINNED
+ * (the reference never differentiates render_rgb: SURVEY.md 8a').
+ */
+EXPORT void nr_backward_pixel_map(const float *faces, const int32_t *face_index_map, const float *rgb_map,
+                                  const float *alpha_map, const float *grad_rgb_map, const float *grad_alpha_map,
+                                  float *grad_faces, int batch_size, int num_faces, int image_size, float eps,
+                                  int return_rgb, int return_alpha)
+{
+    const int is = image_size;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)batch_size * num_faces; i++) {
+        const int bn = i / num_faces;
+        const int fn = i % num_faces;
+        const float *face = &faces[i * 9];
+        float grad_face[9] = {0};
+
+        /* check backside */
+        if ((face[7] - face[1]) * (face[3] - face[0]) < (face[4] - face[1]) * (face[6] - face[0]))
+            continue;
+
+        /* for each edge */
+        for (int edge_num = 0; edge_num < 3; edge_num++) {
+            int pi[3];
+            float pp[3][2];
+            for (int num = 0; num < 3; num++)
+                pi[num] = (edge_num + num) % 3;
+            for (int num = 0; num < 3; num++)
+                for (int dim = 0; dim < 2; dim++)
+                    pp[num][dim] = 0.5 * (face[3 * pi[num] + dim] * is + is - 1);
+
+            /* for dy, dx */
+            for (int axis = 0; axis < 2; axis++) {
+                float p[3][2];
+                for (int num = 0; num < 3; num++)
+                    for (int dim = 0; dim < 2; dim++)
+                        p[num][dim] = pp[num][(dim + axis) % 2];
+
+                /* set direction */
+                int direction;
+                if (axis == 0)
+                    direction = (p[0][0] < p[1][0]) ? -1 : 1;
+                else
+                    direction = (p[0][0] < p[1][0]) ? 1 : -1;
+
+                /* along edge */
+                const int d0_from = (int)fmax(ceilf(fminf(p[0][0], p[1][0])), 0.);
+                const int d0_to = (int)fmin(fmaxf(p[0][0], p[1][0]), is - 1.);
+                for (int d0 = d0_from; d0 <= d0_to; d0++) {
+                    /* get cross point */
+                    int d1_in, d1_out;
+                    const float d1_cross = (p[1][1] - p[0][1]) / (p[1][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
+                    if (0 < direction)
+                        d1_in = (int)floorf(d1_cross);
+                    else
+                        d1_in = (int)ceilf(d1_cross);
+                    d1_out = d1_in + direction;
+
+                    /* continue if cross point is not shown */
+                    if (d1_in < 0 || is <= d1_in)
+                        continue;
+                    if (d1_out < 0 || is <= d1_out)
+                        continue;
+
+                    /* get color of in-pixel and out-pixel */
+                    float alpha_in = 0, alpha_out = 0;
+                    const float *rgb_in = NULL, *rgb_out = NULL;
+                    long map_index_in, map_index_out;
+                    if (axis == 0) {
+                        map_index_in = (long)bn * is * is + (long)d1_in * is + d0;
+                        map_index_out = (long)bn * is * is + (long)d1_out * is + d0;
+                    } else {
+                        map_index_in = (long)bn * is * is + (long)d0 * is + d1_in;
+                        map_index_out = (long)bn * is * is + (long)d0 * is + d1_out;
+                    }
+                    if (return_alpha) {
+                        alpha_in = alpha_map[map_index_in];
+                        alpha_out = alpha_map[map_index_out];
+                    }
+                    if (return_rgb) {
+                        rgb_in = &rgb_map[map_index_in * 3];
+                        rgb_out = &rgb_map[map_index_out * 3];
+                    }
+
+                    /* out */
+                    const int is_in_fn = (face_index_map[map_index_in] == fn);
+                    if (is_in_fn) {
+                        const int d1_limit = (0 < direction) ? is - 1 : 0;
+                        const int d1_from = d1_out < d1_limit ? (d1_out > 0 ? d1_out : 0) : (d1_limit > 0 ? d1_limit : 0);
+                        const int d1_to_ = d1_out > d1_limit ? d1_out : d1_limit;
+                        const int d1_to = d1_to_ < is - 1 ? d1_to_ : is - 1;
+                        const long map_offset = (axis == 0) ? is : 1;
+                        long idx = (axis == 0) ? (long)bn * is * is + (long)d1_from * is + d0
+                                               : (long)bn * is * is + (long)d0 * is + d1_from;
+                        for (int d1 = d1_from; d1 <= d1_to; d1++, idx += map_offset) {
+                            float diff_grad = 0;
+                            if (return_alpha)
+                                diff_grad += (alpha_map[idx] - alpha_in) * grad_alpha_map[idx];
+                            if (return_rgb)
+                                for (int k = 0; k < 3; k++)
+                                    diff_grad += (rgb_map[idx * 3 + k] - rgb_in[k]) * grad_rgb_map[idx * 3 + k];
+                            if (diff_grad <= 0)
+                                continue;
+                            if (p[1][0] != d0) {
+                                float dist = (p[1][0] - p[0][0]) / (p[1][0] - d0) * (d1 - d1_cross) * 2. / is;
+                                dist = (0 < dist) ? dist + eps : dist - eps;
+                                grad_face[pi[0] * 3 + (1 - axis)] -= diff_grad / dist;
+                            }
+                            if (p[0][0] != d0) {
+                                float dist = (p[1][0] - p[0][0]) / (d0 - p[0][0]) * (d1 - d1_cross) * 2. / is;
+                                dist = (0 < dist) ? dist + eps : dist - eps;
+                                grad_face[pi[1] * 3 + (1 - axis)] -= diff_grad / dist;
+                            }
+                        }
+                    }
+
+                    /* in */
+                    {
+                        int d1_limit;
+                        float d0_cross2;
+                        if ((d0 - p[0][0]) * (d0 - p[2][0]) < 0)
+                            d0_cross2 = (p[2][1] - p[0][1]) / (p[2][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
+                        else
+                            d0_cross2 = (p[1][1] - p[2][1]) / (p[1][0] - p[2][0]) * (d0 - p[2][0]) + p[2][1];
+                        if (0 < direction)
+                            d1_limit = (int)ceilf(d0_cross2);
+                        else
+                            d1_limit = (int)floorf(d0_cross2);
+                        const int lo = d1_in < d1_limit ? d1_in : d1_limit, hi = d1_in > d1_limit ? d1_in : d1_limit;
+                        const int d1_from = lo > 0 ? lo : 0;
+                        const int d1_to = hi < is - 1 ? hi : is - 1;
+                        const long map_offset = (axis == 0) ? is : 1;
+                        long idx = (axis == 0) ? (long)bn * is * is + (long)d1_from * is + d0
+                                               : (long)bn * is * is + (long)d0 * is + d1_from;
+                        for (int d1 = d1_from; d1 <= d1_to; d1++, idx += map_offset) {
+                            if (face_index_map[idx] != fn)
+                                continue;
+                            float diff_grad = 0;
+                            if (return_alpha)
+                                diff_grad += (alpha_map[idx] - alpha_out) * grad_alpha_map[idx];
+                            if (return_rgb)
+                                for (int k = 0; k < 3; k++)
+                                    diff_grad += (rgb_map[idx * 3 + k] - rgb_out[k]) * grad_rgb_map[idx * 3 + k];
+                            if (diff_grad <= 0)
+                                continue;
+                            if (p[1][0] != d0) {
+                                float dist = (p[1][0] - p[0][0]) / (p[1][0] - d0) * (d1 - d1_cross) * 2. / is;
+                                dist = (0 < dist) ? dist + eps : dist - eps;
+                                grad_face[pi[0] * 3 + (1 - axis)] -= diff_grad / dist;
+                            }
+                            if (p[0][0] != d0) {
+                                float dist = (p[1][0] - p[0][0]) / (d0 - p[0][0]) * (d1 - d1_cross) * 2. / is;
+                                dist = (0 < dist) ? dist + eps : dist - eps;
+                                grad_face[pi[1] * 3 + (1 - axis)] -= diff_grad / dist;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (int k = 0; k < 9; k++)
+            grad_faces[i * 9 + k] = grad_face[k];
     }
 }
 

@@ -25,6 +25,7 @@ struct EmuCam {
 static Cam to_cam(const EmuCam* e) {
     Cam c;
     memcpy(c.K, e->K, sizeof c.K);
+    memcpy(c.Kg, e->K, sizeof c.Kg);
     memcpy(c.invK, e->invK, sizeof c.invK);
     c.rcd = e->rcd; c.os = (float)e->S; c.half_os = (float)(e->S / 2.0);
     c.near = e->near_z; c.far = e->far_z; c.clamp_lo = e->clamp_lo; c.clamp_hi = e->clamp_hi; c.S = e->S;
