@@ -16,11 +16,16 @@ Keys of the JSON line: see the round prompt; `value` = renders/s with inputs res
 ranks; the loss is SURVEY.md 8d's fixed device-resident cotangent on recon_im, handed straight to the backward; nothing but
 the step is in the stream); `e2e` = the same through hostio.HostRenderStep with pinned HOST inputs copied in and the four
 gradients copied out every step (two slots, three streams: the copies of neighbouring steps overlap the kernels, all
-inside the timed region); `roofline` = a second pass with a CUDA-event pair around every kernel (g2s_profile_*; single
-forward lane so that kernels do not overlap), algorithmic bytes from SURVEY.md 8(d); `cpu_baseline` = the oracle (reference
-renderer.py on torch-CPU + the C restatement of the external rasteriser's brute-force loop) on a bounded sample;
-`single_image` = the literal configs[1] shape (1 image x 16 views) eager and as a CUDA graph; `other_configs` = the car
-(64-yaw render_yaw sweep) and face (256^2 x 1024 views) configs of BASELINE.json on one GPU.
+inside the timed region); `e2e_full` = the same with recon_im and recon_depth downloaded as well; `roofline` = the WHOLE
+fwd+bwd step against the HBM roofline (renders/s/GPU x (64 S^2 + 48 S^2/P) bytes / measured peak; `kernel` =
+the dominant kernel, `kernels[]` = every kernel's live time, share and own algorithmic bytes from a second pass with a
+CUDA-event pair around every kernel, single forward lane; `traffic` = DRAM bytes per step from the committed warm-cache ncu
+capture of this shape and code, profiles/r02_traffic.json, or null); `cpu_baseline` = the oracle (reference renderer.py on
+torch-CPU + the C restatement of the external rasteriser's brute-force loop) on a bounded sample, with the bounding-box-culled
+variant (bit-identical outputs) beside it as `cpu_baseline.culled`; `single_image` = the literal configs[1] shape (1 image x
+16 views) eager and as a CUDA graph; `other_configs` = the car (64-yaw render_yaw sweep) and face (256^2 x 1024 views)
+configs of BASELINE.json on one GPU; under --gpus N > 1 `face_sharded` = the face config with its 1024 views split over the
+ranks (strong scaling, the per-image gradients all-reduced over NCCL inside the timed region).
 """
 import argparse
 import ctypes
@@ -92,7 +97,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(S, views, steps, warmup, threads):
+def cpu_reference_run(S, views, steps, warmup, threads, mode="brute"):
     """The reference's CPU implementation of the path = the oracle: reference renderer.py arithmetic on torch-CPU plus
     the faithful O((2S)^2 * 4(S-1)^2) rasteriser loop (oracle/nr_raster.c, OpenMP).  Returns renders/s over `steps`
     steps of `views` views of one image (fwd+bwd)."""
@@ -103,7 +108,7 @@ def cpu_reference_run(S, views, steps, warmup, threads):
     from oracle import nr_port, renderer_oracle as ro
     torch.set_num_threads(threads)
     nr_port.lib().nr_set_threads(threads)      # torchrun exports OMP_NUM_THREADS=1: pin the OpenMP team explicitly
-    nr_port.MODE["raster"] = "brute"
+    nr_port.MODE["raster"] = mode          # "brute": the reference's face loop; "culled": bounding-box culled, same outputs
     case = synthetic.make_case(S, views, seed=1234)
     orc = ro.OracleRenderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH)
 
@@ -206,6 +211,7 @@ def run_ours(args):
     # neighbouring steps overlap the kernels on separate streams, all inside the timed region.
     from g2s_b200 import hostio
     hstep = hostio.HostRenderStep(ren, N, P, cot)
+    hfull = hostio.HostRenderStep(ren, N, P, cot, outputs=("recon_im", "recon_depth"))
 
     def step_e2e():
         hstep.submit(host)
@@ -253,24 +259,55 @@ def run_ours(args):
     kernels = [{"name": names[i].decode(), "launches": int(cnt[i]), "ms_per_launch": tot[i] / cnt[i],
                 "ms_per_step": tot[i] / args.steps} for i in range(nk)]
 
-    def e2e_join():
-        hstep.drain()                      # host waits for the last downloads ...
-        cur = torch.cuda.current_stream()
-        for st_ in (hstep.h2d, hstep.comp, hstep.d2h):
-            cur.wait_stream(st_)           # ... and the timing stream is ordered after all three pipelines
+    def e2e_time(hs):
+        def join():
+            hs.drain()                         # host waits for the last downloads ...
+            cur = torch.cuda.current_stream()
+            for st_ in (hs.h2d, hs.comp, hs.d2h):
+                cur.wait_stream(st_)           # ... and the timing stream is ordered after all three pipelines
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        step_e2e()
-    e2e_join()
+        for _ in range(max(1, min(args.warmup, 3))):
+            hs.submit(host)
+        join()
 
-    def e2e_run():
-        for st_ in (hstep.h2d, hstep.comp, hstep.d2h):
-            st_.wait_stream(torch.cuda.current_stream())    # nothing starts before the opening event
-        for _ in range(args.steps):
-            step_e2e()
-        e2e_join()
+        def run():
+            for st_ in (hs.h2d, hs.comp, hs.d2h):
+                st_.wait_stream(torch.cuda.current_stream())    # nothing starts before the opening event
+            for _ in range(args.steps):
+                hs.submit(host)
+            join()
 
-    ms_e2e = timed(e2e_run, 1)
+        return timed(run, 1)
+
+    ms_e2e = e2e_time(hstep)
+    ms_e2e_full = e2e_time(hfull)      # + recon_im and recon_depth downloaded every step
+    d2h_full = hfull.d2h_bytes
+    del hfull
+
+    # BASELINE.json configs[3] under N > 1 ranks: ONE 256^2 image x 1024 views, the views split over the ranks (strong
+    # scaling); every step ends in the NCCL all_reduce of grad_depth + grad_albedo, inside the timed region
+    face_sharded = None
+    if world > 1 and not args.no_single_image:
+        from g2s_b200.sharding import render_chain_sharded
+        FS, FP = 256, 1024
+        fcase = {k: v.to(dev) for k, v in synthetic.make_case(FS, FP, seed=11, n_images=1).items()}
+        fren = g2s_b200.Renderer(dict(CFGS), FS, MIN_DEPTH, MAX_DEPTH, device=dev)
+
+        def ffn(d, a, v, l, vpi):
+            return fren.render_chain(d, a, v, l, views_per_image=vpi)
+
+        def fstep():
+            render_chain_sharded(ffn, fcase["depth"], fcase["albedo"], fcase["view"], fcase["light"], fcase["cotangent"], FP,
+                                 rank, world, want_loss=False)
+
+        for _ in range(3):
+            fstep()
+        ms_f = timed(fstep, 10) / 10
+        face_sharded = {"workload": "face config: one 256x256 image x 1024 views split over %d ranks, fwd+bwd, gradients "
+                                    "all-reduced (NCCL) every step" % world, "scaling": "strong", "ms_per_step": ms_f,
+                        "value": FP / (ms_f * 1e-3), "unit": UNIT, "views_per_rank": FP // world,
+                        "all_reduce_bytes_per_step": 16 * FS * FS}
+        del fcase, fren
 
     if rank != 0:
         if world > 1:
@@ -287,7 +324,7 @@ def run_ours(args):
     # share of SURVEY.md 8(d)'s per-render budget; per launch = per step / launches per step (chunked launches)
     S2 = float(S * S)
     kb = {"k_normal_fwd": N * 4 * S2,                              # reads depth; the normal map is L2-resident scratch
-          "k_splat": N * 4 * S2,                                   # reads the depth maps; the z-buffer is L2 scratch
+          "k_splat_tile": N * 4 * S2,                              # reads the depth maps; the z-buffer is L2 scratch
           "k_resolve_fused": B * 32 * S2 + N * 12 * S2,            # writes recon_depth+recon_im+face_idx; reads albedo
           "k_render_bwd_pixel": B * (12 + 4) * S2 + N * 12 * S2,   # reads grad_recon_im, recon_depth, albedo
           "k_render_bwd_tex": N * 12 * S2,                         # writes grad_albedo
@@ -303,29 +340,33 @@ def run_ours(args):
             k["frac"] = k["achieved_gbs"] / peak
     kernels.sort(key=lambda k: -k["ms_per_step"])
     dom = kernels[0] if kernels else None
+    # DRAM bytes the whole step actually moves, per step of this run: from the committed warm-cache ncu capture of the SAME
+    # shape (side, views per image, views per launch) and the same kernels -- profiles/r02_traffic.json, written by
+    # profiles/tools/traffic_from_ncu.py -- or null when the shape differs
     traffic, ncu_ctx = None, None
-    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same launch shape only)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)["kernels"].get(dom["name"])
-        if tj and S == 128 and dom["launches"]:
-            # per launch like `achieved`: the capture's bytes per launch scaled to this run's views per launch
-            traffic = tj["dram_bytes_per_launch"] * (B * args.steps / dom["launches"]) / tj["views_per_launch"]
-            ncu_ctx = {k: tj[k] for k in ("sm_throughput_pct", "issue_active_pct", "occupancy_pct",
-                                         "dram_throughput_pct", "registers", "dram_bytes_per_launch_warm_l2") if k in tj}
-            ncu_ctx["source"] = ("profiles/r01_ncu_full.md (committed ncu --set full capture at %d views per launch, cold "
-                                 "cache; not measured by this run)" % tj["views_per_launch"])
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tj = json.load(f)
+        if tj["image_size"] == S and tj["views_per_image"] == P:
+            traffic = tj["dram_bytes_per_render"] * B
+            ncu_ctx = {"source": tj["source"], "dram_bytes_per_render": tj["dram_bytes_per_render"],
+                       "alg_bytes_per_render": per_render, "ratio_to_algorithmic": tj["dram_bytes_per_render"] / per_render,
+                       "per_kernel_dram_bytes_per_render": tj.get("kernels")}
     except Exception:
         traffic = None
     step_achieved = value / world * per_render / 1e9
     roofline = {"bound": "hbm", "kernel": dom["name"] if dom else None,
-                "achieved": dom.get("achieved_gbs") if dom else None, "peak": peak, "unit": "GB/s",
-                "frac": dom.get("frac") if dom else None, "traffic": traffic, "peak_source": peak_src,
-                "kernel_share_of_step": dom["share_of_step"] if dom else None, "ncu": ncu_ctx,
-                "note": "the dominant kernel is the rasteriser: instruction-issue / latency bound by construction (bit-exact "
-                        "reproduction of the reference's un-fused fp32 arithmetic; its z-buffer lives in L2), so its HBM "
-                        "fraction is tiny; the HBM-bound pixel kernels and the whole-step figure are under kernels[] / step",
-                "step": {"alg_bytes_per_render": per_render, "achieved": step_achieved, "frac": step_achieved / peak,
-                         "note": "whole fwd+bwd step, SURVEY.md 8(d): renders/s/GPU x (64 S^2 + 48 S^2/P) bytes"},
+                "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_render": per_render, "alg_bytes_per_step": per_render * B,
+                "kernel_share_of_step": dom["share_of_step"] if dom else None,
+                "kernel_achieved": dom.get("achieved_gbs") if dom else None, "kernel_frac": dom.get("frac") if dom else None,
+                "ncu": ncu_ctx,
+                "note": "achieved / frac: the WHOLE fwd+bwd step, SURVEY.md 8(d): renders/s/GPU x (64 S^2 + 48 S^2/P) bytes over the "
+                        "measured HBM peak.  `kernel` = the kernel with the largest share of the step (per-kernel live times, "
+                        "shares and own algorithmic bytes under kernels[]).  The rasteriser kernels are instruction-issue bound "
+                        "by construction (bit-exact reproduction of the reference's un-fused fp32 arithmetic; z-buffer and "
+                        "scratch live in L2): the step sits far below the HBM roofline, see DESIGN.md section 7",
                 "kernels": kernels}
 
     # the literal BASELINE.json configs[1] shape, one image x P views per step: launch-bound, so also as a CUDA graph
@@ -395,17 +436,25 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         views = 8 if S <= 128 else 1
         v, dt = cpu_reference_run(S, views, 2, 0, threads)
+        cviews = 64 if S <= 128 else 16
+        vc, dtc = cpu_reference_run(S, cviews, 3, 1, threads, mode="culled")
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "2 steps x %d view(s) of one %dx%d image, fwd+bwd, oracle with the reference's "
-                                  "brute-force face loop (%.1f s)" % (views, S, S, dt)}
+                                  "brute-force face loop (%.1f s)" % (views, S, S, dt),
+                        "culled": {"value": vc, "unit": UNIT, "cores": threads,
+                                   "sample": "3 steps x %d views, the same oracle with the bounding-box-culled face loop "
+                                             "(bit-identical outputs; NOT the reference's algorithm) (%.1f s)" % (cviews, dtc)}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "ms_per_step_with_kernel_events": ms_profiled / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, N), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "returns": "the four gradients"},
+            "e2e_full": {"value": renders / (ms_e2e_full / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                         "d2h_bytes_per_step": d2h_full * world, "ms_per_step": ms_e2e_full / args.steps,
+                         "returns": "the four gradients + recon_im + recon_depth"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "single_image": single, "other_configs": other}
+            "single_image": single, "other_configs": other, "face_sharded": face_sharded}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

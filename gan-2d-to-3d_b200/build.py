@@ -17,7 +17,7 @@ DEPS = SOURCES + [os.path.join(CSRC, "g2s_math.cuh"), os.path.join(CSRC, "g2s_ra
 LIB = os.path.join(CSRC, "libg2s_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-         "-Xcompiler", "-fPIC", "-cudart", "static"]
+         "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
 
 def needs_build():

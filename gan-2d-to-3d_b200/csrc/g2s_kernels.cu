@@ -1730,7 +1730,7 @@ size_t g2s_workspace_bytes(int kind, int n, int image_size) {
     }
 }
 
-int g2s_version(void) { return 100; }
+int g2s_version(void) { return 200; }
 
 const char* g2s_error_string(int code) {
     switch (code) {
@@ -1918,9 +1918,12 @@ int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* d
             cudaStreamWaitEvent(lanes[k], ctx->ev_fork, 0);
         }
     }
+    // equal launches: 128 views in chunks of 12 would end in a launch of 8 (the tail of the face config on 8 GPUs)
+    const long nch = (n_views + chunk - 1) / chunk;
+    const int bal = (int)((n_views + nch - 1) / nch);
     int lane = 0, rc_lane = 0;
-    for (long v0 = 0; v0 < n_views; v0 += chunk, lane = (lane + 1) % nl) {
-        const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
+    for (long v0 = 0; v0 < n_views; v0 += bal, lane = (lane + 1) % nl) {
+        const int nv = (int)(n_views - v0 < bal ? n_views - v0 : bal);
         cudaStream_t ls = lanes[lane];
         unsigned long long* zb = (unsigned long long*)zbuf + (size_t)lane * ws_words(chunk, S);   // this lane's part
         if (int rc = launch_splat<false>(c, depth, (long)S * S, views_per_image, R, t, nullptr, zb, chunk, nv, (int)v0, ls)) {

@@ -37,16 +37,40 @@ def shard_views(n_images, views_per_image, rank, world_size):
     return dict(view_start=v0, view_stop=v1, image_start=i0, image_stop=i1, split_images=split)
 
 
-def reduce_image_grads(grads, n_images, group=None):
-    """Sum per-image gradients over the ranks that share images.  `grads`: list of tensors whose dim 0 is the FULL image
-    axis [n_images, ...] (zero rows for the images a rank did not touch).  One all_reduce per tensor (<= 1 MB per
-    image at 256^2: negligible on NVLink).  No-op when not initialised / single rank."""
+def any_rank_splits(n_images, views_per_image, world_size):
+    """Does ANY rank share an image with another rank?  Every rank can answer this locally from the partition (no
+    collective, no host sync): whole images are kept together whenever there are at least as many images as ranks."""
+    if n_images >= world_size:
+        return False
+    return any(shard_views(n_images, views_per_image, r, world_size)["split_images"] for r in range(world_size))
+
+
+def reduce_image_grads(grads, n_images, group=None, extra=None, async_op=False):
+    """Sum per-image gradients over the ranks that share images: ONE all_reduce of one flat buffer (the tensors of `grads`,
+    whose dim 0 is the FULL image axis [n_images, ...] with zero rows for the images a rank did not touch, plus the optional
+    scalar tensors in `extra`) -- 16 S^2 bytes per image, <= 1 MB at 256^2: launch latency, not bandwidth, is what it costs,
+    so one call instead of one per tensor.  Returns a `finish()` callable that waits for the collective (when async_op) and
+    copies the sums back into the tensors; no-op when not initialised / single rank."""
+    extra = list(extra or [])
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return grads
+        return lambda: grads
     for g in grads:
         assert g.shape[0] == n_images
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-    return grads
+    parts = list(grads) + extra
+    flat = torch.cat([p.reshape(-1).float() for p in parts])
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    def finish():
+        if async_op and work is not None:
+            work.wait()
+        off = 0
+        for p in parts:
+            n = p.numel()
+            p.copy_(flat[off:off + n].reshape(p.shape))
+            off += n
+        return grads
+
+    return finish
 
 
 def render_chain_sharded(render_fn, depth, albedo, view, light, cotangent, views_per_image, rank, world_size,
@@ -89,11 +113,11 @@ def render_chain_sharded(render_fn, depth, albedo, view, light, cotangent, views
             loss = (recon_im.detach() * cot).sum().float()
         out.update(recon_im=recon_im.detach(), recon_depth=recon_depth.detach(), grad_view=vw.grad, grad_light=lt.grad)
     if world_size > 1 and dist.is_initialized():
-        any_split = torch.tensor([1.0 if sh["split_images"] else 0.0], device=depth.device)
-        dist.all_reduce(any_split, op=dist.ReduceOp.MAX, group=group)
-        if float(any_split.item()) > 0:
-            reduce_image_grads([g_depth, g_albedo], n_images, group)
-        if want_loss:
+        # decided locally (round 1 all-reduced a flag and read it back on the host every step); the gradients and the loss
+        # travel in ONE all_reduce
+        if any_rank_splits(n_images, views_per_image, world_size):
+            reduce_image_grads([g_depth, g_albedo], n_images, group, extra=[loss] if want_loss else None)()
+        elif want_loss:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     out.update(grad_depth=g_depth, grad_albedo=g_albedo, loss=loss)
     return out
