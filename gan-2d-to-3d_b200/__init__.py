@@ -12,9 +12,9 @@ from .utils import (get_grid, get_rotation_matrix, get_transform_matrices, get_f
                     get_textures_from_im, vcolor_to_texture_cube, mm_normalize, rand_range, rand_posneg_range)
 from .callers import get_shading, get_clamped_depth, recon_im_mask, PhotometricLoss, SmoothLoss
 from .renderer import Renderer, EPS
-from . import functional, callers, graphs, hostio, nr_compat, synthetic, sharding, build as _build  # noqa: F401
+from . import functional, callers, graphs, hostio, mesh_export, nr_compat, synthetic, sharding, build as _build  # noqa: F401
 
 __all__ = ["Renderer", "get_grid", "get_rotation_matrix", "get_transform_matrices", "get_face_idx",
            "get_lighting_directions", "get_shading", "get_textures_from_im", "vcolor_to_texture_cube", "mm_normalize",
            "rand_range", "rand_posneg_range", "get_clamped_depth", "recon_im_mask", "PhotometricLoss", "SmoothLoss",
-           "callers", "hostio", "nr_compat", "functional", "graphs", "sharding", "synthetic", "EPS"]
+           "callers", "hostio", "mesh_export", "nr_compat", "functional", "graphs", "sharding", "synthetic", "EPS"]

@@ -3,7 +3,7 @@
 // Stage 1 (g2s_tile.cuh) rasterises every quad whose two triangles fit an 8 x 8 sub-pixel box and appends the rest -- the
 // 1-px depth-step walls of GAN2Shape/model.py:341-344 stretch to >100 sub-pixels under yaw; degenerate triangles whose two
 // windings both pass the back-face test; quads with a non-finite vertex -- to a global work list of FACES.  This kernel is
-// persistent: CTAs pull batches of 256 faces from the list until it is empty, so the long faces are balanced over the whole
+// persistent: CTAs pull batches of up to 256 faces from the list until it is empty, so the long faces are balanced over the whole
 // GPU instead of sitting in the border tiles' CTAs (round 1: border tiles took 3.8 of k_splat's 10 ms and scaled worse than
 // 4x from 128^2 to 256^2).  Per batch:
 //   1. one thread per face: re-project its three vertices (the same exact arithmetic as stage 1), sub-pixel box, 3x3 inverse
@@ -19,9 +19,15 @@
 
 namespace g2s {
 
-constexpr int BIG_THREADS = 256;
+#ifndef G2S_BIG_THREADS
+#define G2S_BIG_THREADS 256                // measured (128^2 / 256^2, ms per 4096 / 1024 views): 256 x 2 CTAs per SM 2.14 / 2.78,
+#endif                                     // 128 x 4: 2.92 / 4.06, 64 x 8: 4.67 / 10.7 -- the per-batch phases amortise over large batches
+#ifndef G2S_BIG_CTAS
+#define G2S_BIG_CTAS 2                     // resident CTAs per SM the kernel is sized for (registers, shared memory, grid)
+#endif
+constexpr int BIG_THREADS = G2S_BIG_THREADS;
 constexpr int BIG_HQ = 16 * BIG_THREADS;   // hit-queue entries per drain
-constexpr int BIG_TQ = 8192;               // row tasks per batch; overflow falls to an inline scan
+constexpr int BIG_TQ = 32 * BIG_THREADS;   // row tasks per batch; overflow falls to an inline scan
 constexpr int BREC = 11;                   // x0,y0,x1,y1,x2,y2 (NDC), box x, box y, + pad to an odd stride
 
 struct BigSmem {

@@ -135,7 +135,7 @@ k_splat_tile(const Cam cam, const float* __restrict__ depth, long dstride, int v
 
 // stage 2 (g2s_bigface.cuh): persistent CTAs pull the faces stage 1 deferred (long walls, degenerate quads) from the work list
 template <bool FROM_VERTS>
-__global__ void __launch_bounds__(BIG_THREADS, 2)
+__global__ void __launch_bounds__(BIG_THREADS, G2S_BIG_CTAS)
 k_splat_big(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
             const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
             const WorkList wl, int view0) {
@@ -675,7 +675,7 @@ __global__ void k_light_bwd(const float* __restrict__ light, int B, const float*
 // projected (u, v, z) of every vertex of the chunk's views: proj [chunk, S*S, 3]
 __global__ void __launch_bounds__(PIX_THREADS)
 k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
-                const float* __restrict__ t, int view0, float* __restrict__ proj) {
+                const float* __restrict__ t, int view0, float* __restrict__ proj, float* __restrict__ vgrad_zero) {
     __shared__ float sRt[12];
     const int S = cam.S, bl = blockIdx.y, b = view0 + bl;
     if (threadIdx.x < 9) sRt[threadIdx.x] = R[b * 9 + threadIdx.x];
@@ -689,11 +689,13 @@ k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, in
     warp_point(cam, sRt, sRt + 9, ray, depth[(long)(b / vpi) * dstride + v], q);
     project_ndc(cam, q, ndc);
     reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
+    // the vertex-gradient scratch of the same vertex starts at zero (a 1 GB cudaMemset per step otherwise)
+    reinterpret_cast<float4*>(vgrad_zero)[(long)bl * S * S + v] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // the same for vertices given as 3-D points (the neural_renderer-level entry g2s_render_depth_*): projection only
 __global__ void __launch_bounds__(PIX_THREADS)
-k_project_points(const Cam cam, const float* __restrict__ verts3d, float* __restrict__ proj) {
+k_project_points(const Cam cam, const float* __restrict__ verts3d, float* __restrict__ proj, float* __restrict__ vgrad_zero) {
     const int S = cam.S, bl = blockIdx.y;
     const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
     if (v >= S * S) return;
@@ -702,6 +704,7 @@ k_project_points(const Cam cam, const float* __restrict__ verts3d, float* __rest
     float ndc[3];
     project_ndc(cam, q, ndc);
     reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
+    reinterpret_cast<float4*>(vgrad_zero)[(long)bl * S * S + v] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // (u,v,z) NDC gradient -> gradient of the 3-D vertex ([nr] projection backward); WRITES grad_verts [chunk,S*S,3]
@@ -921,7 +924,7 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
 // (registers, accumulated with a plain += : one thread owns one (image, pixel)) and grad_light (warp
 // reduction + one atomic per warp and view).  grid = (pixel blocks, images spanned by the chunk).
 __global__ void __launch_bounds__(PIX_THREADS)
-k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict__ grad_tex,
+k_render_bwd_tex(int S, const FusedArgs fa, int nviews, float* __restrict__ grad_tex,
                  float* __restrict__ grad_albedo, float* __restrict__ grad_normal, float* __restrict__ grad_light) {
     const int img = fa.view0 / fa.vpi + blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
     const bool live = pix < S * S;
@@ -944,7 +947,8 @@ k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict_
                     dy = __ldg(&fa.light[b * 5 + 3]), dz = __ldg(&fa.light[b * 5 + 4]);
         float T[3] = {0.f, 0.f, 0.f};
         if (live) {
-            const float4 t4 = __ldcs(reinterpret_cast<const float4*>(grad_tex) + (long)(b - fa.view0) * S * S + p);
+            float4* tp = reinterpret_cast<float4*>(grad_tex) + (long)(b - fa.view0) * S * S + p;
+            const float4 t4 = __ldcs(tp);
             T[0] = t4.x; T[1] = t4.y; T[2] = t4.z;
         }
         const float ndl = n0 * dx + n1 * dy + n2 * dz;
@@ -963,6 +967,13 @@ k_render_bwd_tex(int S, const FusedArgs fa, int nviews, const float* __restrict_
         const int lane = threadIdx.x & 31, li = halving_index<3>(lane);
         const float ls = warp_reduce_halving<3>(lg, lane);
         if ((lane & 3) == 0 && li < 5 && ls != 0.f) atomicAdd(&grad_light[b * 5 + li], ls);
+    }
+    // What was consumed is left at zero for the next chunk's reductions (instead of a 1 GB cudaMemset per step) -- in a loop of
+    // its own, after the sums above have waited for every load: a store to a line that a load is still waiting on holds the
+    // load / store unit until the load returns (inside the loop above it serialised the loads: 0.46 -> 4.8 ms).
+    if (live) {
+        for (int b = b0; b < b1; b++)
+            __stcs(reinterpret_cast<float4*>(grad_tex) + (long)(b - fa.view0) * S * S + p, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     if (live && b1 > b0) {
         float* o = grad_normal + ((long)img * S * S + p) * 3;
@@ -1526,7 +1537,7 @@ inline int launch_splat(const Cam& c, const float* depth, long dstride, int vpi,
       else
           k_splat_tile<FROM_VERTS, false><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, tiles, view0); }
     { Launch l_(K_SPLAT_BIG, st);
-      k_splat_big<FROM_VERTS><<<di->sms * 2, BIG_THREADS, sizeof(BigSmem), st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl,
+      k_splat_big<FROM_VERTS><<<di->sms * G2S_BIG_CTAS, BIG_THREADS, sizeof(BigSmem), st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl,
                                                                                 view0); }
     return G2S_OK;
 }
@@ -1661,10 +1672,9 @@ inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, in
     float* proj = raster_ws;
     float* vgrad = proj + (size_t)nv * 4 * img;
     float* g_sub = raster_ws_gsub(raster_ws, nv, S);
-    cudaMemsetAsync(vgrad, 0, sizeof(float) * nv * 4 * img, st);
-    { Launch l_(K_PROJECT, st);
-      if (verts3d) k_project_points<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj);
-      else k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj); }
+    { Launch l_(K_PROJECT, st);     // also zeroes vgrad
+      if (verts3d) k_project_points<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj, vgrad);
+      else k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj, vgrad); }
     { Launch l_(K_RASTER_BWD, st);
       k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), dim3(RBX, RBY), 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
@@ -1967,9 +1977,10 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
     cudaMemsetAsync(grad_albedo, 0, sizeof(float) * n_images * 3 * img_f, st);
     cudaMemsetAsync(grad_normal_ws, 0, sizeof(float) * n_images * 3 * img_f, st);
     const int chunk = ws_views < 32768 ? ws_views : 32768;
+    // the per-view texture-gradient scratch is zeroed once; k_render_bwd_tex leaves what it consumed at zero
+    cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * (size_t)(n_views < chunk ? n_views : chunk) * 4 * img_f, st);
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
-        cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * nv * 4 * img_f, st);
         FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
         { Launch l_(K_BWD_PIXEL, st);
           k_render_bwd_pixel<<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
@@ -2178,8 +2189,7 @@ int g2s_render_rgb_bwd(const g2s_camera* cam, const float* vertices3d, const flo
         Launch l_(K_RESOLVE_RGB, st);
         k_rgb_map<<<pix_grid((long)is * is, n_views), PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, rgb_map);
         k_rgb_gquarter<<<g, PIX_THREADS, 0, st>>>(S, rgb_map, grad_rgb, clamp, g4);
-        cudaMemsetAsync(vgrad, 0, sizeof(float) * n_views * 4 * img, st);
-        k_project_points<<<g, PIX_THREADS, 0, st>>>(c, vertices3d, proj);
+        k_project_points<<<g, PIX_THREADS, 0, st>>>(c, vertices3d, proj, vgrad);      // also zeroes vgrad
         const int Q4 = 4 * (S - 1) * (S - 1);
         k_backward_pixel_map<<<dim3((Q4 + 127) / 128, n_views), 128, 0, st>>>(c, face_idx, proj, rgb_map, g4, eps, vgrad);
         k_points_bwd<<<g, PIX_THREADS, 0, st>>>(c, vertices3d, vgrad, grad_vertices);

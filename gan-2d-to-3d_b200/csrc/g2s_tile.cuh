@@ -8,10 +8,10 @@
 //      coordinates px, py that both the boxes and the 3x3 face inverses are built from; ONE barrier.  Everything after it is
 //      warp-local (a warp owns two rows of 16 quads): the eight warps of a tile drift apart and overlap their phases.
 //   2. every lane classifies its quad from the UNION box of its two triangles and builds the 3x3 inverses of its front
-//      windings into the warp's face table (12 floats per face, conflict-free 16-byte rows).  Quads whose box exceeds 8 x 8
+//      windings into the warp's face table (12 floats per face, conflict-free 16-byte rows).  Quads whose box exceeds 16 x 16
 //      sub-pixels (the long depth-step walls), degenerate and non-finite quads go to a global WORK LIST of faces that the
 //      second stage (k_splat_big, g2s_bigface.cuh) rasterises, balanced over the whole GPU.
-//   3. the boxes are cut into JOBS of 4 x 4 sub-pixels (one for an interior quad, up to four for a sheared one), listed per
+//   3. the boxes are cut into JOBS of 4 x 4 sub-pixels (one for an interior quad, up to sixteen for a sheared one), listed per
 //      warp and scanned one lane per job with straight-line code: the exact inside test `!((yp-yk)*dx < (xp-xk)*dy)` split
 //      into per-row and per-column terms -- three predicated compares per (triangle, candidate) -- into two 16-bit hit
 //      masks.  No loop bound depends on the largest box of the warp (round 1 / the first form of this file scanned
@@ -29,6 +29,11 @@ namespace g2s {
 #define G2S_PHASE 9     // < 9: experiment builds that stop k_splat_tile after a phase (per-phase timing, profiles/r02_notes.md)
 #endif
 constexpr int K_ROUND = 8;                      // hits a lane contributes to one drain round
+#ifndef G2S_MAX_BOX
+#define G2S_MAX_BOX 16                          // largest quad box (sub-pixels per side) rasterised by stage 1
+#endif
+constexpr int MAX_BOX = G2S_MAX_BOX;
+constexpr int MAX_JOBS = (MAX_BOX / 4) * (MAX_BOX / 4);   // 4 x 4 jobs of one quad
 constexpr int TWARPS = SPLAT_THREADS / 32;
 constexpr int REC_F = 12;                       // face-table entry: fi[9], z[3]
 constexpr int NV_PAD = (TV * TVH + 3) & ~3;
@@ -41,7 +46,7 @@ struct TileSmem2 {
     float ftab[TWARPS][64 * REC_F];             // warp-local face table, entry = lane * 2 + triangle
     uint32_t fword[TWARPS][64];                 // face index | z-range verdict << 31
     uint16_t hq[TWARPS][32 * K_ROUND];          // warp-local hit queue: job lane | bit << 5
-    uint8_t jobs[TWARPS][32 * 4];               // warp-local job list: owner lane | box column << 5 | box row << 6
+    uint16_t jobs[TWARPS][32 * MAX_JOBS];       // warp-local job list: owner lane | box column << 5 | box row << 7
 };
 
 // Work list of the second stage.  Every word of the z-buffer workspace is the EMPTY key at rest (so that any later call may
@@ -170,7 +175,7 @@ __device__ __forceinline__ void quad_geometry(const TileSmem2& sm, int is, int q
     if (g.fronts == 0u) g.cls = QC_NONE;
     else if (!(g.finA && g.finB) || dup) g.cls = QC_DEFER;
     else if (g.uw <= 0 || g.uh <= 0) g.cls = QC_NONE;
-    else if (g.uw > 8 || g.uh > 8) g.cls = QC_DEFER;
+    else if (g.uw > MAX_BOX || g.uh > MAX_BOX) g.cls = QC_DEFER;
     else g.cls = (g.uw <= 4 && g.uh <= 4) ? QC_SMALL : QC_MEDIUM;
 }
 
@@ -254,7 +259,7 @@ __device__ __forceinline__ void build_face_records(TileSmem2& sm, const TileCtx&
 // Rounds: every lane queues at most K_ROUND of the hits of its job (M: bits 0..15 = first triangle, 16..31 = second, bit =
 // row * 4 + column of the job's 4 x 4 box) as 16-bit entries `lane | bit << 5`; the warp drains the queue one lane per hit:
 // hit(valid, job lane, triangle, slot, xi, yi, fi, z, face word), called by ALL lanes.
-// jobword = owner lane | box column << 5 | box row << 6 of this lane's job; origin = x0 | y0 << 12 of this lane's OWN quad box.
+// jobword = owner lane | box column << 5 | box row << 7 of this lane's job; origin = x0 | y0 << 12 of this lane's OWN quad box.
 template <class Hit>
 __device__ __forceinline__ void drain_rounds(TileSmem2& sm, unsigned M, unsigned jobword, uint32_t origin, const Hit& hit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -284,8 +289,8 @@ __device__ __forceinline__ void drain_rounds(TileSmem2& sm, unsigned M, unsigned
             const unsigned owner = jw & 31u;
             const uint32_t ow = __shfl_sync(0xffffffffu, origin, (int)owner);
             const unsigned bit = e >> 5, tri = bit >> 4;
-            const int xi = (int)(ow & 4095u) + (int)(((jw >> 5) & 1u) * 4u + (bit & 3u));
-            const int yi = (int)((ow >> 12) & 4095u) + (int)(((jw >> 6) & 1u) * 4u + ((bit >> 2) & 3u));
+            const int xi = (int)(ow & 4095u) + (int)(((jw >> 5) & 3u) * 4u + (bit & 3u));
+            const int yi = (int)((ow >> 12) & 4095u) + (int)(((jw >> 7) & 3u) * 4u + ((bit >> 2) & 3u));
             const int slot = (int)(owner * 2u + tri);            // invalid lanes read slot 0
             const float4* r4 = reinterpret_cast<const float4*>(&sm.ftab[warp][slot * REC_F]);
             const float4 r0 = r4[0], r1 = r4[1], r2 = r4[2];
@@ -349,8 +354,8 @@ __device__ __forceinline__ unsigned scan_job(const TileSmem2& sm, const PixCente
     return (mA & vm) | ((mB & vm) << 16);
 }
 
-// One warp rasterises its 32 quads (lane `active` <=> its quad g has a box of at most 8 x 8 sub-pixels and is neither
-// degenerate nor non-finite): face records, job list, scan, rounds.  Warp-local: no CTA barrier.
+// One warp rasterises its 32 quads (lane `active` <=> its quad g has a box of at most MAX_BOX x MAX_BOX sub-pixels and is
+// neither degenerate nor non-finite): face records, job list, scan, rounds.  Warp-local: no CTA barrier.
 template <bool POW2>
 __device__ __forceinline__ void raster_warp(TileSmem2& sm, const TileCtx& cx, const PixCenterT<POW2>& pc, const QuadGeom& g,
                                             bool active, int quad) {
@@ -361,10 +366,9 @@ __device__ __forceinline__ void raster_warp(TileSmem2& sm, const TileCtx& cx, co
     const int njx = active ? (g.uw + 3) >> 2 : 0, njy = active ? (g.uh + 3) >> 2 : 0, nj = njx * njy;
     int total;
     const int jbase = warp_excl_scan(nj, &total);
-    uint8_t* jobs = sm.jobs[warp];
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (k < nj) jobs[jbase + k] = (uint8_t)(lane | ((k % njx) << 5) | ((k / njx) << 6));
+    uint16_t* jobs = sm.jobs[warp];
+#pragma unroll 1
+    for (int k = 0; k < nj; k++) jobs[jbase + k] = (uint16_t)(lane | ((k % njx) << 5) | ((k / njx) << 7));
     const uint32_t origin = (uint32_t)g.x0 | ((uint32_t)g.y0 << 12) | (g.fronts << 24);
     const uint32_t extent = (uint32_t)g.uw | ((uint32_t)g.uh << 8);
     __syncwarp();
@@ -375,7 +379,7 @@ __device__ __forceinline__ void raster_warp(TileSmem2& sm, const TileCtx& cx, co
         const int j = j0 + lane;
         const bool valid = j < total;
         const unsigned e = valid ? jobs[j] : 0u;
-        const int owner = (int)(e & 31u), bx = (int)((e >> 5) & 1u), by = (int)(e >> 6);
+        const int owner = (int)(e & 31u), bx = (int)((e >> 5) & 3u), by = (int)(e >> 7);
         const uint32_t ow = __shfl_sync(0xffffffffu, origin, owner);
         const uint32_t ex = __shfl_sync(0xffffffffu, extent, owner);
         unsigned M = scan_job<POW2>(sm, pc, (quad & ~31) + owner, ow >> 24, (int)(ow & 4095u) + 4 * bx,

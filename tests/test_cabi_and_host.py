@@ -95,3 +95,32 @@ def test_renderer_constructs_on_cpu_and_refuses_cpu_compute():
         ren.warp_canon_depth(torch.ones(1, 32, 32))
     with pytest.raises(RuntimeError):
         ren.get_normal_from_depth(torch.ones(1, 32, 32))
+
+
+def test_mesh_export_writers(tmp_path):
+    """mesh_export: the OBJ / PLY writers and the plotly array helpers (host-side; SURVEY.md 8f row 4, plotting.py:58-131)"""
+    import numpy as np
+    import g2s_b200
+    from g2s_b200 import mesh_export as me
+    S = 5
+    faces = g2s_b200.get_face_idx(1, S, S)[0].numpy().astype(np.int32)
+    rng = np.random.default_rng(0)
+    mesh = dict(vertices=rng.standard_normal((S * S, 3)).astype(np.float32), faces=faces,
+                colors=rng.random((S * S, 3)).astype(np.float32))
+    obj, ply = tmp_path / "m.obj", tmp_path / "m.ply"
+    me.write_obj(str(obj), mesh)
+    me.write_ply(str(ply), mesh)
+    lines = obj.read_text().splitlines()
+    vs = [l for l in lines if l.startswith("v ")]
+    fs = [l for l in lines if l.startswith("f ")]
+    assert len(vs) == S * S and len(fs) == 2 * (S - 1) ** 2
+    assert [int(t) for t in fs[0].split()[1:]] == [int(i) + 1 for i in faces[0]]
+    assert np.allclose([float(t) for t in vs[3].split()[1:4]], mesh["vertices"][3], rtol=1e-6)
+    raw = ply.read_bytes()
+    head, body = raw.split(b"end_header\n")
+    assert b"element vertex %d" % (S * S) in head and b"element face %d" % len(faces) in head
+    assert len(body) == S * S * (12 + 3) + len(faces) * (1 + 12)
+    kw = me.mesh3d_arrays(mesh)
+    assert set(kw) == {"x", "y", "z", "i", "j", "k", "vertexcolor"} and len(kw["i"]) == len(faces)
+    z, col = me.surface_arrays(torch.full((1, S, S), 0.9), torch.zeros(1, 3, S, S))
+    assert z.shape == (S, S) and float(z[0, 0]) == -np.float32(0.9) and col.shape == (S, S)

@@ -194,3 +194,21 @@ def test_second_device_if_present():
             rd, f = ren.warp_canon_depth(case["depth"].to(dev).expand(P, S, S), return_face_idx=True)
             outs.append((rd.cpu(), f.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_mesh_export_matches_the_rasterised_mesh():
+    """mesh_export.depth_to_mesh: the vertices are the 3-D grid the rasteriser renders (renderer.py:74-80 / 90-95)"""
+    import numpy as np
+    from g2s_b200 import mesh_export as me, synthetic
+    S = 16
+    case = synthetic.make_case(S, 2, seed=4)
+    orc, ren = oracle_renderer(S), _cuda_renderer(S)
+    meshes = me.depth_to_mesh(ren, case["depth"].cuda().expand(2, S, S), image=case["albedo"].cuda(), view=case["view"].cuda())
+    orc.set_transform_matrices(case["view"])
+    want = orc.get_warped_3d_grid(case["depth"].expand(2, S, S)).reshape(2, -1, 3).numpy()
+    assert len(meshes) == 2
+    for b in range(2):
+        assert np.abs(meshes[b]["vertices"] - want[b]).max() < 1e-6        # R from the CUDA sincos: an ulp off the CPU's
+        assert meshes[b]["faces"].shape == (2 * (S - 1) ** 2, 3) and meshes[b]["colors"].shape == (S * S, 3)
+    plain = me.depth_to_mesh(ren, case["depth"].cuda())
+    assert np.array_equal(plain[0]["vertices"], orc.depth_to_3d_grid(case["depth"]).reshape(-1, 3).numpy())
