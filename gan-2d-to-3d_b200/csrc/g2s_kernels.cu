@@ -1643,12 +1643,12 @@ __global__ void k_selftest_face_vertices(int S, unsigned long long* mismatches) 
 
 inline dim3 pix_grid2(int S, int views, int bx = PBX, int by = PBY) { return dim3((S + bx - 1) / bx, (S + by - 1) / by, views); }
 
-// views per chunk so that the per-chunk scratch (z-buffer 32 S^2 B/view, or the backward's texture-gradient
-// scratch 16 S^2 B/view) stays resident in the 126 MB L2 between the kernel that writes it and the one that reads it
+// Views per forward chunk: 128 MB of z-buffer keys (256 views at 128^2, 64 at 256^2), at least 8.  Round 1 kept a chunk's keys
+// inside the 126 MB L2 (24 MB per chunk) for k_resolve; with the round-2 kernels the sweep says otherwise (profiles/r02_notes.md:
+// 48 -> 256 views per chunk at 128^2: k_splat_tile 5.57 -> 4.64 ms, k_resolve 1.80 -> 1.39, k_splat_big 2.13 -> 0.5 in the
+// per-kernel pass, 14.5 -> 14.1 ms per step): fewer, longer launches win, the keys stream through L2 either way.
 inline int chunk_views_for(int S, int cap) {
-    // 24 MB of z-buffer per chunk: two chunks are in flight in the two-lane forward and both must stay in the 126 MB L2
-    // next to the streaming outputs (swept at 128^2 and 256^2, profiles/r01_notes.md); at least 8 views per launch
-    long v = (24L << 20) / (32L * S * S);
+    long v = (128L << 20) / (32L * S * S);
     if (v < 8) v = 8;
     if (v > cap) v = cap;
     return (int)v;

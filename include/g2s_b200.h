@@ -137,8 +137,8 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  *   grid     = get_inv_warped_2d_grid(recon_depth[b])             (renderer.py:110-114)
  *   recon_im[b] = grid_sample(texture, grid).clamp(-1, 1)         (model.py:270)
  * light [n_views,5] = (ambient a, diffuse b, direction dx,dy,dz) as get_lighting_directions returns.
- * The views are processed in chunks so that the per-chunk scratch stays L2-resident between the kernel that writes it
- * and the kernel that reads it; g2s_chunk_views(S) returns the recommended chunk (24 MB of z-buffer).  `ws_views` = views
+ * The views are processed in chunks that bound the z-buffer workspace; g2s_chunk_views(S) returns the recommended chunk
+ * (128 MB of z-buffer keys: 256 views at 128^2, 64 at 256^2 -- the measured optimum, longer launches win).  `ws_views` = views
  * the z-buffer workspace holds: with room for L >= 2 recommended chunks (and more views than one chunk) the chunks rotate
  * over L lanes (L <= 4; the Python host asks for 2, the measured optimum) -- one part of the workspace and one stream each:
  * `stream` and the non-blocking streams of `ctx` (NULL ctx: one lane), forked from and joined back into `stream` with events
