@@ -67,9 +67,10 @@ SIGNATURES = {
     "g2s_shading_fwd": (_c_int, [_vp, _c_long, _vp, _vp, _c_long, _c_int, _c_int, _vp, _vp, _vp]),
     "g2s_shading_bwd": (_c_int, [_vp, _c_long, _vp, _vp, _c_long, _c_int, _c_int, _vp, _vp, _vp, _c_long, _vp, _vp,
                                  _c_long, _vp]),
-    "g2s_photometric_fwd": (_c_int, [_vp, _vp, _c_long, _vp, _c_float, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
-    "g2s_photometric_bwd": (_c_int, [_vp, _vp, _c_long, _vp, _c_float, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
+    "g2s_photometric_fwd": (_c_int, [_vp, _vp, _c_long, _vp, _c_float, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp,
                                      _vp]),
+    "g2s_photometric_bwd": (_c_int, [_vp, _vp, _c_long, _vp, _c_float, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp,
+                                     _vp, _vp, _vp, _vp]),
     "g2s_smooth_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "g2s_smooth_bwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "g2s_launch_count": (_c_long, []),

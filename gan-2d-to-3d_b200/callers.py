@@ -122,8 +122,8 @@ def get_shading(normal, lighting_a, lighting_b, lighting_d, albedo):
 # ----------------------------------------------------------------------------------------------------------
 class PhotometricFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, im1, im2, recon_depth, depth_thresh, mask):
-        _require_cuda(im1, im2, recon_depth, mask)
+    def forward(ctx, im1, im2, recon_depth, depth_thresh, mask, conf_sigma=None):
+        _require_cuda(im1, im2, recon_depth, mask, conf_sigma)
         lib = _lib.load()
         x = _f32c(im1)
         B, C, H, W = x.shape
@@ -138,33 +138,43 @@ class PhotometricFn(torch.autograd.Function):
             if mask.dim() == 4 and mask.shape[1] != 1:
                 raise RuntimeError("PhotometricLoss: the mask must be [B,1,H,W] (it is expanded over the channels)")
             mk = _f32c(mask.expand(B, 1, H, W).reshape(B, HW))
+        sg, sc = None, 1
+        if conf_sigma is not None:      # losses.py:44-45; [B,1,H,W] (broadcast over the channels) or [B,C,H,W]
+            if conf_sigma.dim() != 4 or conf_sigma.shape[1] not in (1, C):
+                raise RuntimeError("PhotometricLoss: conf_sigma must be [B,1,H,W] or [B,C,H,W]")
+            sc = conf_sigma.shape[1]
+            sg = _f32c(conf_sigma.expand(B, sc, H, W))
         ws = _reduce_ws(x.device)
         out = torch.empty(3, device=x.device, dtype=torch.float32)
-        _lib.check(lib.g2s_photometric_fwd(_p(x), _p(y), ys, _p(rd), depth_thresh, _p(mk), B, C, HW, _p(ws), _p(out),
-                                           _stream()), "g2s_photometric_fwd")
-        ctx.save_for_backward(x, y, rd, mk, out)
-        ctx.meta = (ys, depth_thresh, im2.shape)
+        _lib.check(lib.g2s_photometric_fwd(_p(x), _p(y), ys, _p(rd), depth_thresh, _p(mk), _p(sg), sc, B, C, HW, _p(ws),
+                                           _p(out), _stream()), "g2s_photometric_fwd")
+        ctx.save_for_backward(x, y, rd, mk, out, sg)
+        ctx.meta = (ys, depth_thresh, im2.shape, sc, None if conf_sigma is None else conf_sigma.shape)
         return out[0]
 
     @staticmethod
     def backward(ctx, g_loss):
         lib = _lib.load()
-        x, y, rd, mk, out = ctx.saved_tensors
-        ys, thresh, yshape = ctx.meta
+        x, y, rd, mk, out, sg = ctx.saved_tensors
+        ys, thresh, yshape, sc, sshape = ctx.meta
         B, C, H, W = x.shape
         g = _f32c(g_loss).reshape(1)
         need2 = ctx.needs_input_grad[1]
+        needs = sg is not None and len(ctx.needs_input_grad) > 5 and ctx.needs_input_grad[5]
         if need2 and ys == 0:
             raise RuntimeError("PhotometricLoss: no gradient to a broadcast (batch 1) second image; expand it first")
         g1 = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         g2 = torch.empty_like(x) if need2 else None
-        if g1 is None and g2 is None:
-            return None, None, None, None, None
-        _lib.check(lib.g2s_photometric_bwd(_p(x), _p(y), ys, _p(rd), thresh, _p(mk), B, C, H * W, _p(out), _p(g), _p(g1),
-                                           _p(g2), _stream()), "g2s_photometric_bwd")
+        gs = torch.empty_like(sg) if needs else None
+        if g1 is None and g2 is None and gs is None:
+            return None, None, None, None, None, None
+        _lib.check(lib.g2s_photometric_bwd(_p(x), _p(y), ys, _p(rd), thresh, _p(mk), _p(sg), sc, B, C, H * W, _p(out), _p(g),
+                                           _p(g1), _p(g2), _p(gs), _stream()), "g2s_photometric_bwd")
         if g2 is not None:
             g2 = g2.sum_to_size(yshape)
-        return g1, g2, None, None, None
+        if gs is not None:
+            gs = gs.sum_to_size(sshape)
+        return g1, g2, None, None, None, gs
 
 
 class PhotometricLoss:
@@ -174,13 +184,10 @@ class PhotometricLoss:
     EPS = 1e-7
 
     def __call__(self, image1, image2, mask=None, conf_sigma=None, recon_depth=None, depth_thresh=None):
-        if conf_sigma is not None:
-            raise NotImplementedError("PhotometricLoss(conf_sigma=...) is never used by the reference's callers "
-                                      "(model.py:158,215,274) and is not built")
         if (recon_depth is None) != (depth_thresh is None):
             raise RuntimeError("PhotometricLoss: recon_depth and depth_thresh go together")
         return PhotometricFn.apply(image1, image2, recon_depth, float(depth_thresh) if depth_thresh is not None else 0.0,
-                                   mask)
+                                   mask, conf_sigma)
 
 
 def recon_im_mask(recon_depth, min_depth, max_depth):

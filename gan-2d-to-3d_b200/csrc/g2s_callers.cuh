@@ -178,7 +178,16 @@ struct PhotoArgs {
     long im2_stride;     // floats between batch items of im2 (0 = one target for all views)
     float thresh;
     int B, C, HW;
+    const float* sigma;  // conf_sigma [B, sigma_C, HW] (losses.py:44-45) or NULL; sigma_C = 1 (shared by the channels) or C
+    int sigma_C;
 };
+constexpr float PHOTO_EPS = 1e-7f;      // PhotometricLoss.EPS, losses.py:40
+constexpr float PHOTO_SQRT2 = 1.41421356237309515f;   // float(2 ** 0.5)
+// losses.py:45: |d| * 2**0.5 / (sigma + EPS) + log(sigma + EPS)
+__device__ __forceinline__ float photo_sigma_term(float ad, float sg) {
+    const float se = sg + PHOTO_EPS;
+    return ad * PHOTO_SQRT2 / se + logf(se);
+}
 
 __device__ __forceinline__ float4 photo_mask4(const PhotoArgs& a, int b, int i) {
     float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -226,8 +235,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_photo_fwd(PhotoArgs a, double* 
             const float m = photo_mask1(a, b, i);
             den += (double)m;
             float n1 = 0.f;
-            for (int c = 0; c < a.C; c++)
-                n1 += fabsf(a.im1[((long)b * a.C + c) * a.HW + i] - a.im2[b * a.im2_stride + (long)c * a.HW + i]) * m;
+            for (int c = 0; c < a.C; c++) {
+                float l = fabsf(a.im1[((long)b * a.C + c) * a.HW + i] - a.im2[b * a.im2_stride + (long)c * a.HW + i]);
+                if (a.sigma) l = photo_sigma_term(l, a.sigma[((long)b * a.sigma_C + (a.sigma_C == 1 ? 0 : c)) * a.HW + i]);
+                n1 += l * m;
+            }
             num += (double)n1;
         }
     }
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_photo_finish(const double* __re
 template <bool VEC>
 __global__ void __launch_bounds__(RED_THREADS) k_photo_bwd(PhotoArgs a, const float* __restrict__ sums,
                                                            const float* __restrict__ g_loss, float* __restrict__ g_im1,
-                                                           float* __restrict__ g_im2) {
+                                                           float* __restrict__ g_im2, float* __restrict__ g_sigma) {
     const float s = g_loss[0] / sums[2];
     auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
     if (VEC) {
@@ -277,12 +289,22 @@ __global__ void __launch_bounds__(RED_THREADS) k_photo_bwd(PhotoArgs a, const fl
         for (long q = (long)blockIdx.x * RED_THREADS + threadIdx.x; q < n; q += (long)gridDim.x * RED_THREADS) {
             const int b = (int)(q / a.HW), i = (int)(q % a.HW);
             const float m = photo_mask1(a, b, i);
+            float gs_shared = 0.f;
             for (int c = 0; c < a.C; c++) {
                 const long o1 = ((long)b * a.C + c) * a.HW + i;
-                const float g = sgn(a.im1[o1] - a.im2[b * a.im2_stride + (long)c * a.HW + i]) * m * s;
+                const float d = a.im1[o1] - a.im2[b * a.im2_stride + (long)c * a.HW + i];
+                float g = sgn(d) * m * s;
+                if (a.sigma) {      // d/d|d| = 2**0.5 / (sigma + EPS);  d/dsigma = -|d| 2**0.5 / (sigma + EPS)^2 + 1 / (sigma + EPS)
+                    const long os = ((long)b * a.sigma_C + (a.sigma_C == 1 ? 0 : c)) * a.HW + i;
+                    const float se = a.sigma[os] + PHOTO_EPS;
+                    g = g * PHOTO_SQRT2 / se;
+                    const float gsg = m * s * (1.f / se - fabsf(d) * PHOTO_SQRT2 / (se * se));
+                    if (g_sigma) { if (a.sigma_C == 1) gs_shared += gsg; else g_sigma[os] = gsg; }
+                }
                 if (g_im1) g_im1[o1] = g;
                 if (g_im2) g_im2[o1] = -g;
             }
+            if (a.sigma && g_sigma && a.sigma_C == 1) g_sigma[(long)b * a.HW + i] = gs_shared;
         }
     }
 }
@@ -447,13 +469,15 @@ int g2s_shading_bwd(const float* normal, long normal_view_stride, const float* l
 }
 
 int g2s_photometric_fwd(const float* im1, const float* im2, long im2_batch_stride, const float* recon_depth,
-                        float depth_thresh, const float* mask_in, int B, int C, int HW, void* reduce_ws, float* out3,
-                        void* stream) {
+                        float depth_thresh, const float* mask_in, const float* conf_sigma, int sigma_channels, int B, int C,
+                        int HW, void* reduce_ws, float* out3, void* stream) {
     if (!im1 || !im2 || !reduce_ws || !out3) return G2S_ERR_NULL;
     if (B <= 0 || C <= 0 || HW <= 0) return G2S_ERR_SHAPE;
-    const PhotoArgs a{im1, im2, recon_depth, mask_in, im2_batch_stride, depth_thresh, B, C, HW};
-    const bool vec = HW % 4 == 0 && im2_batch_stride % 4 == 0 && aligned16(im1) && aligned16(im2) && aligned16(recon_depth) &&
-                     aligned16(mask_in);
+    if (conf_sigma && sigma_channels != 1 && sigma_channels != C) return G2S_ERR_SHAPE;
+    const PhotoArgs a{im1, im2, recon_depth, mask_in, im2_batch_stride, depth_thresh, B, C, HW, conf_sigma, sigma_channels};
+    // conf_sigma (never used by the reference's callers) takes the scalar path
+    const bool vec = !conf_sigma && HW % 4 == 0 && im2_batch_stride % 4 == 0 && aligned16(im1) && aligned16(im2) &&
+                     aligned16(recon_depth) && aligned16(mask_in);
     const int nb = red_blocks(vec ? (long)B * HW / 4 : (long)B * HW);
     cudaStream_t st = (cudaStream_t)stream;
     { Launch l_(K_PHOTOMETRIC, st);
@@ -464,20 +488,23 @@ int g2s_photometric_fwd(const float* im1, const float* im2, long im2_batch_strid
 }
 
 int g2s_photometric_bwd(const float* im1, const float* im2, long im2_batch_stride, const float* recon_depth,
-                        float depth_thresh, const float* mask_in, int B, int C, int HW, const float* sums3,
-                        const float* grad_loss, float* grad_im1, float* grad_im2, void* stream) {
+                        float depth_thresh, const float* mask_in, const float* conf_sigma, int sigma_channels, int B, int C,
+                        int HW, const float* sums3, const float* grad_loss, float* grad_im1, float* grad_im2,
+                        float* grad_sigma, void* stream) {
     if (!im1 || !im2 || !sums3 || !grad_loss) return G2S_ERR_NULL;
-    if (!grad_im1 && !grad_im2) return G2S_ERR_NULL;
+    if (!grad_im1 && !grad_im2 && !grad_sigma) return G2S_ERR_NULL;
+    if (grad_sigma && !conf_sigma) return G2S_ERR_NULL;
     if (B <= 0 || C <= 0 || HW <= 0) return G2S_ERR_SHAPE;
+    if (conf_sigma && sigma_channels != 1 && sigma_channels != C) return G2S_ERR_SHAPE;
     if (grad_im2 && im2_batch_stride != (long)C * HW) return G2S_ERR_UNSUPPORTED;   // a broadcast target gets no gradient here
-    const PhotoArgs a{im1, im2, recon_depth, mask_in, im2_batch_stride, depth_thresh, B, C, HW};
-    const bool vec = HW % 4 == 0 && im2_batch_stride % 4 == 0 && aligned16(im1) && aligned16(im2) && aligned16(recon_depth) &&
-                     aligned16(mask_in) && aligned16(grad_im1) && aligned16(grad_im2);
+    const PhotoArgs a{im1, im2, recon_depth, mask_in, im2_batch_stride, depth_thresh, B, C, HW, conf_sigma, sigma_channels};
+    const bool vec = !conf_sigma && HW % 4 == 0 && im2_batch_stride % 4 == 0 && aligned16(im1) && aligned16(im2) &&
+                     aligned16(recon_depth) && aligned16(mask_in) && aligned16(grad_im1) && aligned16(grad_im2);
     const int nb = red_blocks(vec ? (long)B * HW / 4 : (long)B * HW);
     cudaStream_t st = (cudaStream_t)stream;
     { Launch l_(K_PHOTOMETRIC, st);
-      if (vec) k_photo_bwd<true><<<nb, RED_THREADS, 0, st>>>(a, sums3, grad_loss, grad_im1, grad_im2);
-      else k_photo_bwd<false><<<nb, RED_THREADS, 0, st>>>(a, sums3, grad_loss, grad_im1, grad_im2); }
+      if (vec) k_photo_bwd<true><<<nb, RED_THREADS, 0, st>>>(a, sums3, grad_loss, grad_im1, grad_im2, grad_sigma);
+      else k_photo_bwd<false><<<nb, RED_THREADS, 0, st>>>(a, sums3, grad_loss, grad_im1, grad_im2, grad_sigma); }
     return launch_status();
 }
 

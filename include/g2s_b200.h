@@ -262,18 +262,21 @@ int g2s_shading_bwd(const float *normal, long normal_view_stride, const float *l
                     float *grad_normal, long grad_normal_view_stride, float *grad_light5, float *grad_albedo,
                     long grad_albedo_view_stride, void *stream);
 
-/* Validity mask + PhotometricLoss (conf_sigma=None) in one pass: model.py:146-150 / 265-269 and losses.py:39-51.
+/* Validity mask + PhotometricLoss in one pass: model.py:146-150 / 265-269 and losses.py:39-51.
  *   mask[b,i] = (recon_depth ? recon_depth[b,i] < depth_thresh : 1) * (mask_in ? mask_in[b,i] : 1)
- *   loss      = sum(|im1 - im2| * mask) / (C * sum(mask))         (both NULL: the plain mean of losses.py:50)
+ *   l         = |im1 - im2|;  with conf_sigma (losses.py:44-45): l * 2**0.5 / (sigma + 1e-7) + log(sigma + 1e-7)
+ *   loss      = sum(l * mask) / (C * sum(mask))                   (no mask at all: the plain mean of losses.py:50)
  * im1 [B,C,HW]; im2 [*,C,HW] with im2_batch_stride floats between items (0 = one target for all views);
- * recon_depth, mask_in [B,HW].  out3 = {loss, numerator, denominator}; the backward reads it back as sums3 and WRITES
- * grad_im1 and/or grad_im2 [B,C,HW] (grad_im2 needs im2_batch_stride == C*HW); grad_loss is a DEVICE scalar. */
+ * recon_depth, mask_in [B,HW]; conf_sigma [B,sigma_channels,HW] with sigma_channels = 1 or C, or NULL.
+ * out3 = {loss, numerator, denominator}; the backward reads it back as sums3 and WRITES grad_im1 and/or grad_im2 [B,C,HW]
+ * (grad_im2 needs im2_batch_stride == C*HW) and/or grad_sigma [B,sigma_channels,HW]; grad_loss is a DEVICE scalar. */
 int g2s_photometric_fwd(const float *im1, const float *im2, long im2_batch_stride, const float *recon_depth,
-                        float depth_thresh, const float *mask_in, int B, int C, int HW, void *reduce_ws, float *out3,
-                        void *stream);
+                        float depth_thresh, const float *mask_in, const float *conf_sigma, int sigma_channels, int B,
+                        int C, int HW, void *reduce_ws, float *out3, void *stream);
 int g2s_photometric_bwd(const float *im1, const float *im2, long im2_batch_stride, const float *recon_depth,
-                        float depth_thresh, const float *mask_in, int B, int C, int HW, const float *sums3,
-                        const float *grad_loss, float *grad_im1, float *grad_im2, void *stream);
+                        float depth_thresh, const float *mask_in, const float *conf_sigma, int sigma_channels, int B,
+                        int C, int HW, const float *sums3, const float *grad_loss, float *grad_im1, float *grad_im2,
+                        float *grad_sigma, void *stream);
 
 /* SmoothLoss of ONE map [M,H,W]: losses.py:54-79 (mean|dx2| + mean|dxdy| + mean|dydx| + mean|dy2|, the differences taken
  * in the reference's order).  out5 = {loss, the four means}.  H, W >= 3.  Backward WRITES grad_map [M,H,W]; grad_loss is a

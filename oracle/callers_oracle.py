@@ -37,9 +37,12 @@ def recon_im_mask(recon_depth, min_depth, max_depth, masks=None):
     return m if masks is None else m * masks
 
 
-def photometric_loss(image1, image2, mask=None):
-    """GAN2Shape/losses.py:39-51 with conf_sigma=None."""
+def photometric_loss(image1, image2, mask=None, conf_sigma=None):
+    """GAN2Shape/losses.py:39-51."""
     loss = (image1 - image2).abs()
+    if conf_sigma is not None:
+        eps = 1e-7                                                       # losses.py:40
+        loss = loss * 2 ** 0.5 / (conf_sigma + eps) + (conf_sigma + eps).log()
     if mask is not None:
         mask = mask.expand_as(loss)
         return (loss * mask).sum() / mask.sum()

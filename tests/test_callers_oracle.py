@@ -37,6 +37,10 @@ def test_oracle_matches_reference_code_bitwise(S, B, seed):
     assert torch.equal(co.recon_im_mask(rd, MIN_D, MAX_D, masks), m_ref)
     assert torch.equal(co.photometric_loss(im1, im2, m_ref), losses.PhotometricLoss()(im1, im2, mask=m_ref))
     assert torch.equal(co.photometric_loss(im1, im2), losses.PhotometricLoss()(im1, im2))
+    for sig in (0.05 + torch.rand(B, 1, S, S, generator=g), 0.05 + torch.rand(B, 3, S, S, generator=g)):
+        assert torch.equal(co.photometric_loss(im1, im2, m_ref, sig),
+                           losses.PhotometricLoss()(im1, im2, mask=m_ref, conf_sigma=sig))
+        assert torch.equal(co.photometric_loss(im1, im2, None, sig), losses.PhotometricLoss()(im1, im2, conf_sigma=sig))
     for m in (raw, im1[:, :1], [raw, raw[:, ::2, ::2]]):
         assert torch.equal(co.smooth_loss(m), losses.SmoothLoss()(m))
 

@@ -2,6 +2,7 @@
 against the oracle (oracle/callers_oracle.py, pinned to the reference's own model.py / losses.py) and against the golden
 vectors the reference's code produced.  Floating point: 1e-5 relative (max|a-b| / max|b|), the north star's bar; the
 losses are sums of up to 10^8 terms whose order differs from torch-CPU's, so scalars are held to 1e-5 relative as well."""
+import numpy as np
 import pytest
 import torch
 
@@ -127,6 +128,37 @@ def test_photometric_vs_oracle(B, C, S, use_depth, use_mask, bcast):
         assert rel_err(y.grad.cpu(), y_o.grad) < TOL
 
 
+@pytest.mark.parametrize("B,C,S,sigma_c,use_mask", [(4, 3, 32, 1, True), (3, 3, 21, 3, True), (2, 1, 17, 1, False),
+                                                    (2, 3, 64, 1, False)])
+def test_photometric_conf_sigma_vs_oracle(B, C, S, sigma_c, use_mask):
+    """losses.py:44-45: the confidence-weighted form, value and the gradients to both images and to sigma."""
+    g2s = _g()
+    gen = torch.Generator().manual_seed(11 * B + C + S)
+    im1 = torch.rand(B, C, S, S, generator=gen) * 2 - 1
+    im2 = torch.rand(B, C, S, S, generator=gen) * 2 - 1
+    im2[..., :2, :] = im1[..., :2, :]
+    sig = 0.05 + torch.rand(B, sigma_c, S, S, generator=gen)
+    rd = 0.8 + 0.4 * torch.rand(B, S, S, generator=gen)
+    masks = (torch.rand(B, 1, S, S, generator=gen) > 0.25).float()
+    x_o, y_o, s_o = (t.clone().requires_grad_(True) for t in (im1, im2, sig))
+    m_o = co.recon_im_mask(rd, MIN_D, MAX_D, masks) if use_mask else None
+    l_o = co.photometric_loss(x_o, y_o, m_o, s_o)
+    (l_o * 1.3).backward()
+    x, y, sg = (t.cuda().requires_grad_(True) for t in (im1, im2, sig))
+    kw = dict(mask=masks.cuda(), **g2s.recon_im_mask(rd.cuda(), MIN_D, MAX_D)) if use_mask else {}
+    loss = g2s.PhotometricLoss()(x, y, conf_sigma=sg, **kw)
+    (loss * 1.3).backward()
+    assert rel_err(loss.detach().cpu(), l_o.detach()) < TOL
+    assert rel_err(x.grad.cpu(), x_o.grad) < TOL
+    assert rel_err(y.grad.cpu(), y_o.grad) < TOL
+    assert rel_err(sg.grad.cpu(), s_o.grad) < TOL
+    # sigma = 2**0.5 - EPS (to rounding) and the log term vanishing: equal to the plain loss when log(sigma) is subtracted
+    one = torch.full((B, 1, S, S), 2 ** 0.5, device="cuda")
+    plain = g2s.PhotometricLoss()(x.detach(), y.detach(), **kw)
+    withs = g2s.PhotometricLoss()(x.detach(), y.detach(), conf_sigma=one, **kw)
+    assert abs(withs.item() - plain.item() - 0.5 * np.log(2.0)) < 1e-5
+
+
 @pytest.mark.parametrize("shape", [(1, 128, 128), (3, 1, 33, 20), (2, 3, 3), (4, 1, 64, 64)])
 def test_smooth_vs_oracle(shape):
     g2s = _g()
@@ -177,8 +209,8 @@ def test_errors():
         g2s.get_clamped_depth(torch.zeros(1, 8, 8), 8, 8, MIN_D, MAX_D)            # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         g2s.get_clamped_depth(torch.zeros(1, 8, 9, device="cuda"), 8, 8, MIN_D, MAX_D)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         g2s.PhotometricLoss()(torch.zeros(1, 3, 4, 4, device="cuda"), torch.zeros(1, 3, 4, 4, device="cuda"),
-                              conf_sigma=torch.ones(1, 1, 4, 4, device="cuda"))
+                              conf_sigma=torch.ones(1, 2, 4, 4, device="cuda"))                  # 1 or C channels
     with pytest.raises(RuntimeError):
         g2s.SmoothLoss()(torch.zeros(1, 2, 2, device="cuda"))                        # H, W >= 3
