@@ -241,6 +241,13 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_device()
+    if args.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -471,6 +478,9 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-image", action="store_true", help="skip the 1-image CUDA-graph extra (profiling runs)")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling runs only: after the warm-up, bracket ONE step with cudaProfilerStart/Stop and exit "
+                         "(ncu --profile-from-start off ...); prints no bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
