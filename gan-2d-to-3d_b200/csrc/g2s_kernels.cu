@@ -726,77 +726,160 @@ k_points_bwd(const Cam cam, const float* __restrict__ verts3d, const float* __re
     o[2] = gp.z - (gx_ * x_ + gy_ * y_) * iz;
 }
 
-constexpr int RBX = 16, RBY = 8;
-__global__ void __launch_bounds__(RBX * RBY)
+// One (pixel, face) item: the face's record from the projected vertices, the owned sub-pixels' weights / z, the three
+// 16-byte vertex reductions.  `mine` = which of the pixel's 2x2 sub-pixels (bit k: column k & 1, row k >> 1) the face owns.
+__device__ __forceinline__ void raster_bwd_item(const Cam& cam, const float4* __restrict__ pv, float4* __restrict__ vg, int S,
+                                                int is, int face, unsigned mine, int j, int i, float g) {
+    const float hs = 0.5f * (float)is;
+    int vidx[3];
+    face_vertices(face, S, vidx);
+    float nd[3][3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const float4 q = __ldg(&pv[vidx[m]]);
+        nd[m][0] = q.x; nd[m][1] = q.y; nd[m][2] = q.z;
+    }
+    float rec[16];
+    face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
+    float A[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    while (mine) {
+        const int k2 = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const int xi = 2 * j + (k2 & 1), yi = is - 1 - (2 * i + (k2 >> 1));
+        float w[3], zp = 0.f;
+        record_weights_depth(rec, xi, yi, cam.near, cam.far, w, &zp);
+        const float s = g * zp * zp;
+        A[0] += s * w[0]; A[1] += s * w[1]; A[2] += s * w[2];
+    }
+    // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
+    const float z[3] = {rec[9], rec[10], rec[11]};
+    // six exact quotients fi[m][l] / z_m from the tabulated reciprocal seeds, one merged range check
+    float qd[6];
+    unsigned bad = 0;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const float yz = rcp_seed(z[m]);
+        qd[m] = div_core(rec[3 * m], z[m], yz);
+        qd[3 + m] = div_core(rec[3 * m + 1], z[m], yz);
+        bad = max(bad, rec[3 * m] == 0.0f ? 0u : range_key(rec[3 * m]));
+        bad = max(bad, rec[3 * m + 1] == 0.0f ? 0u : range_key(rec[3 * m + 1]));
+    }
+    if (bad >= RANGE_SPAN || rec[FT_FLAG] != 0.0f) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) { qd[m] = __fdiv_rn(rec[3 * m], z[m]); qd[3 + m] = __fdiv_rn(rec[3 * m + 1], z[m]); }
+    }
+    const float t0 = -(qd[0] + qd[1] + qd[2]);
+    const float t1 = -(qd[3] + qd[4] + qd[5]);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        if (A[m] == 0.f) continue;
+        // one 16-byte vector reduction per vertex instead of three scalar ones
+        atomicAdd(&vg[vidx[m]], make_float4(-t0 * A[m] * hs, -t1 * A[m] * hs, __fdiv_rn(A[m], z[m] * z[m]), 0.f));
+    }
+}
+
+// A CTA of four warps covers 16 x 32 output pixels, a warp 16 x 8 of them in four groups of 16 x 2.  A pixel holds 0-4
+// distinct faces (2.9 on average where covered, none where the view left the frame), so a loop "one thread per pixel, one
+// trip per face" runs at 19 of 32 lanes (profiles/r01_notes.md).  Instead every lane lists its pixel's (face, owned
+// sub-pixels) ITEMS in a warp-private queue and the warp takes them off 32 at a time: all lanes busy in every round but
+// the last of a warp's 128 pixels.  Warp-local throughout (no CTA barrier).
+constexpr int RBX = 16, RBY = 32, RB_THREADS = 128, RB_GROUPS = 4;
+#ifndef G2S_RB_DUAL
+#define G2S_RB_DUAL 1
+#endif
+// Items that own ONE sub-pixel (most of them) and items that own several are queued from the two ends of one buffer and
+// taken off in separate rounds: the per-item loop over owned sub-pixels then runs one trip in the rounds of singles instead
+// of the warp-wide maximum in every round.
+constexpr int RB_QCAP = 32 * 4 + 2 * 32;     // one group's worst case on top of two remainders below 32
+struct RasterBwdSmem {
+    int face[RB_THREADS / 32][RB_QCAP];
+    unsigned short meta[RB_THREADS / 32][RB_QCAP];    // pixel within the warp's 128 (7 bits) | owned sub-pixels << 7
+    float g[RB_THREADS / 32][32 * RB_GROUPS];
+};
+
+__global__ void __launch_bounds__(RB_THREADS)
 k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
                 const float* __restrict__ proj, float* __restrict__ vgrad, int view0) {
+    __shared__ RasterBwdSmem sm;
     const int S = cam.S, is = 2 * S, bl = blockIdx.z, b = view0 + bl;
-    const int j = blockIdx.x * RBX + threadIdx.x, i = blockIdx.y * RBY + threadIdx.y;
-    if (j >= S || i >= S) return;
-    const float g = g_sub[(long)bl * S * S + i * S + j];
-    if (g == 0.f) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * RBX + (lane & 15);
+    const int i_w = blockIdx.y * RBY + warp * (2 * RB_GROUPS);
+    if (i_w >= S) return;                                                            // whole warp below the image
     const int* fm = face_idx + (long)b * is * is;
-    const int2 r0 = *reinterpret_cast<const int2*>(fm + (long)(2 * i) * is + 2 * j);
-    const int2 r1 = *reinterpret_cast<const int2*>(fm + (long)(2 * i + 1) * is + 2 * j);
-    const int f0 = r0.x, f1 = r0.y, f2 = r1.x, f3 = r1.y;
     const float4* pv = reinterpret_cast<const float4*>(proj) + (long)bl * S * S;   // projected vertices, packed uvz-
     float4* vg = reinterpret_cast<float4*>(vgrad) + (long)bl * S * S;              // vertex gradients, packed uvz-
-    const float hs = 0.5f * (float)is;
-    // Distinct faces of the 2x2 block, one per trip of ONE loop body (not four unrolled copies: the unrolled form ran
-    // at 17 active lanes per instruction and stalled on instruction fetch, profiles/r01_notes.md): `rem` = sub-pixels
-    // still to do; a trip takes the face of the lowest one and every other sub-pixel that shares it.
-    unsigned rem = (f0 >= 0 ? 1u : 0u) | (f1 >= 0 ? 2u : 0u) | (f2 >= 0 ? 4u : 0u) | (f3 >= 0 ? 8u : 0u);
+    int* qf = sm.face[warp];
+    unsigned short* qm = sm.meta[warp];
+    float* gs = sm.g[warp];
+    // a group's inputs are requested one group ahead
+    float g_next;
+    int2 r0_next, r1_next;
+    auto request = [&](int grp) {
+        const int i = i_w + 2 * grp + (lane >> 4);
+        const bool in = j < S && i < S;
+        g_next = in ? __ldg(&g_sub[(long)bl * S * S + i * S + j]) : 0.f;
+        r0_next = r1_next = make_int2(-1, -1);
+        if (in) {
+            r0_next = __ldg(reinterpret_cast<const int2*>(fm + (long)(2 * i) * is + 2 * j));
+            r1_next = __ldg(reinterpret_cast<const int2*>(fm + (long)(2 * i + 1) * is + 2 * j));
+        }
+    };
+    request(0);
+    int n_one = 0, n_many = 0;      // queued singles (slots [0, n_one)) and multi-sub-pixel items (slots (CAP - 1 - n_many, CAP - 1])
+    // ONE copy of the item body (four unrolled copies stall on instruction fetch, profiles/r01_notes.md)
 #pragma unroll 1
-    while (rem) {
-        const int k = __ffs(rem) - 1;
-        const int face = k == 0 ? f0 : (k == 1 ? f1 : (k == 2 ? f2 : f3));
-        unsigned mine = ((f0 == face ? 1u : 0u) | (f1 == face ? 2u : 0u) | (f2 == face ? 4u : 0u) | (f3 == face ? 8u : 0u)) & rem;
-        rem &= ~mine;
-        int vidx[3];
-        face_vertices(face, S, vidx);
-        float nd[3][3];
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const float4 q = __ldg(&pv[vidx[m]]);
-            nd[m][0] = q.x; nd[m][1] = q.y; nd[m][2] = q.z;
-        }
-        float rec[16];
-        face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
-        float A[3] = {0.f, 0.f, 0.f};
+    for (int grp = 0; grp < RB_GROUPS; grp++) {
+        const float gq = g_next;
+        const bool on = gq != 0.f;
+        const int f0 = on ? r0_next.x : -1, f1 = on ? r0_next.y : -1, f2 = on ? r1_next.x : -1, f3 = on ? r1_next.y : -1;
+        if (grp + 1 < RB_GROUPS) request(grp + 1);
+        // first occurrence of every distinct face of the 2x2 block, and the sub-pixels it owns
+        const bool a0 = f0 >= 0, a1 = f1 >= 0 && f1 != f0, a2 = f2 >= 0 && f2 != f0 && f2 != f1,
+                   a3 = f3 >= 0 && f3 != f0 && f3 != f1 && f3 != f2;
+        const unsigned m0 = 1u | (f1 == f0 ? 2u : 0u) | (f2 == f0 ? 4u : 0u) | (f3 == f0 ? 8u : 0u);
+        const unsigned m1 = 2u | (f2 == f1 ? 4u : 0u) | (f3 == f1 ? 8u : 0u);
+        const unsigned m2 = 4u | (f3 == f2 ? 8u : 0u);
+        const bool s0 = G2S_RB_DUAL && (m0 & (m0 - 1u)) != 0u, s1 = G2S_RB_DUAL && (m1 & (m1 - 1u)) != 0u,
+                   s2 = G2S_RB_DUAL && (m2 & (m2 - 1u)) != 0u;      // owns several sub-pixels
+        const int c_many = (int)(a0 && s0) + (int)(a1 && s1) + (int)(a2 && s2);
+        const int c_one = (int)a0 + (int)a1 + (int)a2 + (int)a3 - c_many;
+        int tot;
+        const int ex = warp_excl_scan(c_one | c_many << 8, &tot);
+        int p_one = n_one + (ex & 255), p_many = RB_QCAP - 1 - (n_many + (ex >> 8));
+        const unsigned pid = (unsigned)(grp * 32 + lane);
+        gs[pid] = gq;
+        if (a0) { const int q = s0 ? p_many-- : p_one++; qf[q] = f0; qm[q] = (unsigned short)(pid | m0 << 7); }
+        if (a1) { const int q = s1 ? p_many-- : p_one++; qf[q] = f1; qm[q] = (unsigned short)(pid | m1 << 7); }
+        if (a2) { const int q = s2 ? p_many-- : p_one++; qf[q] = f2; qm[q] = (unsigned short)(pid | m2 << 7); }
+        if (a3) { qf[p_one] = f3; qm[p_one] = (unsigned short)(pid | 8u << 7); }
+        n_one += tot & 255;
+        n_many += tot >> 8;
+        __syncwarp();
+        // full rounds off the ends of the queue; what stays (< 32 of either kind) waits for the next group, the last group
+        // drains it in mixed rounds
+        const bool last = grp == RB_GROUPS - 1;
 #pragma unroll 1
-        while (mine) {
-            const int k2 = __ffs(mine) - 1;
-            mine &= mine - 1;
-            const int xi = 2 * j + (k2 & 1), yi = is - 1 - (2 * i + (k2 >> 1));
-            float w[3], zp = 0.f;
-            record_weights_depth(rec, xi, yi, cam.near, cam.far, w, &zp);
-            const float s = g * zp * zp;
-            A[0] += s * w[0]; A[1] += s * w[1]; A[2] += s * w[2];
-        }
-        // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
-        const float z[3] = {rec[9], rec[10], rec[11]};
-        // six exact quotients fi[m][l] / z_m from the tabulated reciprocal seeds, one merged range check
-        float qd[6];
-        unsigned bad = 0;
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const float yz = rcp_seed(z[m]);
-            qd[m] = div_core(rec[3 * m], z[m], yz);
-            qd[3 + m] = div_core(rec[3 * m + 1], z[m], yz);
-            bad = max(bad, rec[3 * m] == 0.0f ? 0u : range_key(rec[3 * m]));
-            bad = max(bad, rec[3 * m + 1] == 0.0f ? 0u : range_key(rec[3 * m + 1]));
-        }
-        if (bad >= RANGE_SPAN || rec[FT_FLAG] != 0.0f) {
-#pragma unroll
-            for (int m = 0; m < 3; m++) { qd[m] = __fdiv_rn(rec[3 * m], z[m]); qd[3 + m] = __fdiv_rn(rec[3 * m + 1], z[m]); }
-        }
-        const float t0 = -(qd[0] + qd[1] + qd[2]);
-        const float t1 = -(qd[3] + qd[4] + qd[5]);
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            if (A[m] == 0.f) continue;
-            // one 16-byte vector reduction per vertex instead of three scalar ones
-            atomicAdd(&vg[vidx[m]], make_float4(-t0 * A[m] * hs, -t1 * A[m] * hs, __fdiv_rn(A[m], z[m] * z[m]), 0.f));
+        while (true) {
+            int src = -1;
+            if (n_one >= 32) { n_one -= 32; src = n_one + lane; }
+            else if (n_many >= 32) { n_many -= 32; src = RB_QCAP - 1 - (n_many + lane); }
+            else if (last && n_one + n_many > 0) {
+                const int t_one = n_one, t_many = min(n_many, 32 - t_one);
+                n_one = 0; n_many -= t_many;
+                if (lane < t_one) src = lane;
+                else if (lane - t_one < t_many) src = RB_QCAP - 1 - (n_many + lane - t_one);
+            } else break;
+            int face = -1;
+            unsigned meta = 0;
+            if (src >= 0) { face = qf[src]; meta = qm[src]; }
+            const unsigned p = meta & 127u;
+            const float g = gs[p];
+            __syncwarp();                 // the slots are free for the next group's items
+            if (face >= 0)
+                raster_bwd_item(cam, pv, vg, S, is, face, meta >> 7, blockIdx.x * RBX + (int)(p & 15u),
+                                i_w + 2 * (int)(p >> 5) + (int)((p >> 4) & 1u), g);
         }
     }
 }
@@ -1676,7 +1759,7 @@ inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, in
       if (verts3d) k_project_points<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj, vgrad);
       else k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj, vgrad); }
     { Launch l_(K_RASTER_BWD, st);
-      k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), dim3(RBX, RBY), 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
+      k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), RB_THREADS, 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
       if (verts3d) k_points_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, vgrad, grad_verts);
       else k_vertex_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
