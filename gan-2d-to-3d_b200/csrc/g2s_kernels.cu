@@ -672,7 +672,9 @@ __global__ void k_light_bwd(const float* __restrict__ light, int B, const float*
 // vertex through projection / rotation to grad_depth, grad_R, grad_t.  neural_renderer does 9 float atomics per
 // covered sub-pixel into grad_faces[B,F,3,3] and leaves the gather to autograd (index_put over 6 faces per vertex).
 
-// projected (u, v, z) of every vertex of the chunk's views: proj [chunk, S*S, 3]
+// projected (u, v, z) of every vertex of the chunk's views: proj [chunk, S*S] float4 = (u, v, z, -) in NDC or, with PIX, the
+// sub-pixel coordinates ndc_to_pix(u), ndc_to_pix(v) the face inverse is built from (what k_raster_bwd_px wants)
+template <bool PIX>
 __global__ void __launch_bounds__(PIX_THREADS)
 k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
                 const float* __restrict__ t, int view0, float* __restrict__ proj, float* __restrict__ vgrad_zero) {
@@ -688,12 +690,14 @@ k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, in
     pixel_ray(cam, vx, vy, ray);
     warp_point(cam, sRt, sRt + 9, ray, depth[(long)(b / vpi) * dstride + v], q);
     project_ndc(cam, q, ndc);
+    if (PIX) { ndc[0] = ndc_to_pix(ndc[0], 2 * S); ndc[1] = ndc_to_pix(ndc[1], 2 * S); }
     reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
     // the vertex-gradient scratch of the same vertex starts at zero (a 1 GB cudaMemset per step otherwise)
     reinterpret_cast<float4*>(vgrad_zero)[(long)bl * S * S + v] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // the same for vertices given as 3-D points (the neural_renderer-level entry g2s_render_depth_*): projection only
+template <bool PIX>
 __global__ void __launch_bounds__(PIX_THREADS)
 k_project_points(const Cam cam, const float* __restrict__ verts3d, float* __restrict__ proj, float* __restrict__ vgrad_zero) {
     const int S = cam.S, bl = blockIdx.y;
@@ -703,6 +707,7 @@ k_project_points(const Cam cam, const float* __restrict__ verts3d, float* __rest
     const float q[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
     float ndc[3];
     project_ndc(cam, q, ndc);
+    if (PIX) { ndc[0] = ndc_to_pix(ndc[0], 2 * S); ndc[1] = ndc_to_pix(ndc[1], 2 * S); }
     reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
     reinterpret_cast<float4*>(vgrad_zero)[(long)bl * S * S + v] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -726,21 +731,28 @@ k_points_bwd(const Cam cam, const float* __restrict__ verts3d, const float* __re
     o[2] = gp.z - (gx_ * x_ + gy_ * y_) * iz;
 }
 
-// One (pixel, face) item: the face's record from the projected vertices, the owned sub-pixels' weights / z, the three
-// 16-byte vertex reductions.  `mine` = which of the pixel's 2x2 sub-pixels (bit k: column k & 1, row k >> 1) the face owns.
+#ifndef G2S_RB_EXACT
+#define G2S_RB_EXACT 0
+#endif
+// One (pixel, face) item: the face's 3x3 inverse from the projected vertices (sub-pixel coordinates), the owned
+// sub-pixels' weights / z, the three 16-byte vertex reductions.  `mine` = which of the pixel's 2x2 sub-pixels (bit k:
+// column k & 1, row k >> 1) the face owns.
+// Arithmetic: the face inverse and the clamped weights are the forward's own operation sequence (the inverse is
+// ill-conditioned -- fi * x + fi * y + fi cancels to a weight in [0,1] from terms of size ~is/2 -- so a 1-ulp change in fi is a
+// 1e-5 change in a weight), and so are the six quotients of the x / y gradient (see below); the normalisation of the weights,
+// the perspective z and the z gradient have no cancellation and run on refined reciprocals (MUFU.RCP + one Newton step,
+// ~1 ulp) instead of correctly rounded quotients: gradients hold 1e-5, not bits.
 __device__ __forceinline__ void raster_bwd_item(const Cam& cam, const float4* __restrict__ pv, float4* __restrict__ vg, int S,
                                                 int is, int face, unsigned mine, int j, int i, float g) {
     const float hs = 0.5f * (float)is;
     int vidx[3];
     face_vertices(face, S, vidx);
-    float nd[3][3];
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-        const float4 q = __ldg(&pv[vidx[m]]);
-        nd[m][0] = q.x; nd[m][1] = q.y; nd[m][2] = q.z;
-    }
+    const float4 q0 = __ldg(&pv[vidx[0]]), q1 = __ldg(&pv[vidx[1]]), q2 = __ldg(&pv[vidx[2]]);
+#if G2S_RB_EXACT
     float rec[16];
-    face_record(make_tri(nd[0], nd[1], nd[2]), is, rec);
+    bool zb;
+    face_record_px(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q0.z, q1.z, q2.z, rec, &zb);
+    rec[FT_FLAG] = zb ? 1.0f : 0.0f;
     float A[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
     while (mine) {
@@ -754,7 +766,6 @@ __device__ __forceinline__ void raster_bwd_item(const Cam& cam, const float4* __
     }
     // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m
     const float z[3] = {rec[9], rec[10], rec[11]};
-    // six exact quotients fi[m][l] / z_m from the tabulated reciprocal seeds, one merged range check
     float qd[6];
     unsigned bad = 0;
 #pragma unroll
@@ -774,9 +785,43 @@ __device__ __forceinline__ void raster_bwd_item(const Cam& cam, const float4* __
 #pragma unroll
     for (int m = 0; m < 3; m++) {
         if (A[m] == 0.f) continue;
-        // one 16-byte vector reduction per vertex instead of three scalar ones
         atomicAdd(&vg[vidx[m]], make_float4(-t0 * A[m] * hs, -t1 * A[m] * hs, __fdiv_rn(A[m], z[m] * z[m]), 0.f));
     }
+#else
+    float fi[REC_F];
+    bool zb;
+    face_record_px(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q0.z, q1.z, q2.z, fi, &zb);
+    const float rz[3] = {rcp_seed(q0.z), rcp_seed(q1.z), rcp_seed(q2.z)};
+    float A[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    while (mine) {
+        const int k2 = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const float fx = (float)(2 * j + (k2 & 1)), fy = (float)(is - 1 - (2 * i + (k2 >> 1)));
+        float wc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {      // [nr] kernel 2: the forward's clamped weights, same operations
+            const float v = add(add(mul(fi[3 * k], fx), mul(fi[3 * k + 1], fy)), fi[3 * k + 2]);
+            wc[k] = fminf(fmaxf(v, 0.0f), 1.0f);
+        }
+        const float ys = rcp_seed(add(add(add(0.0f, wc[0]), wc[1]), wc[2]));
+        const float w0 = wc[0] * ys, w1 = wc[1] * ys, w2 = wc[2] * ys;
+        const float zp = rcp_seed(w0 * rz[0] + w1 * rz[1] + w2 * rz[2]);
+        const float s = g * zp * zp;
+        A[0] += s * w0; A[1] += s * w1; A[2] += s * w2;
+    }
+    // [nr] backward_depth_map: tmp[l] = -sum_m face_inv[m][l] / z_m.  The columns of the inverse sum to zero (the weights sum to
+    // one), so with three nearly equal z's this sum cancels to its last bits: correctly rounded quotients, summed in the
+    // reference's order, or the result is off by 1e-4 (measured with reciprocals: profiles/r02_notes.md)
+    const float t0 = -add(add(dvd(fi[0], q0.z), dvd(fi[3], q1.z)), dvd(fi[6], q2.z)) * hs;
+    const float t1 = -add(add(dvd(fi[1], q0.z), dvd(fi[4], q1.z)), dvd(fi[7], q2.z)) * hs;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        if (A[m] == 0.f) continue;
+        // one 16-byte vector reduction per vertex instead of three scalar ones
+        atomicAdd(&vg[vidx[m]], make_float4(-t0 * A[m], -t1 * A[m], A[m] * rz[m] * rz[m], 0.f));
+    }
+#endif
 }
 
 // A CTA of four warps covers 16 x 32 output pixels, a warp 16 x 8 of them in four groups of 16 x 2.  A pixel holds 0-4
@@ -784,7 +829,10 @@ __device__ __forceinline__ void raster_bwd_item(const Cam& cam, const float4* __
 // trip per face" runs at 19 of 32 lanes (profiles/r01_notes.md).  Instead every lane lists its pixel's (face, owned
 // sub-pixels) ITEMS in a warp-private queue and the warp takes them off 32 at a time: all lanes busy in every round but
 // the last of a warp's 128 pixels.  Warp-local throughout (no CTA barrier).
-constexpr int RBX = 16, RBY = 32, RB_THREADS = 128, RB_GROUPS = 4;
+#ifndef G2S_RB_GROUPS
+#define G2S_RB_GROUPS 4
+#endif
+constexpr int RB_GROUPS = G2S_RB_GROUPS, RBX = 16, RBY = 8 * RB_GROUPS, RB_THREADS = 128;
 #ifndef G2S_RB_DUAL
 #define G2S_RB_DUAL 1
 #endif
@@ -794,7 +842,7 @@ constexpr int RBX = 16, RBY = 32, RB_THREADS = 128, RB_GROUPS = 4;
 constexpr int RB_QCAP = 32 * 4 + 2 * 32;     // one group's worst case on top of two remainders below 32
 struct RasterBwdSmem {
     int face[RB_THREADS / 32][RB_QCAP];
-    unsigned short meta[RB_THREADS / 32][RB_QCAP];    // pixel within the warp's 128 (7 bits) | owned sub-pixels << 7
+    unsigned short meta[RB_THREADS / 32][RB_QCAP];    // pixel within the warp's 32 * RB_GROUPS (8 bits) | owned sub-pixels << 8
     float g[RB_THREADS / 32][32 * RB_GROUPS];
 };
 
@@ -850,10 +898,10 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
         int p_one = n_one + (ex & 255), p_many = RB_QCAP - 1 - (n_many + (ex >> 8));
         const unsigned pid = (unsigned)(grp * 32 + lane);
         gs[pid] = gq;
-        if (a0) { const int q = s0 ? p_many-- : p_one++; qf[q] = f0; qm[q] = (unsigned short)(pid | m0 << 7); }
-        if (a1) { const int q = s1 ? p_many-- : p_one++; qf[q] = f1; qm[q] = (unsigned short)(pid | m1 << 7); }
-        if (a2) { const int q = s2 ? p_many-- : p_one++; qf[q] = f2; qm[q] = (unsigned short)(pid | m2 << 7); }
-        if (a3) { qf[p_one] = f3; qm[p_one] = (unsigned short)(pid | 8u << 7); }
+        if (a0) { const int q = s0 ? p_many-- : p_one++; qf[q] = f0; qm[q] = (unsigned short)(pid | m0 << 8); }
+        if (a1) { const int q = s1 ? p_many-- : p_one++; qf[q] = f1; qm[q] = (unsigned short)(pid | m1 << 8); }
+        if (a2) { const int q = s2 ? p_many-- : p_one++; qf[q] = f2; qm[q] = (unsigned short)(pid | m2 << 8); }
+        if (a3) { qf[p_one] = f3; qm[p_one] = (unsigned short)(pid | 8u << 8); }
         n_one += tot & 255;
         n_many += tot >> 8;
         __syncwarp();
@@ -874,11 +922,11 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
             int face = -1;
             unsigned meta = 0;
             if (src >= 0) { face = qf[src]; meta = qm[src]; }
-            const unsigned p = meta & 127u;
+            const unsigned p = meta & 255u;
             const float g = gs[p];
             __syncwarp();                 // the slots are free for the next group's items
             if (face >= 0)
-                raster_bwd_item(cam, pv, vg, S, is, face, meta >> 7, blockIdx.x * RBX + (int)(p & 15u),
+                raster_bwd_item(cam, pv, vg, S, is, face, meta >> 8, blockIdx.x * RBX + (int)(p & 15u),
                                 i_w + 2 * (int)(p >> 5) + (int)((p >> 4) & 1u), g);
         }
     }
@@ -1756,8 +1804,8 @@ inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, in
     float* vgrad = proj + (size_t)nv * 4 * img;
     float* g_sub = raster_ws_gsub(raster_ws, nv, S);
     { Launch l_(K_PROJECT, st);     // also zeroes vgrad
-      if (verts3d) k_project_points<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj, vgrad);
-      else k_project_verts<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj, vgrad); }
+      if (verts3d) k_project_points<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj, vgrad);
+      else k_project_verts<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj, vgrad); }
     { Launch l_(K_RASTER_BWD, st);
       k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), RB_THREADS, 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
@@ -2272,7 +2320,7 @@ int g2s_render_rgb_bwd(const g2s_camera* cam, const float* vertices3d, const flo
         Launch l_(K_RESOLVE_RGB, st);
         k_rgb_map<<<pix_grid((long)is * is, n_views), PIX_THREADS, 0, st>>>(c, face_idx, vertices3d, im, im_view_stride, b4, eps, rgb_map);
         k_rgb_gquarter<<<g, PIX_THREADS, 0, st>>>(S, rgb_map, grad_rgb, clamp, g4);
-        k_project_points<<<g, PIX_THREADS, 0, st>>>(c, vertices3d, proj, vgrad);      // also zeroes vgrad
+        k_project_points<false><<<g, PIX_THREADS, 0, st>>>(c, vertices3d, proj, vgrad);      // also zeroes vgrad
         const int Q4 = 4 * (S - 1) * (S - 1);
         k_backward_pixel_map<<<dim3((Q4 + 127) / 128, n_views), 128, 0, st>>>(c, face_idx, proj, rgb_map, g4, eps, vgrad);
         k_points_bwd<<<g, PIX_THREADS, 0, st>>>(c, vertices3d, vgrad, grad_vertices);
