@@ -47,7 +47,7 @@ SIGNATURES = {
     "g2s_chunk_views_bwd": (_c_int, [_c_int]),
     "g2s_render_fused_fwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _vp]),
-    "g2s_render_fused_bwd": (_c_int, [_CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
+    "g2s_render_fused_bwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
                                       _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_rgb_fwd": (_c_int, [_CAMP, _vp, _vp, _c_long, _c_int, _c_int, _c_int, ctypes.POINTER(_c_float),
                                     _c_int, _vp, _vp, _vp, _vp]),

@@ -1795,23 +1795,38 @@ inline float* raster_ws_gsub(float* raster_ws, int nv, int S) { return raster_ws
 // Backward of the rasteriser for `nv` views.  raster_ws [nv, 9, S, S] floats: projected vertices (uvz-, 16-byte texels) |
 // vertex gradients (uvz-) | masked quarter gradient g_sub [nv, S, S].  Mesh from (depth, R, t) or, when verts3d is given, from
 // 3-D points (gradient -> grad_verts [nv, S*S, 3], written).
-inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
-                              const float* verts3d, const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth,
-                              long gdstride, float* grad_verts, float* grad_R, float* grad_t, cudaStream_t st) {
+inline void launch_raster_project(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
+                                  const float* verts3d, float* raster_ws, int nv, int view0, cudaStream_t st) {
     const int S = c.S;
-    const size_t img = (size_t)S * S;
     float* proj = raster_ws;
-    float* vgrad = proj + (size_t)nv * 4 * img;
+    float* vgrad = proj + (size_t)nv * 4 * S * S;
+    Launch l_(K_PROJECT, st);     // also zeroes vgrad
+    if (verts3d) k_project_points<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj, vgrad);
+    else k_project_verts<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj, vgrad);
+}
+
+inline void launch_raster_gather(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
+                                 const float* verts3d, const int* face_idx, float* raster_ws, int nv, int view0,
+                                 float* grad_depth, long gdstride, float* grad_verts, float* grad_R, float* grad_t,
+                                 cudaStream_t st) {
+    const int S = c.S;
+    float* proj = raster_ws;
+    float* vgrad = proj + (size_t)nv * 4 * S * S;
     float* g_sub = raster_ws_gsub(raster_ws, nv, S);
-    { Launch l_(K_PROJECT, st);     // also zeroes vgrad
-      if (verts3d) k_project_points<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, proj, vgrad);
-      else k_project_verts<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, proj, vgrad); }
     { Launch l_(K_RASTER_BWD, st);
       k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), RB_THREADS, 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
       if (verts3d) k_points_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, vgrad, grad_verts);
       else k_vertex_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
                                                                         gdstride, grad_R, grad_t); }
+}
+
+inline void launch_raster_bwd(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
+                              const float* verts3d, const int* face_idx, float* raster_ws, int nv, int view0, float* grad_depth,
+                              long gdstride, float* grad_verts, float* grad_R, float* grad_t, cudaStream_t st) {
+    launch_raster_project(c, depth, dstride, vpi, R, t, verts3d, raster_ws, nv, view0, st);
+    launch_raster_gather(c, depth, dstride, vpi, R, t, verts3d, face_idx, raster_ws, nv, view0, grad_depth, gdstride, grad_verts,
+                         grad_R, grad_t, st);
 }
 
 }  // namespace
@@ -2084,7 +2099,7 @@ int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* d
     return rc_lane ? rc_lane : launch_status();
 }
 
-int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+int g2s_render_fused_bwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners,
                          const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
                          const float* grad_recon_im, const float* grad_recon_depth, int ws_views, float* grad_sub_ws,
@@ -2110,12 +2125,29 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
     const int chunk = ws_views < 32768 ? ws_views : 32768;
     // the per-view texture-gradient scratch is zeroed once; k_render_bwd_tex leaves what it consumed at zero
     cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * (size_t)(n_views < chunk ? n_views : chunk) * 4 * img_f, st);
+    // Two lanes inside a chunk: the bandwidth-bound kernels (vertex projection, texture-gradient reduction) run on the
+    // context's side stream under the issue-bound ones (pixel stage, raster gather) of the caller's stream:
+    //   caller:  k_render_bwd_pixel ............ k_raster_bwd_px  k_vertex_bwd
+    //   side:    k_project_verts     (wait pixel) k_render_bwd_tex
+    // Fork / join with the context's events (capturable in a CUDA graph); without a context everything is serial.
+    const bool two = ctx != nullptr && !ctx->no_pipeline;
+    cudaStream_t sd = two ? ctx->aux[1] : st;
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
+        if (two) {
+            cudaEventRecord(ctx->ev_fork, st);             // after the memsets / the previous chunk's gather
+            cudaStreamWaitEvent(sd, ctx->ev_fork, 0);
+            launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, sd);
+            cudaEventRecord(ctx->ev_join[1], sd);
+        }
         { Launch l_(K_BWD_PIXEL, st);
           k_render_bwd_pixel<<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
                                                                          raster_ws_gsub(grad_sub_ws, nv, S), grad_tex_ws, grad_R, grad_t); }
+        if (two) {
+            cudaEventRecord(ctx->ev_join[2], st);
+            cudaStreamWaitEvent(sd, ctx->ev_join[2], 0);
+        }
         const int img_lo = (int)(v0 / views_per_image), img_hi = (int)((v0 + nv - 1) / views_per_image);
         dim3 tex_grid = pix_grid((long)S * S, img_hi - img_lo + 1);
         {   // enough CTAs to fill the GPU: split an image's views over up to 16 groups when there are few (image, pixel) blocks
@@ -2126,11 +2158,18 @@ int g2s_render_fused_bwd(const g2s_camera* cam, const float* depth, const float*
             if (groups > 16) groups = 16;
             tex_grid.z = (unsigned)(groups < 1 ? 1 : groups);
         }
-        { Launch l_(K_BWD_TEX, st);
-          k_render_bwd_tex<<<tex_grid, PIX_THREADS, 0, st>>>(S, fa, nv, grad_tex_ws, grad_albedo,
+        { Launch l_(K_BWD_TEX, sd);
+          k_render_bwd_tex<<<tex_grid, PIX_THREADS, 0, sd>>>(S, fa, nv, grad_tex_ws, grad_albedo,
                                                                                              grad_normal_ws, grad_light); }
-        launch_raster_bwd(c, depth, (long)S * S, views_per_image, R, t, nullptr, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,
-                          (long)S * S, nullptr, grad_R, grad_t, st);
+        if (two) {
+            cudaEventRecord(ctx->ev_join[3], sd);
+            cudaStreamWaitEvent(st, ctx->ev_join[1], 0);   // the projected vertices
+        } else {
+            launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, st);
+        }
+        launch_raster_gather(c, depth, (long)S * S, views_per_image, R, t, nullptr, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,
+                             (long)S * S, nullptr, grad_R, grad_t, st);
+        if (two) cudaStreamWaitEvent(st, ctx->ev_join[3], 0);   // the texture scratch is free for the next chunk; join
     }
     for (int i0 = 0; i0 < n_images; i0 += 32768) {
         const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;

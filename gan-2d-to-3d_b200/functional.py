@@ -390,7 +390,7 @@ class RenderChainFn(torch.autograd.Function):
         gR = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
         gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
         gL = torch.empty(B, 5, device=dev, dtype=torch.float32)
-        _lib.check(lib.g2s_render_fused_bwd(ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N, vpi, align,
+        _lib.check(lib.g2s_render_fused_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N, vpi, align,
                                             _p(normal), _p(recon_depth), _p(fidx), _p(gi), _p(gd_out), ws_views, _p(ws_sub),
                                             _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR), _p(gt), _p(gL),
                                             _stream()), "g2s_render_fused_bwd")

@@ -163,8 +163,10 @@ int g2s_render_fused_fwd(g2s_context *ctx, const g2s_camera *cam, const float *d
  * grad_tex_ws [ws_views,S,S,4] (per-view texture gradient, packed rgb-; 16-byte aligned; chunked like the forward), grad_normal_ws [n_images,S,S,8] (packed texels: normal xyz,
  * albedo rgb, 2 pad; kept for the backward).
  * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
- * grad_t [n_views,3], grad_light [n_views,5]. */
-int g2s_render_fused_bwd(const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
+ * grad_t [n_views,3], grad_light [n_views,5].
+ * ctx (may be NULL = everything on `stream`): the bandwidth-bound kernels of a chunk run on the context's side stream under the
+ * issue-bound ones, forked from / joined to `stream` with the context's events. */
+int g2s_render_fused_bwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, const float *normal_ws, const float *recon_depth,
                          const int32_t *face_idx, const float *grad_recon_im, const float *grad_recon_depth,
