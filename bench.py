@@ -438,6 +438,44 @@ def run_ours(args):
         except Exception as exc:   # the headline numbers do not depend on these extras
             other = {"error": str(exc)[:200]}
 
+    # SURVEY.md 8(f) row 1 measured: the step WITH the reference's step-3 photometric loss (model.py:265-274) on the bench
+    # shape -- taken inside the render (Renderer.render_chain_loss: resolve epilogue + loss-driven pixel backward) against
+    # the unfused composition render_chain -> PhotometricLoss (three more passes over recon_im / target / recon_depth)
+    loss_step = None
+    if world == 1 and not args.no_single_image:
+        try:
+            gen = torch.Generator().manual_seed(5)
+            target = (torch.rand(B, 3, S, S, generator=gen) * 2 - 1).to(dev)
+            vmask = (torch.rand(B, 1, S, S, generator=gen) > 0.2).float().to(dev)
+            photo = g2s_b200.PhotometricLoss()
+
+            def leaves():
+                ts = [d_in[k].requires_grad_(True) for k in ("depth", "albedo", "view", "light")]
+                for tns in ts:
+                    tns.grad = None
+                return ts
+
+            def step_fused():
+                depth, albedo, view, light = leaves()
+                ren.render_chain_loss(depth, albedo, view, light, target, vmask, views_per_image=P)[0].backward()
+
+            def step_unfused():
+                depth, albedo, view, light = leaves()
+                im_, rd_, _ = ren.render_chain(depth, albedo, view, light, views_per_image=P)
+                photo(im_, target, mask=vmask, **g2s_b200.recon_im_mask(rd_.detach(), MIN_DEPTH, MAX_DEPTH)).backward()
+
+            for fn in (step_fused, step_unfused):
+                for _ in range(2):
+                    fn()
+            reps = max(3, args.steps // 3)
+            ms_fu, ms_un = timed(step_fused, reps) / reps, timed(step_unfused, reps) / reps
+            loss_step = {"workload": "the bench step with the masked photometric loss of model.py:265-274 instead of a fixed "
+                                     "cotangent", "fused": {"value": B / (ms_fu * 1e-3), "unit": UNIT, "ms_per_step": ms_fu},
+                         "unfused": {"value": B / (ms_un * 1e-3), "unit": UNIT, "ms_per_step": ms_un}}
+            del target, vmask
+        except Exception as exc:   # the headline numbers do not depend on this extra
+            loss_step = {"error": str(exc)[:200]}
+
     threads = os.cpu_count() or 1
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -461,7 +499,7 @@ def run_ours(args):
                          "d2h_bytes_per_step": d2h_full * world, "ms_per_step": ms_e2e_full / args.steps,
                          "returns": "the four gradients + recon_im + recon_depth"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "single_image": single, "other_configs": other, "face_sharded": face_sharded}
+            "single_image": single, "other_configs": other, "loss_step": loss_step, "face_sharded": face_sharded}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

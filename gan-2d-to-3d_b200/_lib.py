@@ -22,6 +22,14 @@ class Camera(ctypes.Structure):
 
 _CAMP = ctypes.POINTER(Camera)
 
+
+class PhotoLoss(ctypes.Structure):
+    """g2s_photo_loss (include/g2s_b200.h): the fused masked photometric loss of model.py:265-274."""
+    _fields_ = [("target", ctypes.c_void_p), ("view_mask", ctypes.c_void_p), ("depth_thresh", ctypes.c_float)]
+
+
+_LOSSP = ctypes.POINTER(PhotoLoss)
+
 # name -> (restype, argtypes); must list every symbol include/g2s_b200.h declares
 SIGNATURES = {
     "g2s_version": (_c_int, []),
@@ -49,6 +57,10 @@ SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_fused_bwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
                                       _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g2s_render_fused_loss_fwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp,
+                                           _vp, _vp, _vp, _LOSSP, _vp, _vp, _vp]),
+    "g2s_render_fused_loss_bwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
+                                           _vp, _LOSSP, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_rgb_fwd": (_c_int, [_CAMP, _vp, _vp, _c_long, _c_int, _c_int, _c_int, ctypes.POINTER(_c_float),
                                     _c_int, _vp, _vp, _vp, _vp]),
     "g2s_render_depth_fwd": (_c_int, [_CAMP, _vp, _c_int, _vp, _vp, _vp, _vp]),
@@ -88,7 +100,7 @@ SIGNATURES = {
 }
 
 # g2s_workspace_bytes kinds (include/g2s_b200.h)
-WS_ZBUFFER, WS_RASTER_BWD, WS_TEX_BWD, WS_TEXELS, WS_GRAD_NORMAL, WS_RGB_MAP = range(6)
+WS_ZBUFFER, WS_RASTER_BWD, WS_TEX_BWD, WS_TEXELS, WS_GRAD_NORMAL, WS_RGB_MAP, WS_LOSS = range(7)
 
 _lib = None
 

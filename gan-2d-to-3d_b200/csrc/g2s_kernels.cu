@@ -169,6 +169,13 @@ struct FusedArgs {
     int view0;            // first view of this launch (chunked launches)
     const float* mask_in; // optional [n_images,S,S] canonical mask (NULL = all ones)
     float* mask_out;      // optional [n_views,S,S]: grid_sample(mask, grid, mode='nearest') (renderer.py:263)
+    // fused masked photometric loss (model.py:265-274 + losses.py:39-51), all optional
+    const float* target;  // [n_views,3,S,S] the images the renders are compared with
+    const float* vmask;   // [n_views,S,S] per-view masks or NULL
+    float thresh;         // validity: recon_depth < thresh
+    double* loss_parts;   // forward: [n_views * CTAs per view][2] partial (numerator, mask count)
+    const float* sums3;   // backward: {loss, numerator, denominator} of the forward
+    const float* gloss;   // backward: d(total) / d(loss), a device scalar
 };
 
 // pixel-kernel blocks (threads = output pixels): the z-buffer resolve streams rows (64 x 4); the two backward pixel
@@ -253,7 +260,7 @@ k_pack_albedo(const float* __restrict__ albedo, int HW, float* __restrict__ pack
 // z-buffer resolve: face-index map, flip + 2x2 mean + clamp -> recon_depth, z-buffer reset; when FUSED
 // also inverse warp grid + shaded bilinear sampling -> recon_im.  One thread per output pixel,
 // block = 64 columns x 4 rows, grid = (cols, rows, views).
-template <bool FUSED>
+template <bool FUSED, bool LOSS = false>
 __global__ void __launch_bounds__(PBX * PBY)
 k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restrict__ recon_depth,
           int* __restrict__ face_idx, const FusedArgs fa) {
@@ -268,6 +275,13 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
     // anything waits on them, together with the view's R, t, light: one round trip where there were three (profiles/r01_notes.md).
     ulonglong2 k0 = make_ulonglong2(0ull, 0ull), k1 = k0;
     if (inside) { k0 = __ldcg(r0); k1 = __ldcg(r1); }
+    // LOSS: the target pixel and its mask are requested with the keys; nobody returns before the block sum at the end
+    float tg[3] = {0.f, 0.f, 0.f}, vm = 1.f, l_num = 0.f, l_den = 0.f;
+    if (LOSS && inside) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) tg[c] = __ldcs(&fa.target[((long)b * 3 + c) * S * S + i * S + j]);
+        if (fa.vmask) vm = __ldcs(&fa.vmask[(long)b * S * S + i * S + j]);
+    }
     // R, t, light of the view: warp-uniform loads (one L1 transaction per warp, broadcast), no shared memory and no barrier
     float sview[17];
     if (FUSED) {
@@ -278,7 +292,8 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
 #pragma unroll
         for (int k = 0; k < 5; k++) sview[12 + k] = __ldg(&fa.light[b * 5 + k]);
     }
-    if (!inside) return;
+    if (!LOSS && !inside) return;
+    if (inside) {
     const int pix = i * S + j;
     if (face_idx) {
         int* fo = face_idx + (long)b * is * is;
@@ -311,7 +326,13 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float o = tp.w[0] * tex[0][c] + tp.w[1] * tex[1][c] + tp.w[2] * tex[2][c] + tp.w[3] * tex[3][c];
-            __stcs(&fa.recon_im[((long)b * 3 + c) * S * S + pix], fminf(fmaxf(o, -1.f), 1.f));
+            const float oc = fminf(fmaxf(o, -1.f), 1.f);
+            __stcs(&fa.recon_im[((long)b * 3 + c) * S * S + pix], oc);
+            if (LOSS) l_num += fabsf(oc - tg[c]);
+        }
+        if (LOSS) {      // model.py:268-269: (recon_depth < max_depth + margin) * masks
+            l_den = (rd < fa.thresh ? 1.f : 0.f) * vm;
+            l_num *= l_den;
         }
         if (fa.mask_out) {   // nearest-neighbour warp of the canonical mask with the same grid (sample_pseudo_imgs)
             const float ix = nearbyintf(grid_unnormalize(g[0], S, fa.align)), iy = nearbyintf(grid_unnormalize(g[1], S, fa.align));
@@ -321,7 +342,28 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
             __stcs(&fa.mask_out[(long)b * S * S + pix], m);
         }
     }
+    }
+    if (LOSS) {      // one (numerator, mask count) pair per CTA, summed in a fixed order by k_photo_finish: deterministic
+        __shared__ double sh[2][PBX * PBY / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l_num += __shfl_xor_sync(0xffffffffu, l_num, o);
+            l_den += __shfl_xor_sync(0xffffffffu, l_den, o);
+        }
+        const int lin = threadIdx.y * PBX + threadIdx.x;
+        if ((lin & 31) == 0) { sh[0][lin >> 5] = (double)l_num; sh[1][lin >> 5] = (double)l_den; }
+        __syncthreads();
+        if (lin == 0) {
+            double n = 0.0, d = 0.0;
+#pragma unroll
+            for (int w = 0; w < PBX * PBY / 32; w++) { n += sh[0][w]; d += sh[1][w]; }
+            const long cta = ((long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            fa.loss_parts[2 * cta] = n;
+            fa.loss_parts[2 * cta + 1] = d;
+        }
+    }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // standalone per-pixel operators
@@ -986,7 +1028,10 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
 // recon_depth (g_sub) and accumulates grad_R / grad_t.  grad_tex / g_sub are indexed by the LOCAL view
 // (chunked launches), everything else by the global view fa.view0 + blockIdx.z.
 // 12 CTAs of 128 threads per SM (40 registers): measured best of 1 / 12 / 16 (54-64 / 40 / 32 registers + spills)
-__global__ void __launch_bounds__(BPX * BPY, 12)
+// LOSS: the fused photometric loss's cotangent is formed here (a variant of its own: the extra live values do not fit the 40
+// registers of the plain kernel without spills)
+template <bool LOSS>
+__global__ void __launch_bounds__(BPX * BPY, LOSS ? 10 : 12)
 k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ recon_depth,
                    const float* __restrict__ grad_recon_im, const float* __restrict__ grad_recon_depth,
                    float* __restrict__ g_sub, float* __restrict__ grad_tex, float* __restrict__ grad_R,
@@ -1000,8 +1045,19 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
     float rd = 0.f, G[3] = {0.f, 0.f, 0.f};
     if (inside) {
         rd = recon_depth[(long)b * S * S + pix];
+        if (!LOSS || grad_recon_im) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) G[c] = __ldcs(&grad_recon_im[((long)b * 3 + c) * S * S + pix]);
+            for (int c = 0; c < 3; c++) G[c] = __ldcs(&grad_recon_im[((long)b * 3 + c) * S * S + pix]);
+        }
+    }
+    // fused photometric loss: its cotangent sign(recon_im - target) * mask * g_loss / den is formed here from the re-computed
+    // render instead of travelling through memory (k_photo_bwd's write, autograd's add, this kernel's read)
+    float tg[3] = {0.f, 0.f, 0.f}, lscale = 0.f;
+    if (LOSS && inside) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) tg[c] = __ldcs(&fa.target[((long)b * 3 + c) * S * S + pix]);
+        const float vm = fa.vmask ? __ldcs(&fa.vmask[(long)b * S * S + pix]) : 1.f;
+        lscale = (rd < fa.thresh ? 1.f : 0.f) * vm * (__ldg(fa.gloss) / __ldg(&fa.sums3[2]));
     }
     {
         const int k = threadIdx.y * BPX + threadIdx.x;
@@ -1029,8 +1085,13 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float o = tp.w[0] * tex[0][c] + tp.w[1] * tex[1][c] + tp.w[2] * tex[2][c] + tp.w[3] * tex[3][c];
-            // clamp(-1,1) passes the gradient where -1 <= x <= 1
-            Gc[c] = (o >= -1.f && o <= 1.f) ? G[c] : 0.f;
+            // clamp(-1,1) passes the gradient where -1 <= x <= 1 (so the clamped render equals o wherever it matters)
+            float Gl = G[c];
+            if (LOSS) {
+                const float dlt = o - tg[c];
+                Gl += dlt > 0.f ? lscale : (dlt < 0.f ? -lscale : 0.f);
+            }
+            Gc[c] = (o >= -1.f && o <= 1.f) ? Gl : 0.f;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 gix += ((k & 1) ? 1.f : -1.f) * tp.wy[k] * tex[k][c] * Gc[c];
@@ -1882,11 +1943,12 @@ size_t g2s_workspace_bytes(int kind, int n, int image_size) {
         case G2S_WS_TEXELS: return (size_t)n * 8 * S2 * f;
         case G2S_WS_GRAD_NORMAL: return (size_t)n * 3 * S2 * f;
         case G2S_WS_RGB_MAP: return (size_t)n * 20 * S2 * f;      // colour map [n,2S,2S,4] + quarter gradient [n,S,S,4]
+        case G2S_WS_LOSS: { const dim3 g = pix_grid2(image_size, 1); return (size_t)n * g.x * g.y * 2 * sizeof(double); }
         default: return 0;
     }
 }
 
-int g2s_version(void) { return 200; }
+int g2s_version(void) { return 201; }
 
 const char* g2s_error_string(int code) {
     switch (code) {
@@ -2031,12 +2093,19 @@ int g2s_chunk_views(int image_size) {
     return chunk_views_for(image_size, 1 << 20);
 }
 
-int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
-                         const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
-                         int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
-                         const float* mask_in, float* mask_out, void* stream) {
+namespace {
+// defined in g2s_callers.cuh (same translation unit, included at the end)
+__global__ void __launch_bounds__(256) k_photo_finish(const double* __restrict__ parts, int nparts, int C, float* __restrict__ out);
+}
+
+static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+                          const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
+                          int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
+                          const float* mask_in, float* mask_out, const g2s_photo_loss* loss, void* loss_ws, float* out3,
+                          void* stream) {
     if (!cam || !depth || !albedo || !R || !t || !light || !zbuf || !normal_ws || !recon_im || !recon_depth)
         return G2S_ERR_NULL;
+    if (loss && (!loss->target || !loss_ws || !out3)) return G2S_ERR_NULL;
     const long n_views = (long)n_images * views_per_image;
     if (n_images <= 0 || views_per_image <= 0 || n_views > (1L << 30) || ws_views <= 0 || bad_size(cam->image_size))
         return G2S_ERR_SHAPE;
@@ -2087,8 +2156,13 @@ int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* d
             break;
         }
         FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0, mask_in, mask_out};
+        if (loss) {
+            fa.target = loss->target; fa.vmask = loss->view_mask; fa.thresh = loss->depth_thresh;
+            fa.loss_parts = (double*)loss_ws;
+        }
         { Launch l_(K_RESOLVE_FUSED, ls);
-          k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, ls>>>(c, zb, recon_depth, face_idx, fa); }
+          if (loss) k_resolve<true, true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, ls>>>(c, zb, recon_depth, face_idx, fa);
+          else k_resolve<true><<<pix_grid2(S, nv), dim3(PBX, PBY), 0, ls>>>(c, zb, recon_depth, face_idx, fa); }
     }
     if (nl > 1) {
         for (int k = 1; k < nl; k++) {
@@ -2096,19 +2170,45 @@ int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* d
             cudaStreamWaitEvent(st, ctx->ev_join[k], 0);
         }
     }
+    if (loss && !rc_lane) {      // every CTA of every view wrote its pair: sum them in a fixed order
+        const dim3 g = pix_grid2(S, 1);
+        const long nparts = n_views * g.x * g.y;
+        Launch l_(K_PHOTOMETRIC, st);
+        k_photo_finish<<<1, 256, 0, st>>>((const double*)loss_ws, (int)nparts, 3, out3);
+    }
     return rc_lane ? rc_lane : launch_status();
 }
 
-int g2s_render_fused_bwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
-                         const float* light, int n_images, int views_per_image, int align_corners,
-                         const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
-                         const float* grad_recon_im, const float* grad_recon_depth, int ws_views, float* grad_sub_ws,
-                         float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R,
-                         float* grad_t, float* grad_light, void* stream) {
-    if (!cam || !depth || !albedo || !R || !t || !light || !normal_ws || !recon_depth || !face_idx || !grad_recon_im ||
+int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+                         const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
+                         int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
+                         const float* mask_in, float* mask_out, void* stream) {
+    return fused_fwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, zbuf, ws_views, normal_ws,
+                          recon_im, recon_depth, face_idx, mask_in, mask_out, nullptr, nullptr, nullptr, stream);
+}
+
+int g2s_render_fused_loss_fwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R,
+                              const float* t, const float* light, int n_images, int views_per_image, int align_corners,
+                              void* zbuf, int ws_views, float* normal_ws, float* recon_im, float* recon_depth,
+                              int32_t* face_idx, const g2s_photo_loss* loss, void* loss_ws, float* out3, void* stream) {
+    if (!loss) return G2S_ERR_NULL;
+    return fused_fwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, zbuf, ws_views, normal_ws,
+                          recon_im, recon_depth, face_idx, nullptr, nullptr, loss, loss_ws, out3, stream);
+}
+
+static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+                          const float* light, int n_images, int views_per_image, int align_corners,
+                          const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
+                          const float* grad_recon_im, const float* grad_recon_depth, const g2s_photo_loss* loss,
+                          const float* sums3, const float* grad_loss, int ws_views, float* grad_sub_ws,
+                          float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R,
+                          float* grad_t, float* grad_light, void* stream) {
+    if (!cam || !depth || !albedo || !R || !t || !light || !normal_ws || !recon_depth || !face_idx ||
         !grad_sub_ws || !grad_tex_ws || !grad_normal_ws || !grad_depth || !grad_albedo || !grad_R || !grad_t ||
         !grad_light)
         return G2S_ERR_NULL;
+    if (!grad_recon_im && !loss) return G2S_ERR_NULL;
+    if (loss && (!loss->target || !sums3 || !grad_loss)) return G2S_ERR_NULL;
     const long n_views = (long)n_images * views_per_image;
     if (n_images <= 0 || views_per_image <= 0 || n_views > (1L << 30) || ws_views <= 0 || bad_size(cam->image_size))
         return G2S_ERR_SHAPE;
@@ -2130,11 +2230,19 @@ int g2s_render_fused_bwd(g2s_context* ctx, const g2s_camera* cam, const float* d
     //   caller:  k_render_bwd_pixel ............ k_raster_bwd_px  k_vertex_bwd
     //   side:    k_project_verts     (wait pixel) k_render_bwd_tex
     // Fork / join with the context's events (capturable in a CUDA graph); without a context everything is serial.
-    const bool two = ctx != nullptr && !ctx->no_pipeline;
+    bool two = ctx != nullptr && !ctx->no_pipeline && !g_prof_on;     // per-kernel timing wants the kernels alone
+    if (two) {      // the context's streams belong to one device
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev != ctx->device) two = false;
+    }
     cudaStream_t sd = two ? ctx->aux[1] : st;
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
         FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
+        if (loss) {
+            fa.target = loss->target; fa.vmask = loss->view_mask; fa.thresh = loss->depth_thresh;
+            fa.sums3 = sums3; fa.gloss = grad_loss;
+        }
         if (two) {
             cudaEventRecord(ctx->ev_fork, st);             // after the memsets / the previous chunk's gather
             cudaStreamWaitEvent(sd, ctx->ev_fork, 0);
@@ -2142,7 +2250,9 @@ int g2s_render_fused_bwd(g2s_context* ctx, const g2s_camera* cam, const float* d
             cudaEventRecord(ctx->ev_join[1], sd);
         }
         { Launch l_(K_BWD_PIXEL, st);
-          k_render_bwd_pixel<<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
+          if (loss) k_render_bwd_pixel<true><<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
+                                                                         raster_ws_gsub(grad_sub_ws, nv, S), grad_tex_ws, grad_R, grad_t);
+          else k_render_bwd_pixel<false><<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
                                                                          raster_ws_gsub(grad_sub_ws, nv, S), grad_tex_ws, grad_R, grad_t); }
         if (two) {
             cudaEventRecord(ctx->ev_join[2], st);
@@ -2179,6 +2289,31 @@ int g2s_render_fused_bwd(g2s_context* ctx, const g2s_camera* cam, const float* d
                                                                         grad_depth + (long)i0 * S * S, 1);
     }
     return launch_status();
+}
+
+int g2s_render_fused_bwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
+                         const float* light, int n_images, int views_per_image, int align_corners,
+                         const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
+                         const float* grad_recon_im, const float* grad_recon_depth, int ws_views, float* grad_sub_ws,
+                         float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R,
+                         float* grad_t, float* grad_light, void* stream) {
+    if (!grad_recon_im) return G2S_ERR_NULL;
+    return fused_bwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, normal_ws, recon_depth,
+                          face_idx, grad_recon_im, grad_recon_depth, nullptr, nullptr, nullptr, ws_views, grad_sub_ws, grad_tex_ws,
+                          grad_normal_ws, grad_depth, grad_albedo, grad_R, grad_t, grad_light, stream);
+}
+
+int g2s_render_fused_loss_bwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R,
+                              const float* t, const float* light, int n_images, int views_per_image, int align_corners,
+                              const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
+                              const float* grad_recon_im, const float* grad_recon_depth, const g2s_photo_loss* loss,
+                              const float* sums3, const float* grad_loss, int ws_views, float* grad_sub_ws, float* grad_tex_ws,
+                              float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R, float* grad_t,
+                              float* grad_light, void* stream) {
+    if (!loss) return G2S_ERR_NULL;
+    return fused_bwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, normal_ws, recon_depth,
+                          face_idx, grad_recon_im, grad_recon_depth, loss, sums3, grad_loss, ws_views, grad_sub_ws, grad_tex_ws,
+                          grad_normal_ws, grad_depth, grad_albedo, grad_R, grad_t, grad_light, stream);
 }
 
 int g2s_view_fwd(const float* view, int view_width, int B, float* R, float* t, void* stream) {

@@ -399,6 +399,90 @@ class RenderChainFn(torch.autograd.Function):
         return g_depth, g_albedo, gR, gt, gL, None, None, None, None, None
 
 
+class RenderChainLossFn(torch.autograd.Function):
+    """RenderChainFn + the step-3 photometric loss of the reference taken INSIDE the render (model.py:243-274):
+    loss = PhotometricLoss(recon_im, target, mask=(recon_depth < depth_thresh) * view_mask) (losses.py:39-51).  The
+    forward's resolve kernel accumulates the masked sums, the backward's pixel stage forms the loss's cotangent, so the loss
+    costs no pass of its own over recon_im / target / recon_depth and no cotangent image is written or read.
+    Returns (recon_im, recon_depth, face_idx, loss); cotangents on recon_im (e.g. from a perceptual loss) and recon_depth
+    are added to the loss's."""
+
+    @staticmethod
+    def forward(ctx, depth, albedo, R, t, light, target, view_mask, renderer, views_per_image, align_corners, depth_thresh):
+        _require_cuda(depth, albedo, R, t, light, target, view_mask)
+        lib = _lib.load()
+        N, S, _ = depth.shape
+        B = N * views_per_image
+        if S != renderer.image_size or depth.shape[2] != S or tuple(albedo.shape) != (N, 3, S, S):
+            raise RuntimeError("render_chain_loss: depth must be [N,S,S] and albedo [N,3,S,S] with S = image_size")
+        if R.shape[0] != B or light.shape != (B, 5):
+            raise RuntimeError("render_chain_loss: R/t/light must have n_images * views_per_image rows")
+        if tuple(target.shape) != (B, 3, S, S):
+            raise RuntimeError("render_chain_loss: target must be [n_views,3,S,S]")
+        if view_mask is not None and view_mask.numel() != B * S * S:
+            raise RuntimeError("render_chain_loss: view_mask must be [n_views,1,S,S]")
+        d, a = _f32c(depth), _f32c(albedo)
+        Rc, tc = _Rt(R, t, B)
+        L = _f32c(light)
+        tg = _f32c(target.detach())
+        vm = _f32c(view_mask.detach().reshape(B, S, S)) if view_mask is not None else None
+        cam = renderer._camera(depth_pass=True)
+        dev = d.device
+        ws_views = min(B, FWD_LANES * lib.g2s_chunk_views(S))
+        zbuf = renderer._zbuf.get(ws_views, S, cam.far_z, dev)
+        normal = _ws(_lib.WS_TEXELS, N, S, dev)
+        loss_ws = _ws(_lib.WS_LOSS, B, S, dev)
+        recon_im = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
+        recon_depth = torch.empty(B, S, S, device=dev, dtype=torch.float32)
+        fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)
+        out3 = torch.empty(3, device=dev, dtype=torch.float32)
+        la = _lib.PhotoLoss(_p(tg), _p(vm), float(depth_thresh))
+        _checked(renderer, lib.g2s_render_fused_loss_fwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a),
+                                                         _p(Rc), _p(tc), _p(L), N, views_per_image,
+                                                         int(bool(align_corners)), _p(zbuf), ws_views, _p(normal),
+                                                         _p(recon_im), _p(recon_depth), _p(fidx), ctypes.byref(la),
+                                                         _p(loss_ws), _p(out3), _stream()),
+                 "g2s_render_fused_loss_fwd")
+        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3)
+        ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape, float(depth_thresh))
+        ctx.mark_non_differentiable(fidx)
+        ctx.set_materialize_grads(False)
+        return recon_im, recon_depth, fidx, out3[0]
+
+    @staticmethod
+    def backward(ctx, g_im, g_depth_out, _g_fidx, g_loss):
+        lib = _lib.load()
+        d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3 = ctx.saved_tensors
+        renderer, vpi, align, Rshape, tshape, thresh = ctx.meta
+        N, S, _ = d.shape
+        B = N * vpi
+        dev = d.device
+        cam = renderer._camera(depth_pass=True)
+        if g_im is None and g_depth_out is None and g_loss is None:
+            return (None,) * 11
+        gi = _f32c(g_im) if g_im is not None else None
+        gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
+        gl = _f32c(g_loss).reshape(1) if g_loss is not None else torch.zeros(1, device=dev)
+        ws_views = min(B, lib.g2s_chunk_views_bwd(S))
+        ws_sub = _ws(_lib.WS_RASTER_BWD, ws_views, S, dev)
+        ws_tex = _ws(_lib.WS_TEX_BWD, ws_views, S, dev)
+        ws_nrm = _ws(_lib.WS_GRAD_NORMAL, N, S, dev)
+        g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)
+        g_albedo = torch.empty(N, 3, S, S, device=dev, dtype=torch.float32)
+        gR = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
+        gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
+        gL = torch.empty(B, 5, device=dev, dtype=torch.float32)
+        la = _lib.PhotoLoss(_p(tg), _p(vm), thresh)
+        _lib.check(lib.g2s_render_fused_loss_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc),
+                                                 _p(tc), _p(L), N, vpi, align, _p(normal), _p(recon_depth), _p(fidx),
+                                                 _p(gi), _p(gd_out), ctypes.byref(la), _p(out3), _p(gl), ws_views,
+                                                 _p(ws_sub), _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR),
+                                                 _p(gt), _p(gL), _stream()), "g2s_render_fused_loss_bwd")
+        gR = gR.sum_to_size(Rshape)
+        gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
+        return g_depth, g_albedo, gR, gt, gL, None, None, None, None, None, None
+
+
 # ----------------------------------------------------------------------------------------------------------
 class RenderRgbFn(torch.autograd.Function):
     """nr.Renderer.render_rgb(vertices, get_face_idx, get_textures_from_im(im, 2)) (+ clamp) as renderer.py:194-196,

@@ -174,6 +174,25 @@ class Renderer:
         return Fn.RenderChainFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, self, P,
                                       self.align_corners)
 
+    def render_chain_loss(self, depth, albedo, view, light, target, masks=None, depth_thresh=None, views_per_image=None):
+        """render_chain with the step-3 photometric loss of model.py:265-274 taken inside the render:
+        loss = PhotometricLoss(recon_im, target, mask=(recon_depth < depth_thresh).unsqueeze(1) * masks); depth_thresh
+        defaults to max_depth + (max_depth - min_depth) / 2 (model.py:264-268).  target [N*P,3,S,S], masks [N*P,1,S,S] or
+        None.  Returns (loss, recon_im, recon_depth, face_idx): further losses on recon_im / recon_depth (the perceptual
+        loss of model.py:275) back-propagate through the same backward call."""
+        N = depth.shape[0]
+        B = view.shape[0]
+        P = views_per_image if views_per_image is not None else B // N
+        if N * P != B:
+            raise RuntimeError("render_chain_loss: view must have n_images * views_per_image rows")
+        if depth_thresh is None:
+            depth_thresh = self.max_depth + (self.max_depth - self.min_depth) / 2
+        self.set_transform_matrices(view)
+        light5 = Fn.LightFn.apply(light)
+        im, rd, fidx, loss = Fn.RenderChainLossFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, target, masks, self,
+                                                        P, self.align_corners, depth_thresh)
+        return loss, im, rd, fidx
+
     def render_pseudo_views(self, depth, albedo, view, light_a, light_b, light_d, mask=None, views_per_image=None):
         """Forward-only twin of render_chain used by sample_pseudo_imgs (model.py:291-328): shade the canonical
         albedo with per-view lighting `shading = a + b * max(0, n.d)` (for the random relighting of model.py:298-309

@@ -77,9 +77,10 @@ void g2s_context_destroy(g2s_context *ctx);
  *   G2S_WS_TEX_BWD     per-view texture gradient of the fused backward: [n,S,S,4] floats;
  *   G2S_WS_TEXELS      packed texel map of the fused render for n IMAGES: [n,S,S,8] floats;
  *   G2S_WS_GRAD_NORMAL normal-map gradient of the fused backward for n IMAGES: [n,S,S,3] floats;
- *   G2S_WS_RGB_MAP     rgb backward for n views: supersampled colour map [n,2S,2S,4] + quarter gradient [n,S,S,4] floats. */
+ *   G2S_WS_RGB_MAP     rgb backward for n views: supersampled colour map [n,2S,2S,4] + quarter gradient [n,S,S,4] floats.
+ *   G2S_WS_LOSS        partial sums of the fused photometric loss for n views (g2s_render_fused_loss_fwd). */
 enum { G2S_WS_ZBUFFER = 0, G2S_WS_RASTER_BWD = 1, G2S_WS_TEX_BWD = 2, G2S_WS_TEXELS = 3, G2S_WS_GRAD_NORMAL = 4,
-       G2S_WS_RGB_MAP = 5 };
+       G2S_WS_RGB_MAP = 5, G2S_WS_LOSS = 6 };
 size_t g2s_workspace_bytes(int kind, int n, int image_size);
 size_t g2s_zbuffer_bytes(int n_views, int image_size);
 int g2s_zbuffer_init(void *zbuf, int n_views, int image_size, float far_z, void *stream);
@@ -172,6 +173,33 @@ int g2s_render_fused_bwd(g2s_context *ctx, const g2s_camera *cam, const float *d
                          const int32_t *face_idx, const float *grad_recon_im, const float *grad_recon_depth,
                          int ws_views, float *grad_sub_ws, float *grad_tex_ws, float *grad_normal_ws, float *grad_depth,
                          float *grad_albedo, float *grad_R, float *grad_t, float *grad_light, void *stream);
+
+/* ---- fused render + masked photometric loss: model.py:243-274 as one pass ----------------------------------------
+ * The step-3 loss of the reference, loss_l1_im = PhotometricLoss(recon_im, projected_samples, mask = (recon_depth <
+ * max_depth + margin) * masks) (model.py:265-274, losses.py:39-51 without conf_sigma), taken inside the render:
+ * the forward's z-buffer resolve also accumulates sum(|recon_im - target| * m) and sum(m) -- per-CTA pairs in loss_ws
+ * (G2S_WS_LOSS for n_views), summed in a fixed order -- and writes out3 = {loss, numerator, denominator} (device); the
+ * backward forms the loss's cotangent sign(recon_im - target) * m * grad_loss / denominator inside its pixel stage and ADDS it
+ * to grad_recon_im (may be NULL: e.g. no perceptual loss on the render), so neither the loss's own passes over recon_im /
+ * target / recon_depth nor the cotangent image exist.  recon_im, recon_depth, face_idx are written as by
+ * g2s_render_fused_fwd.  grad_loss is a DEVICE scalar; sums3 = the forward's out3. */
+typedef struct {
+    const float *target;     /* [n_views,3,S,S] */
+    const float *view_mask;  /* [n_views,S,S] or NULL (all ones) */
+    float depth_thresh;      /* a pixel counts when recon_depth < depth_thresh */
+} g2s_photo_loss;
+int g2s_render_fused_loss_fwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo,
+                              const float *R, const float *t, const float *light, int n_images, int views_per_image,
+                              int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
+                              float *recon_depth, int32_t *face_idx, const g2s_photo_loss *loss, void *loss_ws,
+                              float *out3, void *stream);
+int g2s_render_fused_loss_bwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo,
+                              const float *R, const float *t, const float *light, int n_images, int views_per_image,
+                              int align_corners, const float *normal_ws, const float *recon_depth,
+                              const int32_t *face_idx, const float *grad_recon_im, const float *grad_recon_depth,
+                              const g2s_photo_loss *loss, const float *sums3, const float *grad_loss, int ws_views,
+                              float *grad_sub_ws, float *grad_tex_ws, float *grad_normal_ws, float *grad_depth,
+                              float *grad_albedo, float *grad_R, float *grad_t, float *grad_light, void *stream);
 
 /* ---- mesh-texture render: nr.Renderer.render_rgb as renderer.py:196,230,248,272,275 call it ------
  * vertices3d [n_views,S*S,3] (already rotated/translated 3-D grid), im [*,C,S,S] per-vertex colours

@@ -212,3 +212,108 @@ def test_mesh_export_matches_the_rasterised_mesh():
         assert meshes[b]["faces"].shape == (2 * (S - 1) ** 2, 3) and meshes[b]["colors"].shape == (S * S, 3)
     plain = me.depth_to_mesh(ren, case["depth"].cuda())
     assert np.array_equal(plain[0]["vertices"], orc.depth_to_3d_grid(case["depth"]).reshape(-1, 3).numpy())
+
+
+# ---- fused render + masked photometric loss (model.py:243-274 in one pass) ------------------------------------------
+@pytest.mark.parametrize("S,N,P,use_mask,extra_cot", [(32, 1, 4, True, True), (64, 2, 3, True, False), (21, 1, 2, False, True),
+                                                      (128, 1, 8, True, True)])
+def test_render_chain_loss_vs_oracle(S, N, P, use_mask, extra_cot):
+    """loss = PhotometricLoss(recon_im, target, mask=(recon_depth < max_depth + margin) * masks) taken inside the render
+    (k_resolve epilogue + k_render_bwd_pixel<LOSS>) against the oracle's render chain + the oracle's loss: value and all
+    five gradients, with and without a further cotangent on recon_im / recon_depth (the perceptual loss's path); and
+    against the unfused CUDA composition render_chain -> PhotometricLoss."""
+    import g2s_b200
+    from g2s_b200 import synthetic
+    from oracle import callers_oracle as co
+    case = synthetic.make_case(S, P, seed=500 + S + P, n_images=N)
+    B = N * P
+    gen = torch.Generator().manual_seed(77 + S)
+    target = torch.rand(B, 3, S, S, generator=gen) * 2 - 1
+    masks = (torch.rand(B, 1, S, S, generator=gen) > 0.2).float() if use_mask else None
+    cot_im = torch.randn(B, 3, S, S, generator=gen) / (3 * S * S * B)
+    cot_d = torch.randn(B, S, S, generator=gen) / (S * S * B)
+    thresh = MAX_DEPTH + (MAX_DEPTH - MIN_DEPTH) / 2
+
+    # oracle: per image (its render chain takes one depth map), injected R, t so that both sides see the same views
+    orc = oracle_renderer(S)
+    R_all = ro.get_transform_matrices(case["view"])[0]
+    d_o = case["depth"].clone().requires_grad_(True)
+    a_o = case["albedo"].clone().requires_grad_(True)
+    R_o = R_all.clone().requires_grad_(True)
+    t_o = case["view"][:, 3:].reshape(B, 1, 3).clone().requires_grad_(True)
+    l_o = case["light"].clone().requires_grad_(True)
+    ims, rds = [], []
+    for i in range(N):
+        sl = slice(i * P, (i + 1) * P)
+        normal = orc.get_normal_from_depth(d_o[i:i + 1])
+        la, lb, ld = ro.get_lighting_directions(l_o[sl])
+        _, tex = ro.get_shading(normal, la, lb, ld, a_o[i:i + 1])
+        orc.rot_mat, orc.trans_xyz = R_o[sl], t_o[sl]
+        rd = orc.warp_canon_depth(d_o[i:i + 1].expand(P, S, S))
+        grid = orc.get_inv_warped_2d_grid(rd)
+        ims.append(F.grid_sample(tex, grid, mode="bilinear", align_corners=False).clamp(min=-1, max=1))
+        rds.append(rd)
+    im_o, rd_o = torch.cat(ims, 0), torch.cat(rds, 0)
+    loss_o = co.photometric_loss(im_o, target, co.recon_im_mask(rd_o, MIN_DEPTH, MAX_DEPTH, masks))
+    total_o = loss_o * 1.7
+    if extra_cot:
+        total_o = total_o + (im_o * cot_im).sum() + (rd_o * cot_d).sum()
+    total_o.backward()
+
+    ren = g2s_b200.Renderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH, device="cuda")
+    d = case["depth"].cuda().requires_grad_(True)
+    a = case["albedo"].cuda().requires_grad_(True)
+    R = R_all.cuda().requires_grad_(True)
+    t = t_o.detach().cuda().requires_grad_(True)
+    light5 = g2s_b200.functional.LightFn.apply(case["light"].cuda()).detach().requires_grad_(True)
+    tg, mk = target.cuda(), masks.cuda() if use_mask else None
+    im, rd, fidx, loss = g2s_b200.functional.RenderChainLossFn.apply(d, a, R, t, light5, tg, mk, ren, P, False, thresh)
+    assert torch.equal(rd.detach().cpu(), rd_o.detach())
+    assert rel_err(im.detach().cpu(), im_o.detach()) < TOL
+    assert rel_err(loss.detach().cpu(), loss_o.detach()) < TOL
+    total = loss * 1.7
+    if extra_cot:
+        total = total + (im * cot_im.cuda()).sum() + (rd * cot_d.cuda()).sum()
+    total.backward()
+    errs = dict(gd=rel_err(d.grad.cpu(), d_o.grad), ga=rel_err(a.grad.cpu(), a_o.grad), gR=rel_err(R.grad.cpu(), R_o.grad),
+                gt=rel_err(t.grad.cpu(), t_o.grad))
+    log_stats("render_chain_loss", S=S, N=N, P=P, loss=rel_err(loss.detach().cpu(), loss_o.detach()), **errs)
+    assert max(errs.values()) < TOL, errs
+    # light: compare through the raw light (LightFn's chain is tested elsewhere)
+    lraw = case["light"].cuda().requires_grad_(True)
+    g2s_b200.functional.LightFn.apply(lraw).backward(light5.grad)
+    assert rel_err(lraw.grad.cpu(), l_o.grad) < TOL
+
+    # the unfused CUDA composition gives the same loss and gradients
+    d2 = case["depth"].cuda().requires_grad_(True)
+    a2 = case["albedo"].cuda().requires_grad_(True)
+    im2, rd2, _ = g2s_b200.functional.RenderChainFn.apply(d2, a2, R.detach(), t.detach(), light5.detach(), ren, P, False)
+    assert torch.equal(im2, im.detach()) and torch.equal(rd2, rd.detach())
+    kw = g2s_b200.recon_im_mask(rd2.detach(), MIN_DEPTH, MAX_DEPTH)
+    loss2 = g2s_b200.PhotometricLoss()(im2, tg, mask=mk, **kw)
+    assert rel_err(loss2.detach(), loss.detach()) < 1e-6
+    tot2 = loss2 * 1.7
+    if extra_cot:
+        tot2 = tot2 + (im2 * cot_im.cuda()).sum() + (rd2 * cot_d.cuda()).sum()
+    tot2.backward()
+    assert rel_err(d2.grad, d.grad) < 2e-6 and rel_err(a2.grad, a.grad) < 2e-6
+
+
+def test_render_chain_loss_api_and_errors():
+    import g2s_b200
+    from g2s_b200 import synthetic
+    S, P = 32, 4
+    case = {k: v.cuda() for k, v in synthetic.make_case(S, P, seed=3).items()}
+    ren = g2s_b200.Renderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH, device="cuda")
+    target = torch.zeros(P, 3, S, S, device="cuda")
+    d = case["depth"].clone().requires_grad_(True)
+    loss, im, rd, fidx = ren.render_chain_loss(d, case["albedo"], case["view"], case["light"], target, views_per_image=P)
+    # against the plain mean over the valid pixels of |recon_im - 0|
+    m = (rd < MAX_DEPTH + (MAX_DEPTH - MIN_DEPTH) / 2).float().unsqueeze(1).expand_as(im)
+    assert abs(loss.item() - ((im.abs() * m).sum() / m.sum()).item()) < 1e-6
+    loss.backward()
+    assert d.grad is not None and torch.isfinite(d.grad).all() and d.grad.abs().sum() > 0
+    with pytest.raises(RuntimeError):
+        ren.render_chain_loss(d, case["albedo"], case["view"], case["light"], target[:, :2], views_per_image=P)
+    lib = g2s_b200._lib.load()
+    assert lib.g2s_workspace_bytes(g2s_b200._lib.WS_LOSS, P, S) == P * 1 * (S // 4) * 16
