@@ -83,6 +83,7 @@ struct Launch {
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? G2S_OK : G2S_ERR_LAUNCH; }
 
 constexpr int MAX_LANES = 4;
+constexpr int LOSS_STAGE_BLOCKS = 512;   // first-stage blocks of the fused loss's fixed-order sum
 
 // Sum the per-thread grad_R (9) | grad_t (3) contributions over the block and atomically add the totals to the view's
 // grad_R / grad_t.  All threads must call.
@@ -260,8 +261,9 @@ k_pack_albedo(const float* __restrict__ albedo, int HW, float* __restrict__ pack
 // z-buffer resolve: face-index map, flip + 2x2 mean + clamp -> recon_depth, z-buffer reset; when FUSED
 // also inverse warp grid + shaded bilinear sampling -> recon_im.  One thread per output pixel,
 // block = 64 columns x 4 rows, grid = (cols, rows, views).
+// (LOSS: 5 CTAs/SM = 48 registers like the plain kernel; left alone the compiler takes 61-72 and the kernel 1.98 ms instead of 1.62)
 template <bool FUSED, bool LOSS = false>
-__global__ void __launch_bounds__(PBX * PBY)
+__global__ void __launch_bounds__(PBX * PBY, LOSS ? 5 : 0)
 k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restrict__ recon_depth,
           int* __restrict__ face_idx, const FusedArgs fa) {
     const int S = cam.S, is = 2 * S, bl = blockIdx.z, b = fa.view0 + bl;
@@ -1943,7 +1945,7 @@ size_t g2s_workspace_bytes(int kind, int n, int image_size) {
         case G2S_WS_TEXELS: return (size_t)n * 8 * S2 * f;
         case G2S_WS_GRAD_NORMAL: return (size_t)n * 3 * S2 * f;
         case G2S_WS_RGB_MAP: return (size_t)n * 20 * S2 * f;      // colour map [n,2S,2S,4] + quarter gradient [n,S,S,4]
-        case G2S_WS_LOSS: { const dim3 g = pix_grid2(image_size, 1); return (size_t)n * g.x * g.y * 2 * sizeof(double); }
+        case G2S_WS_LOSS: { const dim3 g = pix_grid2(image_size, 1); return ((size_t)n * g.x * g.y + LOSS_STAGE_BLOCKS) * 2 * sizeof(double); }
         default: return 0;
     }
 }
@@ -2096,6 +2098,24 @@ int g2s_chunk_views(int image_size) {
 namespace {
 // defined in g2s_callers.cuh (same translation unit, included at the end)
 __global__ void __launch_bounds__(256) k_photo_finish(const double* __restrict__ parts, int nparts, int C, float* __restrict__ out);
+
+// first stage of the fixed-order sum of the per-CTA (numerator, mask count) pairs: block k sums pairs [k * per, (k + 1) * per)
+__global__ void __launch_bounds__(256) k_loss_stage(const double2* __restrict__ parts, long nparts, long per, double2* __restrict__ out) {
+    __shared__ double sh[2][8];
+    const long lo = (long)blockIdx.x * per, hi = lo + per < nparts ? lo + per : nparts;
+    double n = 0.0, d = 0.0;
+    for (long p = lo + threadIdx.x; p < hi; p += 256) { const double2 v = parts[p]; n += v.x; d += v.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); d += __shfl_xor_sync(0xffffffffu, d, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = n; sh[1][threadIdx.x >> 5] = d; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        n = d = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { n += sh[0][w]; d += sh[1][w]; }
+        out[blockIdx.x] = make_double2(n, d);
+    }
+}
 }
 
 static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
@@ -2173,8 +2193,12 @@ static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
     if (loss && !rc_lane) {      // every CTA of every view wrote its pair: sum them in a fixed order
         const dim3 g = pix_grid2(S, 1);
         const long nparts = n_views * g.x * g.y;
+        double2* stage = (double2*)loss_ws + nparts;       // LOSS_STAGE_BLOCKS pairs behind the per-CTA pairs
+        const long per = (nparts + LOSS_STAGE_BLOCKS - 1) / LOSS_STAGE_BLOCKS;
+        const int nb = (int)((nparts + per - 1) / per);
         Launch l_(K_PHOTOMETRIC, st);
-        k_photo_finish<<<1, 256, 0, st>>>((const double*)loss_ws, (int)nparts, 3, out3);
+        k_loss_stage<<<nb, 256, 0, st>>>((const double2*)loss_ws, nparts, per, stage);
+        k_photo_finish<<<1, 256, 0, st>>>((const double*)stage, nb, 3, out3);
     }
     return rc_lane ? rc_lane : launch_status();
 }
@@ -2230,7 +2254,10 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
     //   caller:  k_render_bwd_pixel ............ k_raster_bwd_px  k_vertex_bwd
     //   side:    k_project_verts     (wait pixel) k_render_bwd_tex
     // Fork / join with the context's events (capturable in a CUDA graph); without a context everything is serial.
-    bool two = ctx != nullptr && !ctx->no_pipeline && !g_prof_on;     // per-kernel timing wants the kernels alone
+    // (not for small launches: the four cross-stream hand-offs cost more than the overlap gains below ~2 M pixels per chunk --
+    // the single-image step went from 0.26 to 0.49 ms with them)
+    bool two = ctx != nullptr && !ctx->no_pipeline && !g_prof_on &&      // per-kernel timing wants the kernels alone
+               (n_views < ws_views ? n_views : ws_views) * (long)cam->image_size * cam->image_size >= (1L << 21);
     if (two) {      // the context's streams belong to one device
         int dev = -1;
         if (cudaGetDevice(&dev) != cudaSuccess || dev != ctx->device) two = false;

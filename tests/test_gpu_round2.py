@@ -316,4 +316,4 @@ def test_render_chain_loss_api_and_errors():
     with pytest.raises(RuntimeError):
         ren.render_chain_loss(d, case["albedo"], case["view"], case["light"], target[:, :2], views_per_image=P)
     lib = g2s_b200._lib.load()
-    assert lib.g2s_workspace_bytes(g2s_b200._lib.WS_LOSS, P, S) == P * 1 * (S // 4) * 16
+    assert lib.g2s_workspace_bytes(g2s_b200._lib.WS_LOSS, P, S) == (P * 1 * (S // 4) + 512) * 16
