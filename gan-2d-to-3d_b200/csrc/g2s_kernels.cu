@@ -177,7 +177,22 @@ struct FusedArgs {
     double* loss_parts;   // forward: [n_views * CTAs per view][2] partial (numerator, mask count)
     const float* sums3;   // backward: {loss, numerator, denominator} of the forward
     const float* gloss;   // backward: d(total) / d(loss), a device scalar
+    unsigned vpi_magic;   // ceil(2^32 / vpi) when view / vpi == umulhi(view, magic) for every view of the call, else 0
 };
+
+// image of view b = b / views_per_image as a multiply-high by ceil(2^32 / vpi) (host: vpi_magic(); 0 = divide)
+__device__ __forceinline__ int view_image(int b, int vpi, unsigned magic) {
+    return magic ? (int)__umulhi((unsigned)b, magic) : b / vpi;
+}
+
+// host: the multiply-high constant of view_image() for a call of n_views views (0 = the kernel divides)
+inline unsigned vpi_magic(int vpi, long n_views) {
+    if (vpi < 2) return 0u;
+    const unsigned long long m = ((1ull << 32) + (unsigned long long)vpi - 1) / (unsigned long long)vpi;
+    const unsigned long long e = m * (unsigned long long)vpi - (1ull << 32);      // < vpi
+    // umulhi(n, m) == n / vpi for every n with n * e < 2^32
+    return (unsigned long long)n_views * (e + 1) < (1ull << 32) && m < (1ull << 32) ? (unsigned)m : 0u;
+}
 
 // pixel-kernel blocks (threads = output pixels): the z-buffer resolve streams rows (64 x 4); the two backward pixel
 // kernels gather vertices / texels around a 2-D patch and run faster on square blocks (measured, profiles/r01_notes.md)
@@ -277,12 +292,14 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
     // anything waits on them, together with the view's R, t, light: one round trip where there were three (profiles/r01_notes.md).
     ulonglong2 k0 = make_ulonglong2(0ull, 0ull), k1 = k0;
     if (inside) { k0 = __ldcg(r0); k1 = __ldcg(r1); }
-    // LOSS: the target pixel and its mask are requested with the keys; nobody returns before the block sum at the end
-    float tg[3] = {0.f, 0.f, 0.f}, vm = 1.f, l_num = 0.f, l_den = 0.f;
+    // LOSS: the target pixel and its mask are only PREFETCHED here (to L2) and loaded where they are used -- four more live
+    // registers across the whole body spill at the 48 this variant is held to; nobody returns before the block sum at the end
+    float l_num = 0.f, l_den = 0.f;
     if (LOSS && inside) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) tg[c] = __ldcs(&fa.target[((long)b * 3 + c) * S * S + i * S + j]);
-        if (fa.vmask) vm = __ldcs(&fa.vmask[(long)b * S * S + i * S + j]);
+        for (int c = 0; c < 3; c++)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&fa.target[((long)b * 3 + c) * S * S + i * S + j]));
+        if (fa.vmask) asm volatile("prefetch.global.L2 [%0];" ::"l"(&fa.vmask[(long)b * S * S + i * S + j]));
     }
     // R, t, light of the view: warp-uniform loads (one L1 transaction per warp, broadcast), no shared memory and no barrier
     float sview[17];
@@ -317,7 +334,8 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
         __stcg(r1, make_ulonglong2(empty, empty));
     }
     if (FUSED) {
-        const int img = b / fa.vpi;
+        // (the LOSS variant sits at its register cap: the multiply-high form spills there, the division does not)
+        const int img = LOSS ? b / fa.vpi : view_image(b, fa.vpi, fa.vpi_magic);
         float ray[3], q[3], v[3], g[2];
         pixel_ray(cam, j, i, ray);
         inv_warp_point(cam, sview, sview + 9, ray, rd, q, v);
@@ -330,9 +348,10 @@ k_resolve(const Cam cam, unsigned long long* __restrict__ zbuf, float* __restric
             const float o = tp.w[0] * tex[0][c] + tp.w[1] * tex[1][c] + tp.w[2] * tex[2][c] + tp.w[3] * tex[3][c];
             const float oc = fminf(fmaxf(o, -1.f), 1.f);
             __stcs(&fa.recon_im[((long)b * 3 + c) * S * S + pix], oc);
-            if (LOSS) l_num += fabsf(oc - tg[c]);
+            if (LOSS) l_num += fabsf(oc - __ldcs(&fa.target[((long)b * 3 + c) * S * S + pix]));
         }
         if (LOSS) {      // model.py:268-269: (recon_depth < max_depth + margin) * masks
+            const float vm = fa.vmask ? __ldcs(&fa.vmask[(long)b * S * S + pix]) : 1.f;
             l_den = (rd < fa.thresh ? 1.f : 0.f) * vm;
             l_num *= l_den;
         }
@@ -716,6 +735,17 @@ __global__ void k_light_bwd(const float* __restrict__ light, int B, const float*
 // vertex through projection / rotation to grad_depth, grad_R, grad_t.  neural_renderer does 9 float atomics per
 // covered sub-pixel into grad_faces[B,F,3,3] and leaves the gather to autograd (index_put over 6 faces per vertex).
 
+// v / S and v % S for 0 <= v < S*S, S <= 2048, without the generic integer-division sequence (~22 instructions per thread in
+// the one-thread-per-vertex kernels): float estimate (within one of the quotient) + one fix-up
+__device__ __forceinline__ void div_side(int v, int S, int* q_out, int* r_out) {
+    int q = __float2int_rz(__fmul_rz((float)v, __frcp_rz((float)S)));
+    int r = v - q * S;
+    if (r >= S) { q++; r -= S; }
+    else if (r < 0) { q--; r += S; }
+    *q_out = q; *r_out = r;
+}
+
+
 // projected (u, v, z) of every vertex of the chunk's views: proj [chunk, S*S] float4 = (u, v, z, -) in NDC or, with PIX, the
 // sub-pixel coordinates ndc_to_pix(u), ndc_to_pix(v) the face inverse is built from (what k_raster_bwd_px wants)
 template <bool PIX>
@@ -723,16 +753,19 @@ __global__ void __launch_bounds__(PIX_THREADS)
 k_project_verts(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
                 const float* __restrict__ t, int view0, float* __restrict__ proj, float* __restrict__ vgrad_zero) {
     __shared__ float sRt[12];
+    __shared__ int s_img;
     const int S = cam.S, bl = blockIdx.y, b = view0 + bl;
     if (threadIdx.x < 9) sRt[threadIdx.x] = R[b * 9 + threadIdx.x];
     else if (threadIdx.x < 12) sRt[threadIdx.x] = t[b * 3 + threadIdx.x - 9];
+    else if (threadIdx.x == 32) s_img = b / vpi;          // one division per CTA, not one per thread
     __syncthreads();
     const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
     if (v >= S * S) return;
-    const int vy = v / S, vx = v - vy * S;
+    int vy, vx;
+    div_side(v, S, &vy, &vx);
     float ray[3], q[3], ndc[3];
     pixel_ray(cam, vx, vy, ray);
-    warp_point(cam, sRt, sRt + 9, ray, depth[(long)(b / vpi) * dstride + v], q);
+    warp_point(cam, sRt, sRt + 9, ray, depth[(long)s_img * dstride + v], q);
     project_ndc(cam, q, ndc);
     if (PIX) { ndc[0] = ndc_to_pix(ndc[0], 2 * S); ndc[1] = ndc_to_pix(ndc[1], 2 * S); }
     reinterpret_cast<float4*>(proj)[(long)bl * S * S + v] = make_float4(ndc[0], ndc[1], ndc[2], 0.f);
@@ -982,9 +1015,11 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
              const float* __restrict__ t, int view0, const float* __restrict__ vgrad, float* __restrict__ grad_depth,
              long gdstride, float* __restrict__ grad_R, float* __restrict__ grad_t) {
     __shared__ float sRt[12];
+    __shared__ int s_img;
     const int S = cam.S, bl = blockIdx.y, b = view0 + bl;
     if (threadIdx.x < 9) sRt[threadIdx.x] = R[b * 9 + threadIdx.x];
     else if (threadIdx.x < 12) sRt[threadIdx.x] = t[b * 3 + threadIdx.x - 9];
+    else if (threadIdx.x == 32) s_img = b / vpi;
     __syncthreads();
     const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
     float acc[12];
@@ -994,10 +1029,11 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
         const float4 gp = __ldcs(reinterpret_cast<const float4*>(vgrad) + (long)bl * S * S + v);
         const float gu = gp.x, gv = gp.y, gz = gp.z;
         if (gu != 0.f || gv != 0.f || gz != 0.f) {
-            const int vy = v / S, vx = v - vy * S;
+            int vy, vx;
+            div_side(v, S, &vy, &vx);
             float ray[3], q[3];
             pixel_ray(cam, vx, vy, ray);
-            const float d = depth[(long)(b / vpi) * dstride + v];
+            const float d = depth[(long)s_img * dstride + v];
             warp_point(cam, sRt, sRt + 9, ray, d, q);
             const float p3[3] = {ray[0] * d, ray[1] * d, ray[2] * d - cam.rcd};
             const float zz = q[2] + 1e-9f, iz = 1.0f / zz;
@@ -1014,7 +1050,7 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
                 for (int jj = 0; jj < 3; jj++) acc[3 * jj + k] += gq[jj] * p3[k];
                 acc[9 + k] += gq[k];
             }
-            float* o = &grad_depth[(long)(b / vpi) * gdstride + v];
+            float* o = &grad_depth[(long)s_img * gdstride + v];
             if (vpi == 1 && gdstride != 0) *o += gd;   // one view per depth map: this thread is the only writer
             else atomicAdd(o, gd);
         }
@@ -1039,6 +1075,7 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
                    float* __restrict__ g_sub, float* __restrict__ grad_tex, float* __restrict__ grad_R,
                    float* __restrict__ grad_t) {
     __shared__ float sview[17];
+    __shared__ int s_img;
     const int S = cam.S, bl = blockIdx.z, b = fa.view0 + bl;
     const int j = blockIdx.x * BPX + threadIdx.x, i = blockIdx.y * BPY + threadIdx.y;
     const bool inside = j < S && i < S;
@@ -1066,13 +1103,14 @@ k_render_bwd_pixel(const Cam cam, const FusedArgs fa, const float* __restrict__ 
         if (k < 9) sview[k] = fa.R[b * 9 + k];
         else if (k < 12) sview[k] = fa.t[b * 3 + k - 9];
         else if (k < 17) sview[k] = fa.light[b * 5 + k - 12];
+        else if (k == 32) s_img = b / fa.vpi;          // one division per CTA, not one per thread
         __syncthreads();
     }
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
     if (inside) {
-        const int img = b / fa.vpi;
+        const int img = s_img;
         float ray[3], q[3], v[3], g[2];
         pixel_ray(cam, j, i, ray);
         inv_warp_point(cam, sview, sview + 9, ray, rd, q, v);
@@ -2176,6 +2214,7 @@ static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
             break;
         }
         FusedArgs fa = {R, t, light, normal_ws, albedo, recon_im, views_per_image, align_corners, (int)v0, mask_in, mask_out};
+        fa.vpi_magic = vpi_magic(views_per_image, n_views);
         if (loss) {
             fa.target = loss->target; fa.vmask = loss->view_mask; fa.thresh = loss->depth_thresh;
             fa.loss_parts = (double*)loss_ws;
