@@ -115,8 +115,22 @@ __global__ void k_zbuf_init(unsigned long long* zb, long n, unsigned long long k
     for (; i < n; i += stride) zb[i] = key;
 }
 
+// image of view b = b / views_per_image as a multiply-high by ceil(2^32 / vpi) (host: vpi_magic(); 0 = divide)
+__device__ __forceinline__ int view_image(int b, int vpi, unsigned magic) {
+    return magic ? (int)__umulhi((unsigned)b, magic) : (vpi == 1 ? b : b / vpi);
+}
+
+// host: the multiply-high constant of view_image() for a call of n_views views (0 = the kernel divides)
+inline unsigned vpi_magic(int vpi, long n_views) {
+    if (vpi < 2) return 0u;
+    const unsigned long long m = ((1ull << 32) + (unsigned long long)vpi - 1) / (unsigned long long)vpi;
+    const unsigned long long e = m * (unsigned long long)vpi - (1ull << 32);      // < vpi
+    // umulhi(n, m) == n / vpi for every n with n * e < 2^32
+    return (unsigned long long)n_views * (e + 1) < (1ull << 32) && m < (1ull << 32) ? (unsigned)m : 0u;
+}
+
 // Forward rasterisation of the grid mesh into the packed-key z-buffer, stage 1 (g2s_tile.cuh): one CTA per 16 x 16 block
-// of quads of one view, grid = (views, tiles).  4 CTAs per SM (64 registers), 37 KB of static shared memory.
+// of quads of one view, grid = (views, tile columns, tile rows).  4 CTAs per SM (64 registers), 37 KB of static shared memory.
 #ifndef G2S_TILE_MINBLOCKS
 #define G2S_TILE_MINBLOCKS 4
 #endif
@@ -124,11 +138,12 @@ template <bool FROM_VERTS, bool POW2>
 __global__ void __launch_bounds__(SPLAT_THREADS, G2S_TILE_MINBLOCKS)
 k_splat_tile(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
              const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
-             const WorkList wl, int tiles_x, int view0) {
+             const WorkList wl, unsigned magic, int view0) {
     __shared__ TileSmem2 sm;
+    // grid = (views, tile columns, tile rows): no per-thread integer division to find the tile or the image
     const int bl = blockIdx.x, b = view0 + bl, S = cam.S, is = 2 * S;
-    const int tile_y = blockIdx.y / tiles_x, tile_x = blockIdx.y % tiles_x;
-    splat_tile_body<FROM_VERTS, POW2>(sm, cam, FROM_VERTS ? nullptr : depth + (long)(b / vpi) * dstride,
+    const int tile_y = blockIdx.z, tile_x = blockIdx.y;
+    splat_tile_body<FROM_VERTS, POW2>(sm, cam, FROM_VERTS ? nullptr : depth + (long)view_image(b, vpi, magic) * dstride,
                                 FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, FROM_VERTS ? nullptr : R + (long)b * 9,
                                 FROM_VERTS ? nullptr : t + (long)b * 3, zbuf + (long)bl * is * is, wl, bl, tile_y * TILE_H,
                                 tile_x * TILE);
@@ -180,19 +195,6 @@ struct FusedArgs {
     unsigned vpi_magic;   // ceil(2^32 / vpi) when view / vpi == umulhi(view, magic) for every view of the call, else 0
 };
 
-// image of view b = b / views_per_image as a multiply-high by ceil(2^32 / vpi) (host: vpi_magic(); 0 = divide)
-__device__ __forceinline__ int view_image(int b, int vpi, unsigned magic) {
-    return magic ? (int)__umulhi((unsigned)b, magic) : b / vpi;
-}
-
-// host: the multiply-high constant of view_image() for a call of n_views views (0 = the kernel divides)
-inline unsigned vpi_magic(int vpi, long n_views) {
-    if (vpi < 2) return 0u;
-    const unsigned long long m = ((1ull << 32) + (unsigned long long)vpi - 1) / (unsigned long long)vpi;
-    const unsigned long long e = m * (unsigned long long)vpi - (1ull << 32);      // < vpi
-    // umulhi(n, m) == n / vpi for every n with n * e < 2^32
-    return (unsigned long long)n_views * (e + 1) < (1ull << 32) && m < (1ull << 32) ? (unsigned)m : 0u;
-}
 
 // pixel-kernel blocks (threads = output pixels): the z-buffer resolve streams rows (64 x 4); the two backward pixel
 // kernels gather vertices / texels around a 2-D patch and run faster on square blocks (measured, profiles/r01_notes.md)
@@ -1763,11 +1765,12 @@ inline int launch_splat(const Cam& c, const float* depth, long dstride, int vpi,
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
     const WorkList wl = ws_worklist(ws, cap, S, c.far);
     { Launch l_(K_SPLAT, st);
-      const dim3 grid(nv, tiles * tiles_y);
+      const dim3 grid(nv, tiles, tiles_y);
+      const unsigned magic = vpi_magic(vpi, (long)view0 + nv);
       if (((2 * S) & (2 * S - 1)) == 0)     // power-of-two side: sub-pixel centres are exact products
-          k_splat_tile<FROM_VERTS, true><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, tiles, view0);
+          k_splat_tile<FROM_VERTS, true><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, magic, view0);
       else
-          k_splat_tile<FROM_VERTS, false><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, tiles, view0); }
+          k_splat_tile<FROM_VERTS, false><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, magic, view0); }
     { Launch l_(K_SPLAT_BIG, st);
       k_splat_big<FROM_VERTS><<<di->sms * G2S_BIG_CTAS, BIG_THREADS, sizeof(BigSmem), st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl,
                                                                                 view0); }
