@@ -54,13 +54,13 @@ SIGNATURES = {
     "g2s_chunk_views": (_c_int, [_c_int]),
     "g2s_chunk_views_bwd": (_c_int, [_c_int]),
     "g2s_render_fused_fwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp,
-                                      _vp, _vp, _vp, _vp, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_fused_bwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
-                                      _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                      _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_fused_loss_fwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp,
-                                           _vp, _vp, _vp, _LOSSP, _vp, _vp, _vp]),
+                                           _vp, _vp, _vp, _LOSSP, _vp, _vp, _vp, _vp]),
     "g2s_render_fused_loss_bwd": (_c_int, [_vp, _CAMP, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
-                                           _vp, _LOSSP, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                           _vp, _LOSSP, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g2s_render_rgb_fwd": (_c_int, [_CAMP, _vp, _vp, _c_long, _c_int, _c_int, _c_int, ctypes.POINTER(_c_float),
                                     _c_int, _vp, _vp, _vp, _vp]),
     "g2s_render_depth_fwd": (_c_int, [_CAMP, _vp, _c_int, _vp, _vp, _vp, _vp]),

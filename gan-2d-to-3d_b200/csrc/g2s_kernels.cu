@@ -138,7 +138,7 @@ template <bool FROM_VERTS, bool POW2>
 __global__ void __launch_bounds__(SPLAT_THREADS, G2S_TILE_MINBLOCKS)
 k_splat_tile(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
              const float* __restrict__ t, const float* __restrict__ verts3d, unsigned long long* __restrict__ zbuf,
-             const WorkList wl, unsigned magic, int view0) {
+             const WorkList wl, unsigned magic, int view0, float4* __restrict__ proj_out) {
     __shared__ TileSmem2 sm;
     // grid = (views, tile columns, tile rows): no per-thread integer division to find the tile or the image
     const int bl = blockIdx.x, b = view0 + bl, S = cam.S, is = 2 * S;
@@ -146,7 +146,7 @@ k_splat_tile(const Cam cam, const float* __restrict__ depth, long dstride, int v
     splat_tile_body<FROM_VERTS, POW2>(sm, cam, FROM_VERTS ? nullptr : depth + (long)view_image(b, vpi, magic) * dstride,
                                 FROM_VERTS ? verts3d + (long)b * S * S * 3 : nullptr, FROM_VERTS ? nullptr : R + (long)b * 9,
                                 FROM_VERTS ? nullptr : t + (long)b * 3, zbuf + (long)bl * is * is, wl, bl, tile_y * TILE_H,
-                                tile_x * TILE);
+                                tile_x * TILE, proj_out ? proj_out + (long)b * S * S : nullptr);
 }
 
 // stage 2 (g2s_bigface.cuh): persistent CTAs pull the faces stage 1 deferred (long walls, degenerate quads) from the work list
@@ -1759,7 +1759,8 @@ inline WorkList ws_worklist(unsigned long long* ws, long cap, int S, float far_z
 // both stages of the forward rasteriser for `nv` views (view0 .. view0 + nv - 1) into workspace `ws` (capacity >= nv views)
 template <bool FROM_VERTS>
 inline int launch_splat(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
-                        const float* verts3d, unsigned long long* ws, long cap, int nv, int view0, cudaStream_t st) {
+                        const float* verts3d, unsigned long long* ws, long cap, int nv, int view0, cudaStream_t st,
+                        float4* proj_out = nullptr) {
     const DeviceInfo* di = device_info();
     if (!di) return G2S_ERR_LAUNCH;
     const int S = c.S, tiles = (S - 1 + TILE - 1) / TILE, tiles_y = (S - 1 + TILE_H - 1) / TILE_H;
@@ -1768,9 +1769,9 @@ inline int launch_splat(const Cam& c, const float* depth, long dstride, int vpi,
       const dim3 grid(nv, tiles, tiles_y);
       const unsigned magic = vpi_magic(vpi, (long)view0 + nv);
       if (((2 * S) & (2 * S - 1)) == 0)     // power-of-two side: sub-pixel centres are exact products
-          k_splat_tile<FROM_VERTS, true><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, magic, view0);
+          k_splat_tile<FROM_VERTS, true><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, magic, view0, proj_out);
       else
-          k_splat_tile<FROM_VERTS, false><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, magic, view0); }
+          k_splat_tile<FROM_VERTS, false><<<grid, SPLAT_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl, magic, view0, proj_out); }
     { Launch l_(K_SPLAT_BIG, st);
       k_splat_big<FROM_VERTS><<<di->sms * G2S_BIG_CTAS, BIG_THREADS, sizeof(BigSmem), st>>>(c, depth, dstride, vpi, R, t, verts3d, ws, wl,
                                                                                 view0); }
@@ -1912,10 +1913,10 @@ inline void launch_raster_project(const Cam& c, const float* depth, long dstride
 inline void launch_raster_gather(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
                                  const float* verts3d, const int* face_idx, float* raster_ws, int nv, int view0,
                                  float* grad_depth, long gdstride, float* grad_verts, float* grad_R, float* grad_t,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const float* proj_ext = nullptr) {
     const int S = c.S;
-    float* proj = raster_ws;
-    float* vgrad = proj + (size_t)nv * 4 * S * S;
+    const float* proj = proj_ext ? proj_ext : raster_ws;     // the forward's projected vertices of these views, or our own
+    float* vgrad = raster_ws + (size_t)nv * 4 * S * S;
     float* g_sub = raster_ws_gsub(raster_ws, nv, S);
     { Launch l_(K_RASTER_BWD, st);
       k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), RB_THREADS, 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
@@ -2163,7 +2164,7 @@ static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
                           const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
                           int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
                           const float* mask_in, float* mask_out, const g2s_photo_loss* loss, void* loss_ws, float* out3,
-                          void* stream) {
+                          float* proj_ws, void* stream) {
     if (!cam || !depth || !albedo || !R || !t || !light || !zbuf || !normal_ws || !recon_im || !recon_depth)
         return G2S_ERR_NULL;
     if (loss && (!loss->target || !loss_ws || !out3)) return G2S_ERR_NULL;
@@ -2212,7 +2213,8 @@ static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
         const int nv = (int)(n_views - v0 < bal ? n_views - v0 : bal);
         cudaStream_t ls = lanes[lane];
         unsigned long long* zb = (unsigned long long*)zbuf + (size_t)lane * ws_words(chunk, S);   // this lane's part
-        if (int rc = launch_splat<false>(c, depth, (long)S * S, views_per_image, R, t, nullptr, zb, chunk, nv, (int)v0, ls)) {
+        if (int rc = launch_splat<false>(c, depth, (long)S * S, views_per_image, R, t, nullptr, zb, chunk, nv, (int)v0, ls,
+                                          reinterpret_cast<float4*>(proj_ws))) {
             rc_lane = rc;      // the lanes are still joined back below
             break;
         }
@@ -2248,25 +2250,26 @@ static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
 int g2s_render_fused_fwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners, void* zbuf,
                          int ws_views, float* normal_ws, float* recon_im, float* recon_depth, int32_t* face_idx,
-                         const float* mask_in, float* mask_out, void* stream) {
+                         const float* mask_in, float* mask_out, float* proj_ws, void* stream) {
     return fused_fwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, zbuf, ws_views, normal_ws,
-                          recon_im, recon_depth, face_idx, mask_in, mask_out, nullptr, nullptr, nullptr, stream);
+                          recon_im, recon_depth, face_idx, mask_in, mask_out, nullptr, nullptr, nullptr, proj_ws, stream);
 }
 
 int g2s_render_fused_loss_fwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R,
                               const float* t, const float* light, int n_images, int views_per_image, int align_corners,
                               void* zbuf, int ws_views, float* normal_ws, float* recon_im, float* recon_depth,
-                              int32_t* face_idx, const g2s_photo_loss* loss, void* loss_ws, float* out3, void* stream) {
+                              int32_t* face_idx, const g2s_photo_loss* loss, void* loss_ws, float* out3, float* proj_ws,
+                              void* stream) {
     if (!loss) return G2S_ERR_NULL;
     return fused_fwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, zbuf, ws_views, normal_ws,
-                          recon_im, recon_depth, face_idx, nullptr, nullptr, loss, loss_ws, out3, stream);
+                          recon_im, recon_depth, face_idx, nullptr, nullptr, loss, loss_ws, out3, proj_ws, stream);
 }
 
 static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                           const float* light, int n_images, int views_per_image, int align_corners,
                           const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
                           const float* grad_recon_im, const float* grad_recon_depth, const g2s_photo_loss* loss,
-                          const float* sums3, const float* grad_loss, int ws_views, float* grad_sub_ws,
+                          const float* sums3, const float* grad_loss, const float* proj_ws, int ws_views, float* grad_sub_ws,
                           float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R,
                           float* grad_t, float* grad_light, void* stream) {
     if (!cam || !depth || !albedo || !R || !t || !light || !normal_ws || !recon_depth || !face_idx ||
@@ -2315,7 +2318,8 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
         if (two) {
             cudaEventRecord(ctx->ev_fork, st);             // after the memsets / the previous chunk's gather
             cudaStreamWaitEvent(sd, ctx->ev_fork, 0);
-            launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, sd);
+            if (proj_ws) cudaMemsetAsync(grad_sub_ws + (size_t)nv * 4 * img_f, 0, sizeof(float) * (size_t)nv * 4 * img_f, sd);
+            else launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, sd);
             cudaEventRecord(ctx->ev_join[1], sd);
         }
         { Launch l_(K_BWD_PIXEL, st);
@@ -2343,11 +2347,13 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
         if (two) {
             cudaEventRecord(ctx->ev_join[3], sd);
             cudaStreamWaitEvent(st, ctx->ev_join[1], 0);   // the projected vertices
+        } else if (proj_ws) {     // the forward's projected vertices: only the vertex-gradient scratch has to start at zero
+            cudaMemsetAsync(grad_sub_ws + (size_t)nv * 4 * img_f, 0, sizeof(float) * (size_t)nv * 4 * img_f, st);
         } else {
             launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, st);
         }
         launch_raster_gather(c, depth, (long)S * S, views_per_image, R, t, nullptr, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,
-                             (long)S * S, nullptr, grad_R, grad_t, st);
+                             (long)S * S, nullptr, grad_R, grad_t, st, proj_ws ? proj_ws + (size_t)v0 * 4 * img_f : nullptr);
         if (two) cudaStreamWaitEvent(st, ctx->ev_join[3], 0);   // the texture scratch is free for the next chunk; join
     }
     for (int i0 = 0; i0 < n_images; i0 += 32768) {
@@ -2363,12 +2369,12 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
 int g2s_render_fused_bwd(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                          const float* light, int n_images, int views_per_image, int align_corners,
                          const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
-                         const float* grad_recon_im, const float* grad_recon_depth, int ws_views, float* grad_sub_ws,
-                         float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R,
-                         float* grad_t, float* grad_light, void* stream) {
+                         const float* grad_recon_im, const float* grad_recon_depth, const float* proj_ws, int ws_views,
+                         float* grad_sub_ws, float* grad_tex_ws, float* grad_normal_ws, float* grad_depth, float* grad_albedo,
+                         float* grad_R, float* grad_t, float* grad_light, void* stream) {
     if (!grad_recon_im) return G2S_ERR_NULL;
     return fused_bwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, normal_ws, recon_depth,
-                          face_idx, grad_recon_im, grad_recon_depth, nullptr, nullptr, nullptr, ws_views, grad_sub_ws, grad_tex_ws,
+                          face_idx, grad_recon_im, grad_recon_depth, nullptr, nullptr, nullptr, proj_ws, ws_views, grad_sub_ws, grad_tex_ws,
                           grad_normal_ws, grad_depth, grad_albedo, grad_R, grad_t, grad_light, stream);
 }
 
@@ -2376,12 +2382,12 @@ int g2s_render_fused_loss_bwd(g2s_context* ctx, const g2s_camera* cam, const flo
                               const float* t, const float* light, int n_images, int views_per_image, int align_corners,
                               const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
                               const float* grad_recon_im, const float* grad_recon_depth, const g2s_photo_loss* loss,
-                              const float* sums3, const float* grad_loss, int ws_views, float* grad_sub_ws, float* grad_tex_ws,
-                              float* grad_normal_ws, float* grad_depth, float* grad_albedo, float* grad_R, float* grad_t,
-                              float* grad_light, void* stream) {
+                              const float* sums3, const float* grad_loss, const float* proj_ws, int ws_views,
+                              float* grad_sub_ws, float* grad_tex_ws, float* grad_normal_ws, float* grad_depth,
+                              float* grad_albedo, float* grad_R, float* grad_t, float* grad_light, void* stream) {
     if (!loss) return G2S_ERR_NULL;
     return fused_bwd_impl(ctx, cam, depth, albedo, R, t, light, n_images, views_per_image, align_corners, normal_ws, recon_depth,
-                          face_idx, grad_recon_im, grad_recon_depth, loss, sums3, grad_loss, ws_views, grad_sub_ws, grad_tex_ws,
+                          face_idx, grad_recon_im, grad_recon_depth, loss, sums3, grad_loss, proj_ws, ws_views, grad_sub_ws, grad_tex_ws,
                           grad_normal_ws, grad_depth, grad_albedo, grad_R, grad_t, grad_light, stream);
 }
 

@@ -81,7 +81,8 @@ __device__ __forceinline__ void face_record_px(float p00, float p01, float p10, 
 template <bool FROM_VERTS>
 __device__ __forceinline__ void tile_project2(const Cam& cam, const float* __restrict__ depth_b,
                                               const float* __restrict__ verts_b, const float* __restrict__ R_b,
-                                              const float* __restrict__ t_b, int ty0, int tx0, TileSmem2& sm) {
+                                              const float* __restrict__ t_b, int ty0, int tx0, TileSmem2& sm,
+                                              float4* __restrict__ proj_view) {
     const int S = cam.S, is = 2 * S;
     constexpr int ROUNDS = (TV * TVH + SPLAT_THREADS - 1) / SPLAT_THREADS;
     float in[ROUNDS][3];
@@ -125,8 +126,16 @@ __device__ __forceinline__ void tile_project2(const Cam& cam, const float* __res
             }
             project_ndc(cam, q, ndc);
         }
-        sm.vxy[i] = make_float4(ndc[0], ndc[1], ndc_to_pix(ndc[0], is), ndc_to_pix(ndc[1], is));
+        const float4 vx4 = make_float4(ndc[0], ndc[1], ndc_to_pix(ndc[0], is), ndc_to_pix(ndc[1], is));
+        sm.vxy[i] = vx4;
         sm.vz[i] = ndc[2];
+        // handed to the backward (k_raster_bwd_px reads sub-pixel x, y and z): every vertex by the tile that owns it (the 17th
+        // row / column of a tile belongs to its neighbour, except on the mesh's last row / column)
+        if (proj_view != nullptr && live[r]) {
+            const int ly = i / TV, lx = i % TV, vy = ty0 + ly, vx = tx0 + lx;
+            if ((ly < TILE_H || vy == S - 1) && (lx < TILE || vx == S - 1))
+                proj_view[vy * S + vx] = make_float4(vx4.z, vx4.w, ndc[2], 0.f);
+        }
     }
 }
 
@@ -425,9 +434,10 @@ template <bool FROM_VERTS, bool POW2>
 __device__ __forceinline__ void splat_tile_body(TileSmem2& sm, const Cam& cam, const float* __restrict__ depth_b,
                                                 const float* __restrict__ verts_b, const float* __restrict__ R_b,
                                                 const float* __restrict__ t_b, unsigned long long* zb_view,
-                                                const WorkList& wl, int view_in_launch, int ty0, int tx0) {
+                                                const WorkList& wl, int view_in_launch, int ty0, int tx0,
+                                                float4* __restrict__ proj_view) {
     const int tid = threadIdx.x, S = cam.S, is = 2 * S;
-    tile_project2<FROM_VERTS>(cam, depth_b, verts_b, R_b, t_b, ty0, tx0, sm);
+    tile_project2<FROM_VERTS>(cam, depth_b, verts_b, R_b, t_b, ty0, tx0, sm, proj_view);
     __syncthreads();
 #if G2S_PHASE < 2
     if (sm.vz[tid] == 1.2345e-30f) zb_view[0] = 0ull;

@@ -101,6 +101,14 @@ def _checked(renderer, code, what):
     _lib.check(code, what)
 
 
+def _proj_buffer(renderer, n_views, S, device, needs_grad):
+    """[n_views, S*S, 4] buffer in which the forward hands its projected vertices to the backward (which then skips
+    k_project_verts): 16 S^2 bytes per view held until the backward; Renderer.share_projection = False turns it off."""
+    if not needs_grad or not getattr(renderer, "share_projection", True):
+        return None
+    return torch.empty(n_views, S * S, 4, device=device, dtype=torch.float32)
+
+
 def _ws(kind, n, S, device):
     """caller-owned workspace sized by g2s_workspace_bytes"""
     return torch.empty(_lib.ws_floats(kind, n, S), device=device, dtype=torch.float32)
@@ -352,12 +360,13 @@ class RenderChainFn(torch.autograd.Function):
         fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)
         mask_in = _f32c(mask.reshape(N, S, S)) if mask is not None else None
         mask_out = torch.empty(B, 1, S, S, device=dev, dtype=torch.float32) if want_mask else None
+        proj = _proj_buffer(renderer, B, S, dev, any(ctx.needs_input_grad[:5]))
         _checked(renderer, lib.g2s_render_fused_fwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc),
                                                     _p(tc), _p(L), N, views_per_image, int(bool(align_corners)), _p(zbuf),
                                                     ws_views, _p(normal), _p(recon_im), _p(recon_depth), _p(fidx),
-                                                    _p(mask_in), _p(mask_out), _stream()),
+                                                    _p(mask_in), _p(mask_out), _p(proj), _stream()),
                  "g2s_render_fused_fwd")
-        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx)
+        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, proj)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape)
         ctx.mark_non_differentiable(fidx)
         # unused outputs reach backward as None instead of zero-filled tensors (autograd would otherwise fill a
@@ -371,7 +380,7 @@ class RenderChainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_im, g_depth_out, _g_fidx, _g_mask=None):
         lib = _lib.load()
-        d, a, Rc, tc, L, normal, recon_depth, fidx = ctx.saved_tensors
+        d, a, Rc, tc, L, normal, recon_depth, fidx, proj = ctx.saved_tensors
         renderer, vpi, align, Rshape, tshape = ctx.meta
         N, S, _ = d.shape
         B = N * vpi
@@ -391,7 +400,7 @@ class RenderChainFn(torch.autograd.Function):
         gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
         gL = torch.empty(B, 5, device=dev, dtype=torch.float32)
         _lib.check(lib.g2s_render_fused_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N, vpi, align,
-                                            _p(normal), _p(recon_depth), _p(fidx), _p(gi), _p(gd_out), ws_views, _p(ws_sub),
+                                            _p(normal), _p(recon_depth), _p(fidx), _p(gi), _p(gd_out), _p(proj), ws_views, _p(ws_sub),
                                             _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR), _p(gt), _p(gL),
                                             _stream()), "g2s_render_fused_bwd")
         gR = gR.sum_to_size(Rshape)
@@ -437,13 +446,14 @@ class RenderChainLossFn(torch.autograd.Function):
         fidx = torch.empty(B, 2 * S, 2 * S, device=dev, dtype=torch.int32)
         out3 = torch.empty(3, device=dev, dtype=torch.float32)
         la = _lib.PhotoLoss(_p(tg), _p(vm), float(depth_thresh))
+        proj = _proj_buffer(renderer, B, S, dev, any(ctx.needs_input_grad[:5]))
         _checked(renderer, lib.g2s_render_fused_loss_fwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a),
                                                          _p(Rc), _p(tc), _p(L), N, views_per_image,
                                                          int(bool(align_corners)), _p(zbuf), ws_views, _p(normal),
                                                          _p(recon_im), _p(recon_depth), _p(fidx), ctypes.byref(la),
-                                                         _p(loss_ws), _p(out3), _stream()),
+                                                         _p(loss_ws), _p(out3), _p(proj), _stream()),
                  "g2s_render_fused_loss_fwd")
-        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3)
+        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3, proj)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape, float(depth_thresh))
         ctx.mark_non_differentiable(fidx)
         ctx.set_materialize_grads(False)
@@ -452,7 +462,7 @@ class RenderChainLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_im, g_depth_out, _g_fidx, g_loss):
         lib = _lib.load()
-        d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3 = ctx.saved_tensors
+        d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3, proj = ctx.saved_tensors
         renderer, vpi, align, Rshape, tshape, thresh = ctx.meta
         N, S, _ = d.shape
         B = N * vpi
@@ -475,7 +485,7 @@ class RenderChainLossFn(torch.autograd.Function):
         la = _lib.PhotoLoss(_p(tg), _p(vm), thresh)
         _lib.check(lib.g2s_render_fused_loss_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc),
                                                  _p(tc), _p(L), N, vpi, align, _p(normal), _p(recon_depth), _p(fidx),
-                                                 _p(gi), _p(gd_out), ctypes.byref(la), _p(out3), _p(gl), ws_views,
+                                                 _p(gi), _p(gd_out), ctypes.byref(la), _p(out3), _p(gl), _p(proj), ws_views,
                                                  _p(ws_sub), _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR),
                                                  _p(gt), _p(gL), _stream()), "g2s_render_fused_loss_bwd")
         gR = gR.sum_to_size(Rshape)

@@ -33,6 +33,9 @@ class Renderer:
         self.renderer_min_depth = cfgs.get('renderer_min_depth', 0.1)
         self.renderer_max_depth = cfgs.get('renderer_max_depth', 10.)
         self.align_corners = bool(align_corners)
+        # the fused chain's forward hands its projected vertices to the backward (16 S^2 bytes per view kept until then, 1 GB for
+        # 4096 views at 128^2) so that the backward does not project the mesh again; False = recompute instead of keep
+        self.share_projection = True
         self.device = torch.device(device)
 
         fx = (self.image_size - 1) / 2 / (math.tan(self.fov / 2 * math.pi / 180))

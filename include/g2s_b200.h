@@ -150,14 +150,16 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * Outputs: recon_im [n_views,3,S,S], recon_depth [n_views,S,S], face_idx [n_views,2S,2S] (may be NULL).
  * Optional (sample_pseudo_imgs, model.py:291-328 -> render_given_view(..., mask, grid_sample=True), renderer.py:257-264):
  * mask_out [n_views,S,S] = grid_sample(mask, grid, mode='nearest') of mask_in [n_images,S,S] (NULL = all ones); pass
- * mask_out = NULL to skip. */
+ * mask_out = NULL to skip.
+ * proj_ws (may be NULL) [n_views,S,S,4] floats: the rasteriser also stores every vertex it projected (sub-pixel x, y, depth z,
+ * pad) for the backward, which then does not project the mesh again (pass the same buffer to g2s_render_fused_bwd). */
 int g2s_chunk_views(int image_size);
 int g2s_chunk_views_bwd(int image_size);   /* recommended ws_views of g2s_render_fused_bwd (~1 GB of scratch) */
 int g2s_render_fused_fwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
                          float *recon_depth, int32_t *face_idx, const float *mask_in, float *mask_out,
-                         void *stream);
+                         float *proj_ws, void *stream);
 
 /* Backward of the fused render.  Cotangents: grad_recon_im [n_views,3,S,S] (required),
  * grad_recon_depth [n_views,S,S] (may be NULL).  Workspaces: grad_sub_ws [ws_views,9,S,S] (as above),
@@ -166,13 +168,15 @@ int g2s_render_fused_fwd(g2s_context *ctx, const g2s_camera *cam, const float *d
  * Outputs, all WRITTEN: grad_depth [n_images,S,S], grad_albedo [n_images,3,S,S], grad_R [n_views,3,3],
  * grad_t [n_views,3], grad_light [n_views,5].
  * ctx (may be NULL = everything on `stream`): the bandwidth-bound kernels of a chunk run on the context's side stream under the
- * issue-bound ones, forked from / joined to `stream` with the context's events. */
+ * issue-bound ones, forked from / joined to `stream` with the context's events.
+ * proj_ws (may be NULL): the projected vertices the forward stored; NULL = re-project them here (k_project_verts). */
 int g2s_render_fused_bwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, const float *normal_ws, const float *recon_depth,
                          const int32_t *face_idx, const float *grad_recon_im, const float *grad_recon_depth,
-                         int ws_views, float *grad_sub_ws, float *grad_tex_ws, float *grad_normal_ws, float *grad_depth,
-                         float *grad_albedo, float *grad_R, float *grad_t, float *grad_light, void *stream);
+                         const float *proj_ws, int ws_views, float *grad_sub_ws, float *grad_tex_ws,
+                         float *grad_normal_ws, float *grad_depth, float *grad_albedo, float *grad_R, float *grad_t,
+                         float *grad_light, void *stream);
 
 /* ---- fused render + masked photometric loss: model.py:243-274 as one pass ----------------------------------------
  * The step-3 loss of the reference, loss_l1_im = PhotometricLoss(recon_im, projected_samples, mask = (recon_depth <
@@ -192,14 +196,15 @@ int g2s_render_fused_loss_fwd(g2s_context *ctx, const g2s_camera *cam, const flo
                               const float *R, const float *t, const float *light, int n_images, int views_per_image,
                               int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
                               float *recon_depth, int32_t *face_idx, const g2s_photo_loss *loss, void *loss_ws,
-                              float *out3, void *stream);
+                              float *out3, float *proj_ws, void *stream);
 int g2s_render_fused_loss_bwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo,
                               const float *R, const float *t, const float *light, int n_images, int views_per_image,
                               int align_corners, const float *normal_ws, const float *recon_depth,
                               const int32_t *face_idx, const float *grad_recon_im, const float *grad_recon_depth,
-                              const g2s_photo_loss *loss, const float *sums3, const float *grad_loss, int ws_views,
-                              float *grad_sub_ws, float *grad_tex_ws, float *grad_normal_ws, float *grad_depth,
-                              float *grad_albedo, float *grad_R, float *grad_t, float *grad_light, void *stream);
+                              const g2s_photo_loss *loss, const float *sums3, const float *grad_loss,
+                              const float *proj_ws, int ws_views, float *grad_sub_ws, float *grad_tex_ws,
+                              float *grad_normal_ws, float *grad_depth, float *grad_albedo, float *grad_R, float *grad_t,
+                              float *grad_light, void *stream);
 
 /* ---- mesh-texture render: nr.Renderer.render_rgb as renderer.py:196,230,248,272,275 call it ------
  * vertices3d [n_views,S*S,3] (already rotated/translated 3-D grid), im [*,C,S,S] per-vertex colours

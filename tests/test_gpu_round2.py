@@ -317,3 +317,22 @@ def test_render_chain_loss_api_and_errors():
         ren.render_chain_loss(d, case["albedo"], case["view"], case["light"], target[:, :2], views_per_image=P)
     lib = g2s_b200._lib.load()
     assert lib.g2s_workspace_bytes(g2s_b200._lib.WS_LOSS, P, S) == (P * 1 * (S // 4) + 512) * 16
+
+
+def test_projection_handoff_equals_recompute():
+    """the forward hands its projected vertices to the backward (proj_ws); the gradients equal the ones of a backward that
+    projects the mesh again (share_projection = False), bit for bit up to the order of the float atomics"""
+    import g2s_b200
+    from g2s_b200 import synthetic
+    for S, N, P in ((33, 2, 3), (128, 1, 8)):           # 33: the mesh's last row / column sits in a tile's 17th slot
+        case = {k: v.cuda() for k, v in synthetic.make_case(S, P, seed=9, n_images=N).items()}
+        grads = []
+        for share in (True, False):
+            ren = g2s_b200.Renderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH, device="cuda")
+            ren.share_projection = share
+            d = case["depth"].clone().requires_grad_(True)
+            v = case["view"].clone().requires_grad_(True)
+            im, rd, _ = ren.render_chain(d, case["albedo"], v, case["light"], views_per_image=P)
+            ((im * case["cotangent"]).sum() + rd.sum() * 1e-3).backward()
+            grads.append((d.grad.clone(), v.grad.clone()))
+        assert rel_err(grads[0][0], grads[1][0]) < 2e-6 and rel_err(grads[0][1], grads[1][1]) < 2e-6
