@@ -1012,9 +1012,12 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
 }
 
 // vertex chain: (u,v,z) NDC gradient -> 3-D point -> depth, R, t.  One thread per vertex.
+// REZERO: what was consumed is set back to zero (the scratch is then zero at rest and nobody has to clear 1 GB of it per
+// step); the store follows the test on the loaded value, so the load it could collide with has already returned.
+template <bool REZERO>
 __global__ void __launch_bounds__(PIX_THREADS)
 k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
-             const float* __restrict__ t, int view0, const float* __restrict__ vgrad, float* __restrict__ grad_depth,
+             const float* __restrict__ t, int view0, float* __restrict__ vgrad, float* __restrict__ grad_depth,
              long gdstride, float* __restrict__ grad_R, float* __restrict__ grad_t) {
     __shared__ float sRt[12];
     __shared__ int s_img;
@@ -1028,9 +1031,11 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
     if (v < S * S) {
-        const float4 gp = __ldcs(reinterpret_cast<const float4*>(vgrad) + (long)bl * S * S + v);
+        float4* gptr = reinterpret_cast<float4*>(vgrad) + (long)bl * S * S + v;
+        const float4 gp = __ldcs(gptr);
         const float gu = gp.x, gv = gp.y, gz = gp.z;
         if (gu != 0.f || gv != 0.f || gz != 0.f) {
+            if (REZERO) __stcs(gptr, make_float4(0.f, 0.f, 0.f, 0.f));
             int vy, vx;
             div_side(v, S, &vy, &vx);
             float ray[3], q[3];
@@ -1915,14 +1920,18 @@ inline void launch_raster_gather(const Cam& c, const float* depth, long dstride,
                                  float* grad_depth, long gdstride, float* grad_verts, float* grad_R, float* grad_t,
                                  cudaStream_t st, const float* proj_ext = nullptr) {
     const int S = c.S;
-    const float* proj = proj_ext ? proj_ext : raster_ws;     // the forward's projected vertices of these views, or our own
-    float* vgrad = raster_ws + (size_t)nv * 4 * S * S;
+    // with the forward's projected vertices the vertex gradients take the front of the workspace (zero at rest, k_vertex_bwd
+    // leaves it so), otherwise they follow our own projection of these nv views (zeroed by the projection kernel)
+    const float* proj = proj_ext ? proj_ext : raster_ws;
+    float* vgrad = proj_ext ? raster_ws : raster_ws + (size_t)nv * 4 * S * S;
     float* g_sub = raster_ws_gsub(raster_ws, nv, S);
     { Launch l_(K_RASTER_BWD, st);
       k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), RB_THREADS, 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
       if (verts3d) k_points_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, vgrad, grad_verts);
-      else k_vertex_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
+      else if (proj_ext) k_vertex_bwd<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad,
+                                                                                            grad_depth, gdstride, grad_R, grad_t);
+      else k_vertex_bwd<false><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
                                                                         gdstride, grad_R, grad_t); }
 }
 
@@ -2318,8 +2327,7 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
         if (two) {
             cudaEventRecord(ctx->ev_fork, st);             // after the memsets / the previous chunk's gather
             cudaStreamWaitEvent(sd, ctx->ev_fork, 0);
-            if (proj_ws) cudaMemsetAsync(grad_sub_ws + (size_t)nv * 4 * img_f, 0, sizeof(float) * (size_t)nv * 4 * img_f, sd);
-            else launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, sd);
+            if (!proj_ws) launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, sd);
             cudaEventRecord(ctx->ev_join[1], sd);
         }
         { Launch l_(K_BWD_PIXEL, st);
@@ -2347,9 +2355,7 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
         if (two) {
             cudaEventRecord(ctx->ev_join[3], sd);
             cudaStreamWaitEvent(st, ctx->ev_join[1], 0);   // the projected vertices
-        } else if (proj_ws) {     // the forward's projected vertices: only the vertex-gradient scratch has to start at zero
-            cudaMemsetAsync(grad_sub_ws + (size_t)nv * 4 * img_f, 0, sizeof(float) * (size_t)nv * 4 * img_f, st);
-        } else {
+        } else if (!proj_ws) {
             launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, st);
         }
         launch_raster_gather(c, depth, (long)S * S, views_per_image, R, t, nullptr, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,

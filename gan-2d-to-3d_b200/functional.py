@@ -94,10 +94,36 @@ class ZBuffer:
         self.buf.clear()
 
 
+class RasterScratch:
+    """The raster backward's scratch when the forward handed over its projected vertices: its vertex-gradient part must be
+    zero on entry and k_vertex_bwd leaves it zero, so it is cleared ONCE, when allocated, and kept by the Renderer (one per
+    device and stream, grown on demand, dropped after a failed launch)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, n_views, S, device):
+        stream = torch.cuda.current_stream(device)
+        key = (device, stream.cuda_stream)
+        need = _lib.ws_floats(_lib.WS_RASTER_BWD, n_views, S)
+        cur = self.buf.get(key)
+        if cur is None or cur[1] != (n_views, S):
+            if cur is not None:
+                cur[0].record_stream(stream)
+            cur = (torch.zeros(need, device=device, dtype=torch.float32), (n_views, S))
+            self.buf[key] = cur
+        return cur[0]
+
+    def invalidate(self):
+        self.buf.clear()
+
+
 def _checked(renderer, code, what):
-    """_lib.check that also drops the renderer's z-buffers on failure (a failed forward may leave stale keys behind)"""
+    """_lib.check that also drops the renderer's persistent workspaces on failure (a failed launch may leave stale keys /
+    gradients behind)"""
     if code != 0:
         renderer._zbuf.invalidate()
+        renderer._raster_scratch.invalidate()
     _lib.check(code, what)
 
 
@@ -391,7 +417,8 @@ class RenderChainFn(torch.autograd.Function):
         gi = _f32c(g_im) if g_im is not None else torch.zeros(B, 3, S, S, device=dev)
         gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
         ws_views = min(B, lib.g2s_chunk_views_bwd(S))
-        ws_sub = _ws(_lib.WS_RASTER_BWD, ws_views, S, dev)     # projected verts | vertex grads (uvz-) | g_sub
+        # projected verts | vertex grads (uvz-) | g_sub; with the forward's projection: vertex grads (zero at rest) | - | g_sub
+        ws_sub = renderer._raster_scratch.get(ws_views, S, dev) if proj is not None else _ws(_lib.WS_RASTER_BWD, ws_views, S, dev)
         ws_tex = _ws(_lib.WS_TEX_BWD, ws_views, S, dev)
         ws_nrm = _ws(_lib.WS_GRAD_NORMAL, N, S, dev)
         g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)
@@ -399,7 +426,7 @@ class RenderChainFn(torch.autograd.Function):
         gR = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
         gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
         gL = torch.empty(B, 5, device=dev, dtype=torch.float32)
-        _lib.check(lib.g2s_render_fused_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N, vpi, align,
+        _checked(renderer, lib.g2s_render_fused_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc), _p(tc), _p(L), N, vpi, align,
                                             _p(normal), _p(recon_depth), _p(fidx), _p(gi), _p(gd_out), _p(proj), ws_views, _p(ws_sub),
                                             _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR), _p(gt), _p(gL),
                                             _stream()), "g2s_render_fused_bwd")
@@ -474,7 +501,7 @@ class RenderChainLossFn(torch.autograd.Function):
         gd_out = _f32c(g_depth_out) if g_depth_out is not None else None
         gl = _f32c(g_loss).reshape(1) if g_loss is not None else torch.zeros(1, device=dev)
         ws_views = min(B, lib.g2s_chunk_views_bwd(S))
-        ws_sub = _ws(_lib.WS_RASTER_BWD, ws_views, S, dev)
+        ws_sub = renderer._raster_scratch.get(ws_views, S, dev) if proj is not None else _ws(_lib.WS_RASTER_BWD, ws_views, S, dev)
         ws_tex = _ws(_lib.WS_TEX_BWD, ws_views, S, dev)
         ws_nrm = _ws(_lib.WS_GRAD_NORMAL, N, S, dev)
         g_depth = torch.empty(N, S, S, device=dev, dtype=torch.float32)
@@ -483,7 +510,7 @@ class RenderChainLossFn(torch.autograd.Function):
         gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
         gL = torch.empty(B, 5, device=dev, dtype=torch.float32)
         la = _lib.PhotoLoss(_p(tg), _p(vm), thresh)
-        _lib.check(lib.g2s_render_fused_loss_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc),
+        _checked(renderer, lib.g2s_render_fused_loss_bwd(renderer._context(dev).handle, ctypes.byref(cam), _p(d), _p(a), _p(Rc),
                                                  _p(tc), _p(L), N, vpi, align, _p(normal), _p(recon_depth), _p(fidx),
                                                  _p(gi), _p(gd_out), ctypes.byref(la), _p(out3), _p(gl), _p(proj), ws_views,
                                                  _p(ws_sub), _p(ws_tex), _p(ws_nrm), _p(g_depth), _p(g_albedo), _p(gR),

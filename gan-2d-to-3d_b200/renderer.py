@@ -47,6 +47,7 @@ class Renderer:
         self._set_K(K.unsqueeze(0), torch.inverse(K).unsqueeze(0), origin=True)
         self.background_color = [1., 1., 1.]  # renderer.py:54
         self._zbuf = Fn.ZBuffer()
+        self._raster_scratch = Fn.RasterScratch()
         self._ctx = {}        # g2s_context per device (created on first use)
         self.rot_mat = None
         self.trans_xyz = None

@@ -169,7 +169,10 @@ int g2s_render_fused_fwd(g2s_context *ctx, const g2s_camera *cam, const float *d
  * grad_t [n_views,3], grad_light [n_views,5].
  * ctx (may be NULL = everything on `stream`): the bandwidth-bound kernels of a chunk run on the context's side stream under the
  * issue-bound ones, forked from / joined to `stream` with the context's events.
- * proj_ws (may be NULL): the projected vertices the forward stored; NULL = re-project them here (k_project_verts). */
+ * proj_ws (may be NULL): the projected vertices the forward stored; NULL = re-project them here (k_project_verts).
+ * WITH proj_ws the first ws_views * 4 * S * S floats of grad_sub_ws (the vertex-gradient scratch) must be ZERO on entry and are
+ * zero again on return (the vertex kernel clears what it consumed): clear the workspace once when it is allocated, not per
+ * call.  Without proj_ws the workspace needs no initialisation. */
 int g2s_render_fused_bwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, const float *normal_ws, const float *recon_depth,
