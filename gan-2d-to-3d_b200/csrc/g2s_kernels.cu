@@ -2001,7 +2001,7 @@ size_t g2s_workspace_bytes(int kind, int n, int image_size) {
     }
 }
 
-int g2s_version(void) { return 201; }
+int g2s_version(void) { return 202; }
 
 const char* g2s_error_string(int code) {
     switch (code) {
