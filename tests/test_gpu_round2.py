@@ -336,3 +336,35 @@ def test_projection_handoff_equals_recompute():
             ((im * case["cotangent"]).sum() + rd.sum() * 1e-3).backward()
             grads.append((d.grad.clone(), v.grad.clone()))
         assert rel_err(grads[0][0], grads[1][0]) < 2e-6 and rel_err(grads[0][1], grads[1][1]) < 2e-6
+
+
+def test_render_chain_loss_multi_chunk_two_lanes():
+    """512 views at 128^2: two forward chunks on two lanes, the two-lane backward and the projection hand-off all active;
+    the fused loss and its gradients equal the unfused CUDA composition (which is held to the oracle at smaller sizes)"""
+    import g2s_b200
+    from g2s_b200 import synthetic
+    S, N, P = 128, 32, 16
+    case = {k: v.cuda() for k, v in synthetic.make_case(S, P, seed=21, n_images=N).items()}
+    B = N * P
+    assert B > g2s_b200._lib.load().g2s_chunk_views(S)
+    gen = torch.Generator().manual_seed(3)
+    target = (torch.rand(B, 3, S, S, generator=gen) * 2 - 1).cuda()
+    masks = (torch.rand(B, 1, S, S, generator=gen) > 0.3).float().cuda()
+    ren = g2s_b200.Renderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH, device="cuda")
+    outs = []
+    for fused in (True, False):
+        d = case["depth"].clone().requires_grad_(True)
+        a = case["albedo"].clone().requires_grad_(True)
+        v = case["view"].clone().requires_grad_(True)
+        l = case["light"].clone().requires_grad_(True)
+        if fused:
+            loss, im, rd, _ = ren.render_chain_loss(d, a, v, l, target, masks, views_per_image=P)
+        else:
+            im, rd, _ = ren.render_chain(d, a, v, l, views_per_image=P)
+            loss = g2s_b200.PhotometricLoss()(im, target, mask=masks, **g2s_b200.recon_im_mask(rd.detach(), MIN_DEPTH, MAX_DEPTH))
+        loss.backward()
+        outs.append((loss.detach(), im.detach(), d.grad, a.grad, v.grad, l.grad))
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-6
+    for k in range(2, 6):
+        assert rel_err(outs[0][k], outs[1][k]) < 5e-6, k
