@@ -24,8 +24,11 @@ capture of this shape and code, profiles/r02_traffic.json, or null); `cpu_baseli
 torch-CPU + the C restatement of the external rasteriser's brute-force loop) on a bounded sample, with the bounding-box-culled
 variant (bit-identical outputs) beside it as `cpu_baseline.culled`; `single_image` = the literal configs[1] shape (1 image x
 16 views) eager and as a CUDA graph; `other_configs` = the car (64-yaw render_yaw sweep) and face (256^2 x 1024 views)
-configs of BASELINE.json on one GPU; under --gpus N > 1 `face_sharded` = the face config with its 1024 views split over the
-ranks (strong scaling, the per-image gradients all-reduced over NCCL inside the timed region).
+configs of BASELINE.json on one GPU; `loss_step` = the step with the reference's masked photometric loss (model.py:265-274)
+in place of the fixed cotangent, taken inside the render (Renderer.render_chain_loss) and as the unfused composition; under
+--gpus N > 1 `face_sharded` = the face config with its 1024 views split over the ranks (strong scaling, the per-image
+gradients all-reduced over NCCL inside the timed region).  `--ncu-step` (profiling only) brackets one step with
+cudaProfilerStart/Stop and prints no line.
 """
 import argparse
 import ctypes
