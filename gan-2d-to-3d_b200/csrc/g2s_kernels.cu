@@ -1918,13 +1918,15 @@ inline void launch_raster_project(const Cam& c, const float* depth, long dstride
 inline void launch_raster_gather(const Cam& c, const float* depth, long dstride, int vpi, const float* R, const float* t,
                                  const float* verts3d, const int* face_idx, float* raster_ws, int nv, int view0,
                                  float* grad_depth, long gdstride, float* grad_verts, float* grad_R, float* grad_t,
-                                 cudaStream_t st, const float* proj_ext = nullptr) {
+                                 cudaStream_t st, const float* proj_ext = nullptr, int layout_views = 0) {
     const int S = c.S;
     // with the forward's projected vertices the vertex gradients take the front of the workspace (zero at rest, k_vertex_bwd
     // leaves it so), otherwise they follow our own projection of these nv views (zeroed by the projection kernel)
     const float* proj = proj_ext ? proj_ext : raster_ws;
     float* vgrad = proj_ext ? raster_ws : raster_ws + (size_t)nv * 4 * S * S;
-    float* g_sub = raster_ws_gsub(raster_ws, nv, S);
+    // the masked quarter gradient sits behind 8 planes of `layout_views` views: the views of this launch, or -- with the
+    // zero-at-rest front -- the workspace's capacity, so that a short last chunk cannot write into that front
+    float* g_sub = raster_ws_gsub(raster_ws, layout_views > 0 ? layout_views : nv, S);
     { Launch l_(K_RASTER_BWD, st);
       k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), RB_THREADS, 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
@@ -2319,6 +2321,9 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
     cudaStream_t sd = two ? ctx->aux[1] : st;
     for (long v0 = 0; v0 < n_views; v0 += chunk) {
         const int nv = (int)(n_views - v0 < chunk ? n_views - v0 : chunk);
+        // workspace layout: per launch [nv x 4 | nv x 4 | nv x 1]; with the forward's projection the FRONT (vertex gradients, zero at
+        // rest) is laid out for the workspace's capacity, whatever this chunk's size
+        const int lay = proj_ws ? chunk : nv;
         FusedArgs fa = {R, t, light, normal_ws, albedo, nullptr, views_per_image, align_corners, (int)v0, nullptr, nullptr};
         if (loss) {
             fa.target = loss->target; fa.vmask = loss->view_mask; fa.thresh = loss->depth_thresh;
@@ -2331,10 +2336,11 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
             cudaEventRecord(ctx->ev_join[1], sd);
         }
         { Launch l_(K_BWD_PIXEL, st);
+          float* gsub = raster_ws_gsub(grad_sub_ws, lay, S);
           if (loss) k_render_bwd_pixel<true><<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
-                                                                         raster_ws_gsub(grad_sub_ws, nv, S), grad_tex_ws, grad_R, grad_t);
+                                                                         gsub, grad_tex_ws, grad_R, grad_t);
           else k_render_bwd_pixel<false><<<pix_grid2(S, nv, BPX, BPY), dim3(BPX, BPY), 0, st>>>(c, fa, recon_depth, grad_recon_im, grad_recon_depth,
-                                                                         raster_ws_gsub(grad_sub_ws, nv, S), grad_tex_ws, grad_R, grad_t); }
+                                                                         gsub, grad_tex_ws, grad_R, grad_t); }
         if (two) {
             cudaEventRecord(ctx->ev_join[2], st);
             cudaStreamWaitEvent(sd, ctx->ev_join[2], 0);
@@ -2359,7 +2365,7 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
             launch_raster_project(c, depth, (long)S * S, views_per_image, R, t, nullptr, grad_sub_ws, nv, (int)v0, st);
         }
         launch_raster_gather(c, depth, (long)S * S, views_per_image, R, t, nullptr, face_idx, grad_sub_ws, nv, (int)v0, grad_depth,
-                             (long)S * S, nullptr, grad_R, grad_t, st, proj_ws ? proj_ws + (size_t)v0 * 4 * img_f : nullptr);
+                             (long)S * S, nullptr, grad_R, grad_t, st, proj_ws ? proj_ws + (size_t)v0 * 4 * img_f : nullptr, lay);
         if (two) cudaStreamWaitEvent(st, ctx->ev_join[3], 0);   // the texture scratch is free for the next chunk; join
     }
     for (int i0 = 0; i0 < n_images; i0 += 32768) {

@@ -368,3 +368,31 @@ def test_render_chain_loss_multi_chunk_two_lanes():
     assert rel_err(outs[0][0], outs[1][0]) < 1e-6
     for k in range(2, 6):
         assert rel_err(outs[0][k], outs[1][k]) < 5e-6, k
+
+
+def test_projection_handoff_short_last_chunk_keeps_scratch_clean():
+    """More views than one backward chunk with a SHORT last chunk: its masked quarter gradient must not land in the
+    zero-at-rest front of the raster scratch (it did when the layout followed the chunk's own size), or the next call
+    reads stale values as vertex gradients.  Two calls in a row against the recomputing backward."""
+    import g2s_b200
+    from g2s_b200 import synthetic
+    S = 64
+    chunk = g2s_b200._lib.load().g2s_chunk_views_bwd(S)
+    P = chunk + 300
+    case = {k: v.cuda() for k, v in synthetic.make_case(S, P, seed=13, n_images=1).items()}
+    ref = None
+    for share, reps in ((False, 1), (True, 2)):
+        ren = g2s_b200.Renderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH, device="cuda")
+        ren.share_projection = share
+        for _ in range(reps):
+            d = case["depth"].clone().requires_grad_(True)
+            v = case["view"].clone().requires_grad_(True)
+            im, rd, _ = ren.render_chain(d, case["albedo"], v, case["light"], views_per_image=P)
+            (im * case["cotangent"]).sum().backward()
+            if ref is None:
+                ref = (d.grad.clone(), v.grad.clone())
+            else:
+                assert rel_err(d.grad, ref[0]) < 2e-6 and rel_err(v.grad, ref[1]) < 2e-6
+        if share:      # and the front of the kept scratch is zero at rest
+            (buf, _), = ren._raster_scratch.buf.values()
+            assert float(buf[: chunk * 4 * S * S].abs().max()) == 0.0
