@@ -925,7 +925,10 @@ struct RasterBwdSmem {
     float g[RB_THREADS / 32][32 * RB_GROUPS];
 };
 
-__global__ void __launch_bounds__(RB_THREADS)
+#ifndef G2S_RB_MINB
+#define G2S_RB_MINB 8
+#endif
+__global__ void __launch_bounds__(RB_THREADS, G2S_RB_MINB)
 k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __restrict__ g_sub,
                 const float* __restrict__ proj, float* __restrict__ vgrad, int view0) {
     __shared__ RasterBwdSmem sm;
