@@ -154,7 +154,7 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  * proj_ws (may be NULL) [n_views,S,S,4] floats: the rasteriser also stores every vertex it projected (sub-pixel x, y, depth z,
  * pad) for the backward, which then does not project the mesh again (pass the same buffer to g2s_render_fused_bwd). */
 int g2s_chunk_views(int image_size);
-int g2s_chunk_views_bwd(int image_size);   /* recommended ws_views of g2s_render_fused_bwd (~1 GB of scratch) */
+int g2s_chunk_views_bwd(int image_size);   /* recommended ws_views of g2s_render_fused_bwd (~2 GB of scratch) */
 int g2s_render_fused_fwd(g2s_context *ctx, const g2s_camera *cam, const float *depth, const float *albedo, const float *R,
                          const float *t, const float *light, int n_images, int views_per_image,
                          int align_corners, void *zbuf, int ws_views, float *normal_ws, float *recon_im,
