@@ -1887,12 +1887,12 @@ __global__ void k_selftest_face_vertices(int S, unsigned long long* mismatches) 
 
 inline dim3 pix_grid2(int S, int views, int bx = PBX, int by = PBY) { return dim3((S + bx - 1) / bx, (S + by - 1) / by, views); }
 
-// Views per forward chunk: 128 MB of z-buffer keys (256 views at 128^2, 64 at 256^2), at least 8.  Round 1 kept a chunk's keys
-// inside the 126 MB L2 (24 MB per chunk) for k_resolve; with the round-2 kernels the sweep says otherwise (profiles/r02_notes.md:
-// 48 -> 256 views per chunk at 128^2: k_splat_tile 5.57 -> 4.64 ms, k_resolve 1.80 -> 1.39, k_splat_big 2.13 -> 0.5 in the
-// per-kernel pass, 14.5 -> 14.1 ms per step): fewer, longer launches win, the keys stream through L2 either way.
+// Views per forward chunk: 256 MB of z-buffer keys (512 views at 128^2, 128 at 256^2), at least 8.  Round 1 kept a chunk's keys
+// inside the 126 MB L2 (24 MB per chunk) for k_resolve; with the round-2 kernels the sweeps say otherwise (profiles/r02_notes.md:
+// 48 -> 256 -> 512 views per chunk at 128^2: 14.5 -> 14.1 ms mid-round, 11.81 -> 11.75 ms with the final kernels): fewer, longer
+// launches win, the keys stream through L2 either way.
 inline int chunk_views_for(int S, int cap) {
-    long v = (128L << 20) / (32L * S * S);
+    long v = (256L << 20) / (32L * S * S);
     if (v < 8) v = 8;
     if (v > cap) v = cap;
     return (int)v;

@@ -139,7 +139,7 @@ int g2s_sample_bwd(const float *input, long input_batch_stride, const float *gri
  *   recon_im[b] = grid_sample(texture, grid).clamp(-1, 1)         (model.py:270)
  * light [n_views,5] = (ambient a, diffuse b, direction dx,dy,dz) as get_lighting_directions returns.
  * The views are processed in chunks that bound the z-buffer workspace; g2s_chunk_views(S) returns the recommended chunk
- * (128 MB of z-buffer keys: 256 views at 128^2, 64 at 256^2 -- the measured optimum, longer launches win).  `ws_views` = views
+ * (256 MB of z-buffer keys: 512 views at 128^2, 128 at 256^2 -- measured: longer launches win).  `ws_views` = views
  * the z-buffer workspace holds: with room for L >= 2 recommended chunks (and more views than one chunk) the chunks rotate
  * over L lanes (L <= 4; the Python host asks for 2, the measured optimum) -- one part of the workspace and one stream each:
  * `stream` and the non-blocking streams of `ctx` (NULL ctx: one lane), forked from and joined back into `stream` with events

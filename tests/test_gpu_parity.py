@@ -522,12 +522,14 @@ def test_raster_fast_path_equals_ieee_path():
     assert int(bad.item()) == 0
 
 
-@pytest.mark.parametrize("S,P,N", [(32, 4, 1), (128, 16, 8)])
+@pytest.mark.parametrize("S,P,N", [(32, 4, 1), (128, 16, 8), (64, 16, 132)])
 def test_cuda_graph_step_matches_eager(S, P, N):
-    """forward + backward captured once into a CUDA graph (small, launch-bound batches) == eager; the second case has
+    """forward + backward captured once into a CUDA graph (small, launch-bound batches) == eager; the last case has
     more views than one forward chunk, so the capture includes the two-lane fork / join (events, internal stream)"""
     import g2s_b200
     from g2s_b200 import synthetic
+    if N > 100:
+        assert N * P > g2s_b200._lib.load().g2s_chunk_views(S)
     case = synthetic.make_case(S, P, seed=81, n_images=N)
     ren = _cuda_renderer(S)
     g = g2s_b200.graphs.GraphedRenderStep(ren, N, P)

@@ -169,7 +169,9 @@ def test_workspace_sizes_and_context():
     # a NULL context is accepted: the fused forward then runs single-lane
     import g2s_b200
     from g2s_b200 import synthetic
-    case = synthetic.make_case(S, 4, seed=3, n_images=30)           # more views than one chunk: would use two lanes
+    S = 64
+    n_img = lib.g2s_chunk_views(S) // 4 + 8                          # more views than one chunk: would use two lanes
+    case = synthetic.make_case(S, 4, seed=3, n_images=n_img)
     ren = _cuda_renderer(S)
     dev = {k: v.cuda() for k, v in case.items()}
     with torch.no_grad():
@@ -339,11 +341,11 @@ def test_projection_handoff_equals_recompute():
 
 
 def test_render_chain_loss_multi_chunk_two_lanes():
-    """512 views at 128^2: two forward chunks on two lanes, the two-lane backward and the projection hand-off all active;
+    """640 views at 128^2: two forward chunks on two lanes, the two-lane backward and the projection hand-off all active;
     the fused loss and its gradients equal the unfused CUDA composition (which is held to the oracle at smaller sizes)"""
     import g2s_b200
     from g2s_b200 import synthetic
-    S, N, P = 128, 32, 16
+    S, N, P = 128, 40, 16
     case = {k: v.cuda() for k, v in synthetic.make_case(S, P, seed=21, n_images=N).items()}
     B = N * P
     assert B > g2s_b200._lib.load().g2s_chunk_views(S)
