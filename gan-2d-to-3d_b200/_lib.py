@@ -88,6 +88,7 @@ SIGNATURES = {
     "g2s_launch_count": (_c_long, []),
     "g2s_selftest_division": (_c_int, [ctypes.c_ulonglong, ctypes.c_uint, _vp, _vp]),
     "g2s_selftest_face_vertices": (_c_int, [_c_int, _vp, _vp]),
+    "g2s_selftest_index_math": (_c_int, [_c_int, _c_int, _c_long, _vp, _vp]),
     "g2s_selftest_raster": (_c_int, [ctypes.c_ulonglong, ctypes.c_uint, _c_int, _vp, _vp]),
     "g2s_profile_enable": (_c_int, [_c_int]),
     "g2s_profile_read": (_c_int, [_c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_c_float),

@@ -1864,6 +1864,20 @@ __global__ void k_selftest_raster(unsigned long long per_thread, unsigned seed, 
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// div_side (v / S, v % S through a float estimate + fix-up) for EVERY vertex index of an S x S mesh, and view_image (view / vpi as a
+// multiply-high by the host's constant) for EVERY view of a call, against plain integer division
+__global__ void k_selftest_index_math(int S, int vpi, long n_views, unsigned magic, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    const long stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long v = t0; v < (long)S * S; v += stride) {
+        int q, r;
+        div_side((int)v, S, &q, &r);
+        bad += (q != (int)(v / S)) + (r != (int)(v % S));
+    }
+    for (long b = t0; b < n_views; b += stride) bad += view_image((int)b, vpi, magic) != (int)(b / vpi);
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // face_vertices' device path (reciprocal estimate + one fix-up) against plain integer arithmetic, for EVERY face index of
 // an S x S grid mesh including the fill_back copies
 __global__ void k_selftest_face_vertices(int S, unsigned long long* mismatches) {
@@ -2601,6 +2615,15 @@ int g2s_selftest_division(unsigned long long n_pairs, unsigned seed, unsigned lo
     const int blocks = 148 * 8, threads = 256;
     const unsigned long long per = (n_pairs + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
     k_selftest_division<<<blocks, threads, 0, (cudaStream_t)stream>>>(per, seed, mismatches_dev);
+    return launch_status();
+}
+
+int g2s_selftest_index_math(int image_size, int views_per_image, long n_views, unsigned long long* mismatches_dev,
+                            void* stream) {
+    if (!mismatches_dev) return G2S_ERR_NULL;
+    if (bad_size(image_size) || views_per_image <= 0 || n_views <= 0 || n_views > (1L << 30)) return G2S_ERR_SHAPE;
+    k_selftest_index_math<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(image_size, views_per_image, n_views,
+                                                                   vpi_magic(views_per_image, n_views), mismatches_dev);
     return launch_status();
 }
 

@@ -334,6 +334,11 @@ int g2s_selftest_division(unsigned long long n_pairs, unsigned seed, unsigned lo
 /* g2s_selftest_face_vertices: the kernels' face-index -> vertex-index map (division by S-1 through a reciprocal estimate
  * and one fix-up) against plain integer arithmetic for every face of an image_size^2 grid mesh; ADDS mismatches. */
 int g2s_selftest_face_vertices(int image_size, unsigned long long *mismatches_dev, void *stream);
+/* g2s_selftest_index_math: the kernels' cheap index arithmetic -- v / S, v % S by a float estimate + fix-up for every vertex of
+ * an S x S mesh, view / views_per_image as a multiply-high for every view of a call of n_views views -- against integer
+ * division; the mismatch count is added to *mismatches_dev. */
+int g2s_selftest_index_math(int image_size, int views_per_image, long n_views, unsigned long long *mismatches_dev,
+                            void *stream);
 /* g2s_selftest_raster: compares the rasteriser's fast per-face / per-hit arithmetic (shared reciprocals, structural
  * operand-range guards) with the plain IEEE formulation bit for bit on n_triangles pseudo-random triangles (ordinary,
  * degenerate and extreme-magnitude ones, 4 sub-pixels each) and ADDS the number of mismatches to *mismatches_dev. */

@@ -398,3 +398,19 @@ def test_projection_handoff_short_last_chunk_keeps_scratch_clean():
         if share:      # and the front of the kept scratch is zero at rest
             (buf, _), = ren._raster_scratch.buf.values()
             assert float(buf[: chunk * 4 * S * S].abs().max()) == 0.0
+
+
+def test_index_math_exact():
+    """the kernels' cheap index arithmetic against integer division: v / S, v % S (float estimate + fix-up) for every vertex at
+    sizes up to the largest supported; view / views_per_image (multiply-high by ceil(2^32 / vpi), or the division when the
+    constant is not exact for the call's view count) for every view, incl. non-power-of-two and large view counts"""
+    from g2s_b200 import _lib
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for S in (2, 3, 17, 33, 128, 255, 256, 1000, 2047, 2048):
+        _lib.check(lib.g2s_selftest_index_math(S, 16, 4096, ctypes.c_void_p(bad.data_ptr()), None), "selftest_index_math")
+    for vpi, n in ((1, 1000), (2, 5000), (3, 100000), (7, 3000000), (16, 1 << 20), (1000, 4000000), (1024, 1 << 22),
+                   (12345, 1 << 24), (3, 1 << 30), (65536, 1 << 30)):
+        _lib.check(lib.g2s_selftest_index_math(128, vpi, n, ctypes.c_void_p(bad.data_ptr()), None), "selftest_index_math")
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
