@@ -414,3 +414,29 @@ def test_index_math_exact():
         _lib.check(lib.g2s_selftest_index_math(128, vpi, n, ctypes.c_void_p(bad.data_ptr()), None), "selftest_index_math")
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+def test_more_views_than_the_grid_limit_at_a_tiny_size():
+    """S = 8 with 33 000 views of one image: more views than one launch may carry (32 768: gridDim limits), forward and
+    backward; equals the same views rendered in two halves"""
+    import g2s_b200
+    from g2s_b200 import synthetic
+    S, P = 8, 33000
+    case = {k: v.cuda() for k, v in synthetic.make_case(S, P, seed=17, n_images=1).items()}
+    ren = g2s_b200.Renderer(dict(CFGS), S, MIN_DEPTH, MAX_DEPTH, device="cuda")
+
+    def run(sl):
+        d = case["depth"].clone().requires_grad_(True)
+        a = case["albedo"].clone().requires_grad_(True)
+        v = case["view"][sl].clone().requires_grad_(True)
+        n = v.shape[0]
+        im, rd, f = ren.render_chain(d, a, v, case["light"][sl], views_per_image=n)
+        (im * case["cotangent"][sl]).sum().backward()
+        return im.detach(), rd.detach(), f, d.grad, a.grad, v.grad
+
+    whole = run(slice(0, P))
+    h1, h2 = run(slice(0, P // 2)), run(slice(P // 2, P))
+    for k in range(3):
+        assert torch.equal(whole[k], torch.cat([h1[k], h2[k]], 0))
+    assert rel_err(whole[3], h1[3] + h2[3]) < 5e-6 and rel_err(whole[4], h1[4] + h2[4]) < 5e-6
+    assert rel_err(whole[5], torch.cat([h1[5], h2[5]], 0)) < 5e-6
