@@ -2294,6 +2294,20 @@ int g2s_render_fused_loss_fwd(g2s_context* ctx, const g2s_camera* cam, const flo
                           recon_im, recon_depth, face_idx, nullptr, nullptr, loss, loss_ws, out3, proj_ws, stream);
 }
 
+namespace {
+struct ZeroList { float* p[6]; size_t n[6]; };
+// zero up to six float arrays in one launch
+__global__ void __launch_bounds__(256) k_zero_list(const ZeroList zl) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        float* __restrict__ p = zl.p[k];
+        const size_t n = zl.n[k];
+        for (size_t i = t0; i < n; i += stride) p[i] = 0.f;
+    }
+}
+}
+
 static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* depth, const float* albedo, const float* R, const float* t,
                           const float* light, int n_images, int views_per_image, int align_corners,
                           const float* normal_ws, const float* recon_depth, const int32_t* face_idx,
@@ -2314,12 +2328,16 @@ static int fused_bwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
     const int S = c.S;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t img_f = (size_t)S * S;
-    cudaMemsetAsync(grad_R, 0, sizeof(float) * n_views * 9, st);
-    cudaMemsetAsync(grad_t, 0, sizeof(float) * n_views * 3, st);
-    cudaMemsetAsync(grad_light, 0, sizeof(float) * n_views * 5, st);
-    cudaMemsetAsync(grad_depth, 0, sizeof(float) * n_images * img_f, st);
-    cudaMemsetAsync(grad_albedo, 0, sizeof(float) * n_images * 3 * img_f, st);
-    cudaMemsetAsync(grad_normal_ws, 0, sizeof(float) * n_images * 3 * img_f, st);
+    {   // the six accumulators start at zero: one launch instead of six memset nodes (the single-image step is launch-bound)
+        ZeroList zl;
+        float* ptrs[6] = {grad_R, grad_t, grad_light, grad_depth, grad_albedo, grad_normal_ws};
+        const size_t cnt[6] = {(size_t)n_views * 9, (size_t)n_views * 3, (size_t)n_views * 5, (size_t)n_images * img_f,
+                               (size_t)n_images * 3 * img_f, (size_t)n_images * 3 * img_f};
+        size_t total = 0;
+        for (int k = 0; k < 6; k++) { zl.p[k] = ptrs[k]; zl.n[k] = cnt[k]; total += cnt[k]; }
+        const long blocks = (long)((total + 4 * 256 - 1) / (4 * 256));
+        k_zero_list<<<(unsigned)(blocks < 148 * 16 ? (blocks < 1 ? 1 : blocks) : 148 * 16), 256, 0, st>>>(zl);
+    }
     const int chunk = ws_views < 32768 ? ws_views : 32768;
     // the per-view texture-gradient scratch is zeroed once; k_render_bwd_tex leaves what it consumed at zero
     cudaMemsetAsync(grad_tex_ws, 0, sizeof(float) * (size_t)(n_views < chunk ? n_views : chunk) * 4 * img_f, st);
