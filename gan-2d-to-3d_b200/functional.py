@@ -376,7 +376,7 @@ class RenderChainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, depth, albedo, R, t, light, renderer, views_per_image, align_corners, mask=None,
-                want_mask=False):
+                want_mask=False, _also_save=()):
         _require_cuda(depth, albedo, R, t, light, mask)
         lib = _lib.load()
         N, S, _ = depth.shape
@@ -405,7 +405,7 @@ class RenderChainFn(torch.autograd.Function):
                                                     ws_views, _p(normal), _p(recon_im), _p(recon_depth), _p(fidx),
                                                     _p(mask_in), _p(mask_out), _p(proj), _stream()),
                  "g2s_render_fused_fwd")
-        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, proj)
+        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, proj, *_also_save)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape)
         ctx.mark_non_differentiable(fidx)
         # unused outputs reach backward as None instead of zero-filled tensors (autograd would otherwise fill a
@@ -419,7 +419,7 @@ class RenderChainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_im, g_depth_out, _g_fidx, _g_mask=None):
         lib = _lib.load()
-        d, a, Rc, tc, L, normal, recon_depth, fidx, proj = ctx.saved_tensors
+        d, a, Rc, tc, L, normal, recon_depth, fidx, proj = ctx.saved_tensors[:9]
         renderer, vpi, align, Rshape, tshape = ctx.meta
         N, S, _ = d.shape
         B = N * vpi
@@ -446,6 +446,47 @@ class RenderChainFn(torch.autograd.Function):
         gR = gR.sum_to_size(Rshape)
         gt = gt.reshape(B, *([1] * (len(tshape) - 2)), 3).sum_to_size(tshape)
         return g_depth, g_albedo, gR, gt, gL, None, None, None, None, None
+
+
+class RenderChainViewFn(torch.autograd.Function):
+    """RenderChainFn from the RAW view [B,3|5|6] (utils.py:52-73) and light [B,4] (model.py:347-353) as ONE autograd node:
+    what Renderer.render_chain runs.  The small batches of the reference (one image x 16 views per step) are host-bound, and
+    three nodes (view -> R, t; light -> directions; the chain) cost a quarter of the step more than one.  Leaves the
+    renderer's rot_mat / trans_xyz set as set_transform_matrices would (without autograd history: the gradient to `view`
+    flows through this node).  Returns (recon_im, recon_depth, face_idx)."""
+
+    @staticmethod
+    def forward(ctx, depth, albedo, view, light, renderer, views_per_image, align_corners):
+        _require_cuda(depth, albedo, view, light)
+        lib = _lib.load()
+        v, l = _f32c(view), _f32c(light)
+        B, w = v.shape
+        if w not in (3, 5, 6):
+            raise Exception("Unsupported view size. size(1) must be either 3, 5, 6.")   # utils.py:70-71
+        if tuple(l.shape) != (B, 4):
+            raise RuntimeError("light must be [B,4]")
+        R = torch.empty(B, 3, 3, device=v.device, dtype=torch.float32)
+        t = torch.empty(B, 1, 3, device=v.device, dtype=torch.float32)
+        L = torch.empty(B, 5, device=v.device, dtype=torch.float32)
+        _lib.check(lib.g2s_view_fwd(_p(v), w, B, _p(R), _p(t), _stream()), "g2s_view_fwd")
+        _lib.check(lib.g2s_light_fwd(_p(l), B, _p(L), _stream()), "g2s_light_fwd")
+        renderer.rot_mat, renderer.trans_xyz = R, t
+        # needs_input_grad[:5] of this node = depth, albedo, view, light, renderer: the same "any gradient wanted" test
+        return RenderChainFn.forward(ctx, depth, albedo, R, t, L, renderer, views_per_image, align_corners, None, False,
+                                     (v, l))
+
+    @staticmethod
+    def backward(ctx, g_im, g_depth_out, _g_fidx):
+        if g_im is None and g_depth_out is None:
+            return (None,) * 7
+        lib = _lib.load()
+        g_depth, g_albedo, gR, gt, gL = RenderChainFn.backward(ctx, g_im, g_depth_out, None)[:5]
+        v, l = ctx.saved_tensors[9:11]
+        B, w = v.shape
+        gv, gl = torch.empty_like(v), torch.empty_like(l)
+        _lib.check(lib.g2s_view_bwd(_p(v), w, B, _p(_f32c(gR)), _p(_f32c(gt)), _p(gv), _stream()), "g2s_view_bwd")
+        _lib.check(lib.g2s_light_bwd(_p(l), B, _p(gL), _p(gl), _stream()), "g2s_light_bwd")
+        return g_depth, g_albedo, gv, gl, None, None, None
 
 
 class RenderChainLossFn(torch.autograd.Function):

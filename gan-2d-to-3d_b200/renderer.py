@@ -173,10 +173,8 @@ class Renderer:
         P = views_per_image if views_per_image is not None else B // N
         if N * P != B:
             raise RuntimeError("render_chain: view must have n_images * views_per_image rows")
-        self.set_transform_matrices(view)
-        light5 = Fn.LightFn.apply(light)
-        return Fn.RenderChainFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, self, P,
-                                      self.align_corners)
+        # one autograd node from the raw view / light (sets rot_mat / trans_xyz like set_transform_matrices)
+        return Fn.RenderChainViewFn.apply(depth, albedo, view, light, self, P, self.align_corners)
 
     def render_chain_loss(self, depth, albedo, view, light, target, masks=None, depth_thresh=None, views_per_image=None):
         """render_chain with the step-3 photometric loss of model.py:265-274 taken inside the render:
