@@ -498,7 +498,8 @@ class RenderChainLossFn(torch.autograd.Function):
     are added to the loss's."""
 
     @staticmethod
-    def forward(ctx, depth, albedo, R, t, light, target, view_mask, renderer, views_per_image, align_corners, depth_thresh):
+    def forward(ctx, depth, albedo, R, t, light, target, view_mask, renderer, views_per_image, align_corners, depth_thresh,
+                _also_save=()):
         _require_cuda(depth, albedo, R, t, light, target, view_mask)
         lib = _lib.load()
         N, S, _ = depth.shape
@@ -534,7 +535,7 @@ class RenderChainLossFn(torch.autograd.Function):
                                                          _p(recon_im), _p(recon_depth), _p(fidx), ctypes.byref(la),
                                                          _p(loss_ws), _p(out3), _p(proj), _stream()),
                  "g2s_render_fused_loss_fwd")
-        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3, proj)
+        ctx.save_for_backward(d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3, proj, *_also_save)
         ctx.meta = (renderer, views_per_image, int(bool(align_corners)), R.shape, t.shape, float(depth_thresh))
         ctx.mark_non_differentiable(fidx)
         ctx.set_materialize_grads(False)
@@ -543,7 +544,7 @@ class RenderChainLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_im, g_depth_out, _g_fidx, g_loss):
         lib = _lib.load()
-        d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3, proj = ctx.saved_tensors
+        d, a, Rc, tc, L, normal, recon_depth, fidx, tg, vm, out3, proj = ctx.saved_tensors[:12]
         renderer, vpi, align, Rshape, tshape, thresh = ctx.meta
         N, S, _ = d.shape
         B = N * vpi
@@ -709,3 +710,40 @@ class Grid3dTo2dFn(torch.autograd.Function):
         _lib.check(lib.g2s_grid_3d_to_2d_bwd(ctypes.byref(cam), _p(g3), B, H, W, _p(_f32c(g_grid)), _p(out), _stream()),
                    "g2s_grid_3d_to_2d_bwd")
         return out, None
+
+
+class RenderChainLossViewFn(torch.autograd.Function):
+    """RenderChainLossFn from the raw view / light as ONE autograd node (see RenderChainViewFn): what
+    Renderer.render_chain_loss runs.  Returns (recon_im, recon_depth, face_idx, loss)."""
+
+    @staticmethod
+    def forward(ctx, depth, albedo, view, light, target, view_mask, renderer, views_per_image, align_corners, depth_thresh):
+        _require_cuda(depth, albedo, view, light, target, view_mask)
+        lib = _lib.load()
+        v, l = _f32c(view), _f32c(light)
+        B, w = v.shape
+        if w not in (3, 5, 6):
+            raise Exception("Unsupported view size. size(1) must be either 3, 5, 6.")   # utils.py:70-71
+        if tuple(l.shape) != (B, 4):
+            raise RuntimeError("light must be [B,4]")
+        R = torch.empty(B, 3, 3, device=v.device, dtype=torch.float32)
+        t = torch.empty(B, 1, 3, device=v.device, dtype=torch.float32)
+        L = torch.empty(B, 5, device=v.device, dtype=torch.float32)
+        _lib.check(lib.g2s_view_fwd(_p(v), w, B, _p(R), _p(t), _stream()), "g2s_view_fwd")
+        _lib.check(lib.g2s_light_fwd(_p(l), B, _p(L), _stream()), "g2s_light_fwd")
+        renderer.rot_mat, renderer.trans_xyz = R, t
+        return RenderChainLossFn.forward(ctx, depth, albedo, R, t, L, target, view_mask, renderer, views_per_image,
+                                         align_corners, depth_thresh, (v, l))
+
+    @staticmethod
+    def backward(ctx, g_im, g_depth_out, _g_fidx, g_loss):
+        if g_im is None and g_depth_out is None and g_loss is None:
+            return (None,) * 10
+        lib = _lib.load()
+        g_depth, g_albedo, gR, gt, gL = RenderChainLossFn.backward(ctx, g_im, g_depth_out, None, g_loss)[:5]
+        v, l = ctx.saved_tensors[12:14]
+        B, w = v.shape
+        gv, gl = torch.empty_like(v), torch.empty_like(l)
+        _lib.check(lib.g2s_view_bwd(_p(v), w, B, _p(_f32c(gR)), _p(_f32c(gt)), _p(gv), _stream()), "g2s_view_bwd")
+        _lib.check(lib.g2s_light_bwd(_p(l), B, _p(gL), _p(gl), _stream()), "g2s_light_bwd")
+        return g_depth, g_albedo, gv, gl, None, None, None, None, None, None

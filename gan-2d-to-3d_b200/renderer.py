@@ -189,10 +189,8 @@ class Renderer:
             raise RuntimeError("render_chain_loss: view must have n_images * views_per_image rows")
         if depth_thresh is None:
             depth_thresh = self.max_depth + (self.max_depth - self.min_depth) / 2
-        self.set_transform_matrices(view)
-        light5 = Fn.LightFn.apply(light)
-        im, rd, fidx, loss = Fn.RenderChainLossFn.apply(depth, albedo, self.rot_mat, self.trans_xyz, light5, target, masks, self,
-                                                        P, self.align_corners, depth_thresh)
+        im, rd, fidx, loss = Fn.RenderChainLossViewFn.apply(depth, albedo, view, light, target, masks, self, P,
+                                                            self.align_corners, depth_thresh)
         return loss, im, rd, fidx
 
     def render_pseudo_views(self, depth, albedo, view, light_a, light_b, light_d, mask=None, views_per_image=None):
