@@ -236,7 +236,7 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int W, int H, int 
 }
 
 // shaded texture of the 4 taps: tex[k][c] = (albedo/2+.5) * (a + b*max(0, n.l)) * 2 - 1.  The per-image normal map
-// and albedo are packed as 8 floats per texel (n0 n1 n2 a0 a1 a2 - -) by k_normal_fwd / k_pack_albedo, so a tap is two
+// and albedo are packed as 8 floats per texel (n0 n1 n2 a0 a1 a2 - -) by k_normal_fwd, so a tap is two
 // 16-byte loads instead of six scalar ones.
 constexpr int TEXEL = 8;
 __device__ __forceinline__ void shade_taps(const float* __restrict__ pack, const Taps& tp, const float* L,
@@ -263,16 +263,6 @@ __device__ __forceinline__ void shade_taps(const float* __restrict__ pack, const
         tex[k][1] = (hi[k].x * 0.5f + 0.5f) * sh * 2.0f - 1.0f;
         tex[k][2] = (hi[k].y * 0.5f + 0.5f) * sh * 2.0f - 1.0f;
     }
-}
-
-// albedo [N,3,S,S] -> channels 3..5 of the packed texel map [N,S,S,8]
-__global__ void __launch_bounds__(PIX_THREADS)
-k_pack_albedo(const float* __restrict__ albedo, int HW, float* __restrict__ pack) {
-    const int n = blockIdx.y, p = blockIdx.x * PIX_THREADS + threadIdx.x;
-    if (p >= HW) return;
-    const float* a = albedo + (long)n * 3 * HW;
-    float* o = pack + ((long)n * HW + p) * TEXEL;
-    o[3] = a[p]; o[4] = a[HW + p]; o[5] = a[2 * HW + p]; o[6] = 0.f; o[7] = 0.f;
 }
 
 // z-buffer resolve: face-index map, flip + 2x2 mean + clamp -> recon_depth, z-buffer reset; when FUSED
@@ -483,7 +473,8 @@ __device__ __forceinline__ void depth_point(const Cam& cam, const float* __restr
 }
 
 __global__ void __launch_bounds__(PIX_THREADS)
-k_normal_fwd(const Cam cam, const float* __restrict__ depth, int H, int W, float* __restrict__ normal, int nstride) {
+k_normal_fwd(const Cam cam, const float* __restrict__ depth, int H, int W, float* __restrict__ normal, int nstride,
+             const float* __restrict__ albedo = nullptr) {
     const int b = blockIdx.y, pix = blockIdx.x * PIX_THREADS + threadIdx.x;
     if (pix >= H * W) return;
     const int y = pix / W, x = pix - y * W;
@@ -498,6 +489,12 @@ k_normal_fwd(const Cam cam, const float* __restrict__ depth, int H, int W, float
         normal_from_points(pl, pr, pu, pd, n, &len);
     }
     float* o = normal + ((long)b * H * W + pix) * nstride;
+    if (albedo) {      // the fused chain's packed texel (nstride == TEXEL): normal xyz, albedo rgb, 2 pad -- two 16-byte stores
+        const float* a = albedo + (long)b * 3 * H * W;
+        reinterpret_cast<float4*>(o)[0] = make_float4(n[0], n[1], n[2], a[pix]);
+        reinterpret_cast<float4*>(o)[1] = make_float4(a[H * W + pix], a[2 * H * W + pix], 0.f, 0.f);
+        return;
+    }
     o[0] = n[0]; o[1] = n[1]; o[2] = n[2];
 }
 
@@ -2207,14 +2204,13 @@ static int fused_fwd_impl(g2s_context* ctx, const g2s_camera* cam, const float* 
         const int ni = n_images - i0 < 32768 ? n_images - i0 : 32768;
         Launch l_(K_NORMAL_FWD, st);
         k_normal_fwd<<<pix_grid((long)S * S, ni), PIX_THREADS, 0, st>>>(c, depth + (long)i0 * S * S, S, S,
-                                                                        normal_ws + (long)i0 * S * S * TEXEL, TEXEL);
-        k_pack_albedo<<<pix_grid((long)S * S, ni), PIX_THREADS, 0, st>>>(albedo + (long)i0 * 3 * S * S, S * S,
-                                                                         normal_ws + (long)i0 * S * S * TEXEL);
+                                                                        normal_ws + (long)i0 * S * S * TEXEL, TEXEL,
+                                                                        albedo + (long)i0 * 3 * S * S);
     }
-    // Chunked so that the z-buffer a k_splat launch writes is still in L2 when k_resolve reads it.  When the workspace
-    // holds two recommended chunks the chunks alternate between its halves on two streams (the caller's and an internal
-    // one, forked and joined with events): the next chunk's k_splat fills the SMs that the tail of the current one leaves
-    // idle (a 64-view launch lost ~8 % to its tail, profiles/r01_notes.md).  Not while per-kernel timing is on.
+    // Chunked to bound the z-buffer workspace.  When the workspace holds two recommended chunks the chunks alternate between
+    // its halves on two streams (the caller's and one of the context's, forked and joined with events): one chunk's
+    // rasteriser (issue-bound) runs beside the other's resolve (bandwidth-bound) and fills the SMs its tail leaves idle.
+    // Not while per-kernel timing is on.
     const int rec = g2s_chunk_views(S);
     int nl = (int)(ws_views / rec);                    // lanes the workspace has room for
     if (nl > MAX_LANES) nl = MAX_LANES;
