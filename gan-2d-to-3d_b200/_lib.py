@@ -71,6 +71,8 @@ SIGNATURES = {
     "g2s_view_bwd": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp]),
     "g2s_light_fwd": (_c_int, [_vp, _c_int, _vp, _vp]),
     "g2s_light_bwd": (_c_int, [_vp, _c_int, _vp, _vp, _vp]),
+    "g2s_view_light_fwd": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp]),
+    "g2s_view_light_bwd": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g2s_reduce_ws_bytes": (ctypes.c_size_t, []),
     "g2s_clamped_depth_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _c_int, _vp, _vp,
                                        _vp, _vp]),

@@ -654,9 +654,7 @@ __global__ void k_clamp_grad(const float* __restrict__ recon_depth, const float*
 // ------------------------------------------------------------------------------------------------
 // view [B, 3|5|6] -> R = Rz Ry Rx [B,3,3], t [B,3]  (utils.py:33-73) and raw light [B,4] -> (a, b, dx, dy, dz)
 // (model.py:347-353): one thread per view.  The reference spends ~40 tiny ATen launches on each.
-__global__ void k_view_fwd(const float* __restrict__ view, int vw, int B, float* __restrict__ R, float* __restrict__ t) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+__device__ __forceinline__ void view_fwd_one(const float* __restrict__ view, int vw, int B, float* __restrict__ R, float* __restrict__ t, int b) {
     const float* v = view + (long)b * vw;
     float sx, cx, sy, cy, sz, cz;
     sincosf(v[0], &sx, &cx);
@@ -671,11 +669,14 @@ __global__ void k_view_fwd(const float* __restrict__ view, int vw, int B, float*
     tt[1] = vw >= 5 ? v[4] : 0.f;
     tt[2] = vw >= 6 ? v[5] : 0.f;
 }
-
-__global__ void k_view_bwd(const float* __restrict__ view, int vw, int B, const float* __restrict__ gR,
-                           const float* __restrict__ gt, float* __restrict__ gview) {
+__global__ void k_view_fwd(const float* __restrict__ view, int vw, int B, float* __restrict__ R, float* __restrict__ t) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    view_fwd_one(view, vw, B, R, t, b);
+}
+
+__device__ __forceinline__ void view_bwd_one(const float* __restrict__ view, int vw, int B, const float* __restrict__ gR,
+                           const float* __restrict__ gt, float* __restrict__ gview, int b) {
     const float* v = view + (long)b * vw;
     float sx, cx, sy, cy, sz, cz;
     sincosf(v[0], &sx, &cx);
@@ -697,10 +698,14 @@ __global__ void k_view_bwd(const float* __restrict__ view, int vw, int B, const 
     if (vw >= 5) { o[3] = gt ? gt[(long)b * 3] : 0.f; o[4] = gt ? gt[(long)b * 3 + 1] : 0.f; }
     if (vw >= 6) o[5] = gt ? gt[(long)b * 3 + 2] : 0.f;
 }
-
-__global__ void k_light_fwd(const float* __restrict__ light, int B, float* __restrict__ light5) {
+__global__ void k_view_bwd(const float* __restrict__ view, int vw, int B, const float* __restrict__ gR,
+                           const float* __restrict__ gt, float* __restrict__ gview) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    view_bwd_one(view, vw, B, gR, gt, gview, b);
+}
+
+__device__ __forceinline__ void light_fwd_one(const float* __restrict__ light, int B, float* __restrict__ light5, int b) {
     const float* l = light + (long)b * 4;
     float* o = light5 + (long)b * 5;
     o[0] = add(dvd(l[0], 2.0f), 0.5f);
@@ -708,11 +713,14 @@ __global__ void k_light_fwd(const float* __restrict__ light, int B, float* __res
     const float n = sqrt_(add(add(mul(l[2], l[2]), mul(l[3], l[3])), 1.0f));
     o[2] = dvd(l[2], n); o[3] = dvd(l[3], n); o[4] = dvd(1.0f, n);
 }
-
-__global__ void k_light_bwd(const float* __restrict__ light, int B, const float* __restrict__ g5,
-                            float* __restrict__ glight) {
+__global__ void k_light_fwd(const float* __restrict__ light, int B, float* __restrict__ light5) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    light_fwd_one(light, B, light5, b);
+}
+
+__device__ __forceinline__ void light_bwd_one(const float* __restrict__ light, int B, const float* __restrict__ g5,
+                            float* __restrict__ glight, int b) {
     const float* l = light + (long)b * 4;
     const float* g = g5 + (long)b * 5;
     const float n = sqrtf(l[2] * l[2] + l[3] * l[3] + 1.0f), inv = 1.0f / n;
@@ -723,6 +731,30 @@ __global__ void k_light_bwd(const float* __restrict__ light, int B, const float*
     o[1] = 0.5f * g[1];
     o[2] = (g[2] - d0 * dot) * inv;
     o[3] = (g[3] - d1 * dot) * inv;
+}
+__global__ void k_light_bwd(const float* __restrict__ light, int B, const float* __restrict__ g5,
+                            float* __restrict__ glight) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    light_bwd_one(light, B, g5, glight, b);
+}
+
+// view -> (R, t) and light -> (a, b, direction) of the same views in one launch (the one-image steps are launch-bound)
+__global__ void k_view_light_fwd(const float* __restrict__ view, int vw, const float* __restrict__ light, int B,
+                                 float* __restrict__ R, float* __restrict__ t, float* __restrict__ light5) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    view_fwd_one(view, vw, B, R, t, b);
+    light_fwd_one(light, B, light5, b);
+}
+
+__global__ void k_view_light_bwd(const float* __restrict__ view, int vw, const float* __restrict__ light, int B,
+                                 const float* __restrict__ gR, const float* __restrict__ gt, const float* __restrict__ g5,
+                                 float* __restrict__ gview, float* __restrict__ glight) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    view_bwd_one(view, vw, B, gR, gt, gview, b);
+    light_bwd_one(light, B, g5, glight, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2470,6 +2502,27 @@ int g2s_light_bwd(const float* light, int B, const float* grad_light5, float* gr
     if (B <= 0) return G2S_ERR_SHAPE;
     { Launch l_(K_LIGHT, (cudaStream_t)stream);
       k_light_bwd<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(light, B, grad_light5, grad_light); }
+    return launch_status();
+}
+
+int g2s_view_light_fwd(const float* view, int view_width, const float* light, int B, float* R, float* t, float* light5,
+                       void* stream) {
+    if (!view || !light || !R || !t || !light5) return G2S_ERR_NULL;
+    if (B <= 0) return G2S_ERR_SHAPE;
+    if (view_width != 3 && view_width != 5 && view_width != 6) return G2S_ERR_UNSUPPORTED;   // utils.py:70-71
+    { Launch l_(K_VIEW, (cudaStream_t)stream);
+      k_view_light_fwd<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view, view_width, light, B, R, t, light5); }
+    return launch_status();
+}
+
+int g2s_view_light_bwd(const float* view, int view_width, const float* light, int B, const float* grad_R, const float* grad_t,
+                       const float* grad_light5, float* grad_view, float* grad_light, void* stream) {
+    if (!view || !light || !grad_light5 || !grad_view || !grad_light) return G2S_ERR_NULL;
+    if (B <= 0) return G2S_ERR_SHAPE;
+    if (view_width != 3 && view_width != 5 && view_width != 6) return G2S_ERR_UNSUPPORTED;
+    { Launch l_(K_VIEW, (cudaStream_t)stream);
+      k_view_light_bwd<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view, view_width, light, B, grad_R, grad_t, grad_light5,
+                                                                          grad_view, grad_light); }
     return launch_status();
 }
 

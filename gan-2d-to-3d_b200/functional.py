@@ -468,8 +468,7 @@ class RenderChainViewFn(torch.autograd.Function):
         R = torch.empty(B, 3, 3, device=v.device, dtype=torch.float32)
         t = torch.empty(B, 1, 3, device=v.device, dtype=torch.float32)
         L = torch.empty(B, 5, device=v.device, dtype=torch.float32)
-        _lib.check(lib.g2s_view_fwd(_p(v), w, B, _p(R), _p(t), _stream()), "g2s_view_fwd")
-        _lib.check(lib.g2s_light_fwd(_p(l), B, _p(L), _stream()), "g2s_light_fwd")
+        _lib.check(lib.g2s_view_light_fwd(_p(v), w, _p(l), B, _p(R), _p(t), _p(L), _stream()), "g2s_view_light_fwd")
         renderer.rot_mat, renderer.trans_xyz = R, t
         # needs_input_grad[:5] of this node = depth, albedo, view, light, renderer: the same "any gradient wanted" test
         return RenderChainFn.forward(ctx, depth, albedo, R, t, L, renderer, views_per_image, align_corners, None, False,
@@ -484,8 +483,8 @@ class RenderChainViewFn(torch.autograd.Function):
         v, l = ctx.saved_tensors[9:11]
         B, w = v.shape
         gv, gl = torch.empty_like(v), torch.empty_like(l)
-        _lib.check(lib.g2s_view_bwd(_p(v), w, B, _p(_f32c(gR)), _p(_f32c(gt)), _p(gv), _stream()), "g2s_view_bwd")
-        _lib.check(lib.g2s_light_bwd(_p(l), B, _p(gL), _p(gl), _stream()), "g2s_light_bwd")
+        _lib.check(lib.g2s_view_light_bwd(_p(v), w, _p(l), B, _p(_f32c(gR)), _p(_f32c(gt)), _p(gL), _p(gv), _p(gl), _stream()),
+                   "g2s_view_light_bwd")
         return g_depth, g_albedo, gv, gl, None, None, None
 
 
@@ -729,8 +728,7 @@ class RenderChainLossViewFn(torch.autograd.Function):
         R = torch.empty(B, 3, 3, device=v.device, dtype=torch.float32)
         t = torch.empty(B, 1, 3, device=v.device, dtype=torch.float32)
         L = torch.empty(B, 5, device=v.device, dtype=torch.float32)
-        _lib.check(lib.g2s_view_fwd(_p(v), w, B, _p(R), _p(t), _stream()), "g2s_view_fwd")
-        _lib.check(lib.g2s_light_fwd(_p(l), B, _p(L), _stream()), "g2s_light_fwd")
+        _lib.check(lib.g2s_view_light_fwd(_p(v), w, _p(l), B, _p(R), _p(t), _p(L), _stream()), "g2s_view_light_fwd")
         renderer.rot_mat, renderer.trans_xyz = R, t
         return RenderChainLossFn.forward(ctx, depth, albedo, R, t, L, target, view_mask, renderer, views_per_image,
                                          align_corners, depth_thresh, (v, l))
@@ -744,6 +742,6 @@ class RenderChainLossViewFn(torch.autograd.Function):
         v, l = ctx.saved_tensors[12:14]
         B, w = v.shape
         gv, gl = torch.empty_like(v), torch.empty_like(l)
-        _lib.check(lib.g2s_view_bwd(_p(v), w, B, _p(_f32c(gR)), _p(_f32c(gt)), _p(gv), _stream()), "g2s_view_bwd")
-        _lib.check(lib.g2s_light_bwd(_p(l), B, _p(gL), _p(gl), _stream()), "g2s_light_bwd")
+        _lib.check(lib.g2s_view_light_bwd(_p(v), w, _p(l), B, _p(_f32c(gR)), _p(_f32c(gt)), _p(gL), _p(gv), _p(gl), _stream()),
+                   "g2s_view_light_bwd")
         return g_depth, g_albedo, gv, gl, None, None, None, None, None, None

@@ -251,6 +251,12 @@ int g2s_view_bwd(const float *view, int view_width, int B, const float *grad_R, 
                  float *grad_view, void *stream);
 int g2s_light_fwd(const float *light, int B, float *light5, void *stream);
 int g2s_light_bwd(const float *light, int B, const float *grad_light5, float *grad_light, void *stream);
+/* both of the above for the same B views in one launch each way (what Renderer.render_chain uses: the reference's one-image
+ * steps are launch-bound).  grad_R / grad_t may be NULL (= zero). */
+int g2s_view_light_fwd(const float *view, int view_width, const float *light, int B, float *R, float *t, float *light5,
+                       void *stream);
+int g2s_view_light_bwd(const float *view, int view_width, const float *light, int B, const float *grad_R,
+                       const float *grad_t, const float *grad_light5, float *grad_view, float *grad_light, void *stream);
 
 /* ---- 3-D grid helpers used by render_yaw / render_view / render_given_view ----------------------
  * depth_to_3d_grid (renderer.py:74-80) followed by an optional inverse warp by (R0,t0)
