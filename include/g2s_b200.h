@@ -60,7 +60,8 @@ const char *g2s_error_string(int code);
 
 /* ---- caller-owned context -------------------------------------------------------------------
  * Holds what the library would otherwise keep in globals: the internal non-blocking streams and the fork / join events of
- * the multi-lane forward (g2s_render_fused_fwd), created for the device that is current at creation time, and the tuning
+ * the multi-lane forward and the two-lane backward (g2s_render_fused_fwd / _bwd), created for the device that is current at
+ * creation time, and the tuning
  * read once from the environment (G2S_FWD_LANES, G2S_NO_PIPELINE).  One context per device and per thread of use; a NULL
  * context is accepted everywhere and means "no internal streams" (single lane). */
 typedef struct g2s_context g2s_context;
@@ -73,7 +74,9 @@ void g2s_context_destroy(g2s_context *ctx);
  *                      list of the rasteriser's second stage and its counters (same as g2s_zbuffer_bytes); must be
  *                      initialised once with g2s_zbuffer_init, every forward leaves it re-initialised;
  *   G2S_WS_RASTER_BWD  backward of the rasteriser for n views: [n,9,S,S] floats (projected vertices | vertex gradients |
- *                      masked quarter gradient); 16-byte aligned;
+ *                      masked quarter gradient); 16-byte aligned; needs no initialisation UNLESS the fused backward is
+ *                      given the forward's projected vertices (proj_ws): then its first n*4*S*S floats must be zero on entry
+ *                      and are left zero (see g2s_render_fused_bwd);
  *   G2S_WS_TEX_BWD     per-view texture gradient of the fused backward: [n,S,S,4] floats;
  *   G2S_WS_TEXELS      packed texel map of the fused render for n IMAGES: [n,S,S,8] floats;
  *   G2S_WS_GRAD_NORMAL normal-map gradient of the fused backward for n IMAGES: [n,S,S,3] floats;
