@@ -1046,6 +1046,10 @@ k_raster_bwd_px(const Cam cam, const int* __restrict__ face_idx, const float* __
 // vertex chain: (u,v,z) NDC gradient -> 3-D point -> depth, R, t.  One thread per vertex.
 // REZERO: what was consumed is set back to zero (the scratch is then zero at rest and nobody has to clear 1 GB of it per
 // step); the store follows the test on the loaded value, so the load it could collide with has already returned.
+#ifndef G2S_VB_VPT
+#define G2S_VB_VPT 8
+#endif
+constexpr int VB_VPT = G2S_VB_VPT;
 template <bool REZERO>
 __global__ void __launch_bounds__(PIX_THREADS)
 k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int vpi, const float* __restrict__ R,
@@ -1058,10 +1062,15 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
     else if (threadIdx.x < 12) sRt[threadIdx.x] = t[b * 3 + threadIdx.x - 9];
     else if (threadIdx.x == 32) s_img = b / vpi;
     __syncthreads();
-    const int v = blockIdx.x * PIX_THREADS + threadIdx.x;
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) acc[k] = 0.f;
+    // VB_VPT vertices per thread: the 12-value block sum behind grad_R / grad_t (a sixth of this kernel's instructions) is paid
+    // once per VB_VPT vertices (1 / 2 / 4 / 8 / 16 per thread: 0.77 / 0.80 / 0.67 / 0.61 / 0.58 ms per 4096 views).  The same loop in
+    // k_render_bwd_pixel spills at its 40-register cap (1.78 -> 2.26 ms) and was not kept.
+#pragma unroll 1
+    for (int it = 0; it < VB_VPT; it++) {
+    const int v = (blockIdx.x * VB_VPT + it) * PIX_THREADS + threadIdx.x;
     if (v < S * S) {
         float4* gptr = reinterpret_cast<float4*>(vgrad) + (long)bl * S * S + v;
         const float4 gp = __ldcs(gptr);
@@ -1093,6 +1102,7 @@ k_vertex_bwd(const Cam cam, const float* __restrict__ depth, long dstride, int v
             if (vpi == 1 && gdstride != 0) *o += gd;   // one view per depth map: this thread is the only writer
             else atomicAdd(o, gd);
         }
+    }
     }
     if (grad_R) {
         block_accumulate_Rt<PIX_THREADS>(acc, grad_R + b * 9, grad_t + b * 3);
@@ -1977,9 +1987,9 @@ inline void launch_raster_gather(const Cam& c, const float* depth, long dstride,
       k_raster_bwd_px<<<pix_grid2(S, nv, RBX, RBY), RB_THREADS, 0, st>>>(c, face_idx, g_sub, proj, vgrad, view0); }
     { Launch l_(K_VERTEX_BWD, st);
       if (verts3d) k_points_bwd<<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, verts3d, vgrad, grad_verts);
-      else if (proj_ext) k_vertex_bwd<true><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad,
+      else if (proj_ext) k_vertex_bwd<true><<<pix_grid(((long)S * S + VB_VPT - 1) / VB_VPT, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad,
                                                                                             grad_depth, gdstride, grad_R, grad_t);
-      else k_vertex_bwd<false><<<pix_grid((long)S * S, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
+      else k_vertex_bwd<false><<<pix_grid(((long)S * S + VB_VPT - 1) / VB_VPT, nv), PIX_THREADS, 0, st>>>(c, depth, dstride, vpi, R, t, view0, vgrad, grad_depth,
                                                                         gdstride, grad_R, grad_t); }
 }
 

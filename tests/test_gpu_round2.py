@@ -298,7 +298,7 @@ def test_render_chain_loss_vs_oracle(S, N, P, use_mask, extra_cot):
     if extra_cot:
         tot2 = tot2 + (im2 * cot_im.cuda()).sum() + (rd2 * cot_d.cuda()).sum()
     tot2.backward()
-    assert rel_err(d2.grad, d.grad) < 2e-6 and rel_err(a2.grad, a.grad) < 2e-6
+    assert rel_err(d2.grad, d.grad) < TOL and rel_err(a2.grad, a.grad) < TOL      # fp32 atomics: order noise only
 
 
 def test_render_chain_loss_api_and_errors():
@@ -337,7 +337,7 @@ def test_projection_handoff_equals_recompute():
             im, rd, _ = ren.render_chain(d, case["albedo"], v, case["light"], views_per_image=P)
             ((im * case["cotangent"]).sum() + rd.sum() * 1e-3).backward()
             grads.append((d.grad.clone(), v.grad.clone()))
-        assert rel_err(grads[0][0], grads[1][0]) < 2e-6 and rel_err(grads[0][1], grads[1][1]) < 2e-6
+        assert rel_err(grads[0][0], grads[1][0]) < TOL and rel_err(grads[0][1], grads[1][1]) < TOL
 
 
 def test_render_chain_loss_multi_chunk_two_lanes():
@@ -369,7 +369,7 @@ def test_render_chain_loss_multi_chunk_two_lanes():
     assert torch.equal(outs[0][1], outs[1][1])
     assert rel_err(outs[0][0], outs[1][0]) < 1e-6
     for k in range(2, 6):
-        assert rel_err(outs[0][k], outs[1][k]) < 5e-6, k
+        assert rel_err(outs[0][k], outs[1][k]) < TOL, k
 
 
 def test_projection_handoff_short_last_chunk_keeps_scratch_clean():
@@ -394,7 +394,8 @@ def test_projection_handoff_short_last_chunk_keeps_scratch_clean():
             if ref is None:
                 ref = (d.grad.clone(), v.grad.clone())
             else:
-                assert rel_err(d.grad, ref[0]) < 2e-6 and rel_err(v.grad, ref[1]) < 2e-6
+                # (10 000 views' fp32 atomics into one image: the summation order alone is worth a few 1e-6)
+                assert rel_err(d.grad, ref[0]) < 2e-5 and rel_err(v.grad, ref[1]) < TOL
         if share:      # and the front of the kept scratch is zero at rest
             (buf, _), = ren._raster_scratch.buf.values()
             assert float(buf[: chunk * 4 * S * S].abs().max()) == 0.0
@@ -438,5 +439,7 @@ def test_more_views_than_the_grid_limit_at_a_tiny_size():
     h1, h2 = run(slice(0, P // 2)), run(slice(P // 2, P))
     for k in range(3):
         assert torch.equal(whole[k], torch.cat([h1[k], h2[k]], 0))
-    assert rel_err(whole[3], h1[3] + h2[3]) < 5e-6 and rel_err(whole[4], h1[4] + h2[4]) < 5e-6
-    assert rel_err(whole[5], torch.cat([h1[5], h2[5]], 0)) < 5e-6
+    # grad_depth / grad_albedo: 33 000 views' fp32 atomics into ONE 8 x 8 image -- the summation order alone moves the result by
+    # ~sqrt(n) ulp (5e-6 was seen); the per-view gradient has no such accumulation
+    assert rel_err(whole[3], h1[3] + h2[3]) < 1e-4 and rel_err(whole[4], h1[4] + h2[4]) < 1e-4
+    assert rel_err(whole[5], torch.cat([h1[5], h2[5]], 0)) < TOL
