@@ -31,6 +31,50 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.g2s_error_string(0) == b"ok"
 
 
+def _declared_prototypes():
+    """name -> list of parameter type strings, from the header (comments stripped)"""
+    hdr = open(os.path.join(ROOT, "include", "g2s_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|long|size_t|void|const char \*)\s*\*?\s*(g2s_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if params == ["void"] else params
+    return protos
+
+
+def test_ctypes_prototypes_match_the_header_argument_for_argument():
+    """a drifted ctypes signature (one pointer too few, an int where the header has a long) corrupts the call silently:
+    every prototype of _lib.SIGNATURES is held against the header's parameter list -- count and kind"""
+    from g2s_b200 import _lib
+    protos = _declared_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def kind(decl):
+        if "*" in decl:
+            return "ptr"
+        base = decl.split()[:-1]
+        if "long" in base or "size_t" in base:
+            return "long"
+        if "float" in base:
+            return "float"
+        return "int"
+
+    def ckind(t):
+        if t in (ctypes.c_long, ctypes.c_ulong, ctypes.c_size_t, ctypes.c_longlong, ctypes.c_ulonglong):
+            return "long"
+        if t is ctypes.c_float:
+            return "float"
+        if t in (ctypes.c_int, ctypes.c_uint, ctypes.c_int32):
+            return "int"
+        return "ptr"
+
+    for name, params in protos.items():
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(argtypes) == len(params), (name, len(argtypes), len(params))
+        for k, (decl, t) in enumerate(zip(params, argtypes)):
+            assert kind(decl) == ckind(t), (name, k, decl, t)
+
+
 def test_argument_validation_returns_error_codes_without_touching_the_gpu():
     from g2s_b200 import _lib
     lib = _lib.load()
