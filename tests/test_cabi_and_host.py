@@ -75,6 +75,35 @@ def test_ctypes_prototypes_match_the_header_argument_for_argument():
             assert kind(decl) == ckind(t), (name, k, decl, t)
 
 
+def test_ctypes_structs_match_the_header_field_for_field():
+    """struct g2s_camera / g2s_photo_loss: field names, order, array lengths and sizes as the header declares them"""
+    from g2s_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "g2s_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+
+    def fields(body):
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(.*?)(\w+)(?:\[(\d+)\])?$", decl)
+            out.append((m.group(2), "*" in m.group(1), int(m.group(3) or 1)))
+        return out
+
+    cam = fields(re.search(r"typedef struct g2s_camera \{(.*?)\} g2s_camera;", hdr, flags=re.S).group(1))
+    loss = fields(re.search(r"typedef struct \{(.*?)\} g2s_photo_loss;", hdr, flags=re.S).group(1))
+    for decl, struct in ((cam, _lib.Camera), (loss, _lib.PhotoLoss)):
+        assert [f[0] for f in decl] == [f[0] for f in struct._fields_]
+        for (name, is_ptr, n), (_, ctype) in zip(decl, struct._fields_):
+            if is_ptr:
+                assert ctype is ctypes.c_void_p, name
+            else:
+                assert ctypes.sizeof(ctype) == 4 * n, name
+    assert ctypes.sizeof(_lib.Camera) == 4 * (9 + 9 + 5 + 1 + 9)
+    assert ctypes.sizeof(_lib.PhotoLoss) == 24          # two pointers, a float, padding
+
+
 def test_argument_validation_returns_error_codes_without_touching_the_gpu():
     from g2s_b200 import _lib
     lib = _lib.load()
