@@ -197,3 +197,39 @@ def test_mesh_export_writers(tmp_path):
     assert set(kw) == {"x", "y", "z", "i", "j", "k", "vertexcolor"} and len(kw["i"]) == len(faces)
     z, col = me.surface_arrays(torch.full((1, S, S), 0.9), torch.zeros(1, 3, S, S))
     assert z.shape == (S, S) and float(z[0, 0]) == -np.float32(0.9) and col.shape == (S, S)
+
+
+def test_header_is_plain_c_and_a_c_host_links_and_runs(tmp_path):
+    """include/g2s_b200.h compiles as C99 (no C++ / torch types at the boundary) and a C program linked against the library
+    calls it -- the binding a non-Python host would use.  No device needed for these entry points."""
+    import shutil
+    import subprocess
+    from g2s_b200 import build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    build.build()
+    lib = os.path.join(ROOT, "gan-2d-to-3d_b200", "csrc", "libg2s_b200.so")
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "g2s_b200.h"
+int main(void) {
+    g2s_camera cam;
+    memset(&cam, 0, sizeof cam);
+    cam.image_size = 16;
+    if (g2s_version() < 200) return 1;
+    if (strcmp(g2s_error_string(0), "ok") != 0) return 2;
+    if (g2s_workspace_bytes(G2S_WS_TEXELS, 3, 16) != 3u * 8u * 16u * 16u * 4u) return 3;
+    if (g2s_warp_depth_fwd(&cam, NULL, 0, NULL, NULL, 1, NULL, NULL, NULL, NULL) != -1) return 4;   /* NULL -> error code */
+    if (g2s_chunk_views(128) != 512) return 5;
+    printf("c host ok %d\n", g2s_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "c host ok" in out.stdout
